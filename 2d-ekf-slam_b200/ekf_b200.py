@@ -1,0 +1,358 @@
+"""Thin ctypes binding over the C ABI (include/ekf_slam_b200.h, include/ekf_synth.h).
+
+Used by tests/, bench.py and __graft_entry__.py. It adds nothing to the arithmetic: every method
+is one C-ABI call. There is no CPU fallback: if lib/libekf_slam_b200.so is missing, or no B200
+is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(HERE, "lib")
+
+OK, ERR_CUDA, ERR_BAD_ARG, ERR_CAPACITY, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(6)
+DECISION_NONE, DECISION_NEW, DECISION_OLD, DECISION_IGNORE, DECISION_DROPPED = -1, 0, 1, 2, 3
+REGIME_AUTO, REGIME_BATCH, REGIME_LARGE = 0, 1, 2
+RECORD_HEADER = 8
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+def record_len(max_meas):
+    return RECORD_HEADER + 6 * max_meas
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+class EkfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ekf_slam_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("sigma_v", C.c_double), ("sigma_w", C.c_double), ("deg2rad_pi", C.c_double),
+                ("two_pi", C.c_double), ("cond_max", C.c_double), ("mahal_init", C.c_double),
+                ("gamma_max", C.c_int32), ("gamma_min", C.c_int32), ("regime", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class RunOutputs(C.Structure):
+    _fields_ = [("decision", c_ip), ("lm_index", c_ip), ("mahal", c_dp), ("pose_trace", c_dp),
+                ("final_pose", c_dp), ("final_nlm", c_ip)]
+
+
+class SynthConfig(C.Structure):
+    _fields_ = [("n_landmarks", C.c_int32), ("steps_per_lap", C.c_int32), ("max_meas", C.c_int32),
+                ("compass_every", C.c_int32), ("dt", C.c_double), ("radius", C.c_double),
+                ("ring_offset", C.c_double), ("sigma_v", C.c_double), ("sigma_w", C.c_double),
+                ("sigma_range", C.c_double), ("sigma_bearing", C.c_double), ("min_range", C.c_double),
+                ("max_range", C.c_double), ("fov", C.c_double), ("sigma_compass", C.c_double),
+                ("compass_R", C.c_double), ("seed", C.c_uint64)]
+
+
+_synth = None
+_core = None
+
+
+def synth_lib():
+    global _synth
+    if _synth is None:
+        L = C.CDLL(os.path.join(LIB_DIR, "libekf_synth.so"))
+        L.ekf_synth_default_config.argtypes = [C.POINTER(SynthConfig), C.c_int]
+        L.ekf_synth_record_len.argtypes = [C.POINTER(SynthConfig)]
+        L.ekf_synth_world.argtypes = [C.POINTER(SynthConfig), c_dp]
+        L.ekf_synth_true_pose.argtypes = [C.POINTER(SynthConfig), C.c_long, c_dp]
+        L.ekf_synth_generate.argtypes = [C.POINTER(SynthConfig), C.c_long, C.c_int, C.c_long, C.c_int, c_dp, c_ip,
+                                         C.c_int]
+        L.ekf_synth_measurement_from_feature.argtypes = [C.c_double, C.c_double, c_dp, c_dp]
+        _synth = L
+    return _synth
+
+
+def core_lib():
+    """The CUDA library. Raises if it has not been built (no fallback)."""
+    global _core
+    if _core is None:
+        path = os.path.join(LIB_DIR, "libekf_slam_b200.so")
+        if not os.path.exists(path):
+            raise EkfError(ERR_NO_DEVICE, "CUDA extension missing: %s (run __graft_entry__.build())" % path)
+        L = C.CDLL(path)
+        H = C.c_void_p
+        L.ekf_default_config.argtypes = [C.POINTER(Config)]
+        L.ekf_create.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.c_int, C.POINTER(Config)]
+        L.ekf_destroy.argtypes = [H]
+        L.ekf_reset.argtypes = [H]
+        L.ekf_n_filters.argtypes = [H]
+        L.ekf_max_landmarks.argtypes = [H]
+        L.ekf_regime.argtypes = [H]
+        L.ekf_set_state.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, C.c_int]
+        L.ekf_get_state.argtypes = [H, C.c_int, C.POINTER(C.c_int), c_dp, c_dp, C.c_int]
+        L.ekf_get_pose.argtypes = [H, c_dp, c_ip]
+        L.ekf_propagate.argtypes = [H, c_dp, c_dp, c_dp, C.c_int]
+        L.ekf_update.argtypes = [H, C.c_int, c_dp, c_dp, c_ip, c_ip, c_dp]
+        L.ekf_update_compass.argtypes = [H, c_dp, c_dp, C.POINTER(C.c_uint8)]
+        L.ekf_run.argtypes = [H, C.c_int, C.c_int, c_dp, C.POINTER(RunOutputs)]
+        L.ekf_upload_records.argtypes = [H, C.c_int, C.c_int, c_dp]
+        L.ekf_run_resident.argtypes = [H, C.c_int, C.c_int]
+        L.ekf_download_outputs.argtypes = [H, C.POINTER(RunOutputs)]
+        L.ekf_sync.argtypes = [H]
+        L.ekf_last_error.argtypes = [H]
+        L.ekf_last_error.restype = C.c_char_p
+        L.ekf_host_alloc.argtypes = [C.c_size_t]
+        L.ekf_host_alloc.restype = C.c_void_p
+        L.ekf_host_free.argtypes = [C.c_void_p]
+        L.ekf_timer_start.argtypes = [H]
+        L.ekf_timer_stop.argtypes = [H, C.POINTER(C.c_float)]
+        L.ekf_kernel_launches.argtypes = [H]
+        L.ekf_kernel_launches.restype = C.c_longlong
+        L.ekf_kernel_time.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.ekf_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.ekf_measure_fp64_peak.argtypes = [C.c_int, c_dp]
+        _core = L
+    return _core
+
+
+# ---- synthetic driver ---------------------------------------------------------------------------
+class Synth:
+    def __init__(self, n_landmarks, **overrides):
+        self.cfg = SynthConfig()
+        synth_lib().ekf_synth_default_config(C.byref(self.cfg), n_landmarks)
+        for k, v in overrides.items():
+            setattr(self.cfg, k, v)
+
+    @property
+    def record_len(self):
+        return record_len(self.cfg.max_meas)
+
+    def world(self):
+        xy = np.zeros((self.cfg.n_landmarks, 2))
+        synth_lib().ekf_synth_world(C.byref(self.cfg), _dp(xy))
+        return xy
+
+    def true_pose(self, t):
+        p = np.zeros(3)
+        synth_lib().ekf_synth_true_pose(C.byref(self.cfg), t, _dp(p))
+        return p
+
+    def generate(self, n_filters, n_steps, f0=0, t0=0, out=None, want_ids=False, n_threads=0):
+        L = self.record_len
+        if out is None:
+            out = np.zeros((n_filters, n_steps, L))
+        assert out.shape == (n_filters, n_steps, L) and out.dtype == np.float64 and out.flags.c_contiguous
+        ids = np.zeros((n_filters, n_steps, max(self.cfg.max_meas, 1)), np.int32) if want_ids else None
+        rc = synth_lib().ekf_synth_generate(C.byref(self.cfg), f0, n_filters, t0, n_steps, _dp(out), _ip(ids),
+                                            n_threads)
+        if rc:
+            raise ValueError("ekf_synth_generate: bad arguments")
+        return (out, ids) if want_ids else out
+
+
+def measurement_from_feature(fx_mm, fy_mm):
+    z = np.zeros(2)
+    R = np.zeros(4)
+    synth_lib().ekf_synth_measurement_from_feature(fx_mm, fy_mm, _dp(z), _dp(R))
+    return z, R
+
+
+# ---- pinned host buffers ----------------------------------------------------------------------
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (ekf_host_alloc)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = core_lib().ekf_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise EkfError(ERR_CUDA, "ekf_host_alloc(%d) failed" % self.nbytes)
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            core_lib().ekf_host_free(self.ptr)
+            self.ptr = None
+
+
+# ---- filter batch -----------------------------------------------------------------------------
+class FilterBatch:
+    """n_filters independent EKF-SLAM filters on one GPU (one ekf_handle)."""
+
+    def __init__(self, n_filters, max_landmarks, device=0, regime=REGIME_AUTO, **cfg_overrides):
+        self.L = core_lib()
+        cfg = Config()
+        self.L.ekf_default_config(C.byref(cfg))
+        cfg.regime = regime
+        for k, v in cfg_overrides.items():
+            setattr(cfg, k, v)
+        self.h = C.c_void_p()
+        rc = self.L.ekf_create(C.byref(self.h), device, n_filters, max_landmarks, C.byref(cfg))
+        if rc:
+            msg = self.L.ekf_last_error(None)
+            self.h = None
+            raise EkfError(rc, msg.decode() if msg else "")
+        self.F = n_filters
+        self.cap_lm = max_landmarks
+        self.cap_n = 3 + 2 * max_landmarks
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ekf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            msg = self.L.ekf_last_error(self.h)
+            raise EkfError(rc, msg.decode() if msg else "")
+
+    @property
+    def regime(self):
+        return self.L.ekf_regime(self.h)
+
+    def reset(self):
+        self._chk(self.L.ekf_reset(self.h))
+
+    def sync(self):
+        self._chk(self.L.ekf_sync(self.h))
+
+    def set_state(self, filt, x, P):
+        x = np.ascontiguousarray(x, np.float64)
+        n = len(x)
+        Pc = np.ascontiguousarray(np.asarray(P, np.float64).T)  # column-major
+        self._chk(self.L.ekf_set_state(self.h, filt, (n - 3) // 2, _dp(x), _dp(Pc), n))
+
+    def get_state(self, filt):
+        nl = C.c_int()
+        x = np.zeros(self.cap_n)
+        P = np.zeros((self.cap_n, self.cap_n))
+        self._chk(self.L.ekf_get_state(self.h, filt, C.byref(nl), _dp(x), _dp(P), self.cap_n))
+        n = 3 + 2 * nl.value
+        return x[:n].copy(), P[:n, :n].T.copy()
+
+    def get_pose(self):
+        p = np.zeros((self.F, 3))
+        nl = np.zeros(self.F, np.int32)
+        self._chk(self.L.ekf_get_pose(self.h, _dp(p), _ip(nl)))
+        return p, nl
+
+    def propagate(self, vel_mm_s, rotvel_deg_s, dt):
+        v = np.ascontiguousarray(np.broadcast_to(vel_mm_s, (self.F,)), np.float64)
+        w = np.ascontiguousarray(np.broadcast_to(rotvel_deg_s, (self.F,)), np.float64)
+        d = np.ascontiguousarray(np.atleast_1d(dt), np.float64)
+        stride = 0 if d.size == 1 else 1
+        assert d.size in (1, self.F)
+        self._chk(self.L.ekf_propagate(self.h, _dp(v), _dp(w), _dp(d), stride))
+
+    def update(self, z, R, want=True):
+        """z [F][n_z][2], R [F][n_z][4]. Returns (decision, lm_index, mahal) arrays [F][n_z]."""
+        z = np.ascontiguousarray(z, np.float64).reshape(self.F, -1, 2)
+        n_z = z.shape[1]
+        R = np.ascontiguousarray(R, np.float64).reshape(self.F, n_z, 4)
+        if not want:
+            self._chk(self.L.ekf_update(self.h, n_z, _dp(z), _dp(R), None, None, None))
+            return None
+        dec = np.zeros((self.F, n_z), np.int32)
+        idx = np.zeros((self.F, n_z), np.int32)
+        mah = np.zeros((self.F, n_z))
+        rc = self.L.ekf_update(self.h, n_z, _dp(z), _dp(R), _ip(dec), _ip(idx), _dp(mah))
+        if rc != ERR_CAPACITY:
+            self._chk(rc)
+        return dec, idx, mah
+
+    def update_compass(self, z, R, valid=None):
+        z = np.ascontiguousarray(np.broadcast_to(z, (self.F,)), np.float64)
+        R = np.ascontiguousarray(np.broadcast_to(R, (self.F,)), np.float64)
+        vp = None
+        if valid is not None:
+            valid = np.ascontiguousarray(valid, np.uint8)
+            vp = valid.ctypes.data_as(C.POINTER(C.c_uint8))
+        self._chk(self.L.ekf_update_compass(self.h, _dp(z), _dp(R), vp))
+
+    def _outputs(self, T, M, trace, pose_trace):
+        o = {
+            "decision": np.zeros((self.F, T, M), np.int32) if trace else None,
+            "index": np.zeros((self.F, T, M), np.int32) if trace else None,
+            "mahal": np.zeros((self.F, T, M)) if trace else None,
+            "pose_trace": np.zeros((self.F, T, 3)) if pose_trace else None,
+            "final_pose": np.zeros((self.F, 3)),
+            "final_nlm": np.zeros(self.F, np.int32),
+        }
+        ro = RunOutputs(_ip(o["decision"]), _ip(o["index"]), _dp(o["mahal"]), _dp(o["pose_trace"]),
+                        _dp(o["final_pose"]), _ip(o["final_nlm"]))
+        return o, ro
+
+    def run(self, records, max_meas, trace=True, pose_trace=False, allow_capacity=False):
+        """End-to-end fused run: H2D records, T steps per filter, D2H outputs."""
+        F, T, L = records.shape
+        assert F == self.F and L == record_len(max_meas) and records.dtype == np.float64
+        o, ro = self._outputs(T, max_meas, trace, pose_trace)
+        rc = self.L.ekf_run(self.h, T, max_meas, _dp(records), C.byref(ro))
+        if not (allow_capacity and rc == ERR_CAPACITY):
+            self._chk(rc)
+        return o
+
+    def upload_records(self, records, max_meas):
+        F, T, L = records.shape
+        assert F == self.F and L == record_len(max_meas) and records.dtype == np.float64
+        self._rec_shape = (T, max_meas)
+        self._chk(self.L.ekf_upload_records(self.h, T, max_meas, _dp(records)))
+
+    def run_resident(self, trace=False, pose_trace=False):
+        self._chk(self.L.ekf_run_resident(self.h, int(trace), int(pose_trace)))
+
+    def download_outputs(self, trace=True, pose_trace=False):
+        T, M = self._rec_shape
+        o, ro = self._outputs(T, M, trace, pose_trace)
+        self._chk(self.L.ekf_download_outputs(self.h, C.byref(ro)))
+        return o
+
+    def timer_start(self):
+        self._chk(self.L.ekf_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._chk(self.L.ekf_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def kernel_launches(self):
+        return self.L.ekf_kernel_launches(self.h)
+
+    def kernel_time(self):
+        ms = C.c_float()
+        n = C.c_int()
+        self._chk(self.L.ekf_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def device_info(device=0):
+    L = core_lib()
+    sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    smem, mem = C.c_size_t(), C.c_size_t()
+    rc = L.ekf_device_info(device, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(smem), C.byref(mem))
+    if rc:
+        raise EkfError(rc, "ekf_device_info failed (no CUDA device?)")
+    return {"sm_count": sm.value, "cc": (maj.value, mnr.value), "smem_optin": smem.value, "total_mem": mem.value}
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double()
+    rc = core_lib().ekf_measure_fp64_peak(device, C.byref(v))
+    if rc:
+        raise EkfError(rc, "ekf_measure_fp64_peak failed")
+    return v.value

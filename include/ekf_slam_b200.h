@@ -1,0 +1,160 @@
+/* ekf_slam_b200.h — C ABI of the B200-native EKF-SLAM filter core (libekf_slam_b200.so).
+ *
+ * This library replaces ONE path of kentsommer/2D-EKF-SLAM: the filter arithmetic in
+ * odometry/kalmanfilter.cpp, odometry/Propagate.cpp and odometry/Update.cpp. Every entry point
+ * cites the reference interface it stands in for. The host-side C++ class `KalmanFilter`
+ * (2d-ekf-slam_b200/host/kalmanfilter.h) keeps the reference's call surface
+ * (odometry/kalmanfilter.h:24-32) on top of these functions, so slam.cpp:130-182 can drive it
+ * unchanged; INTEGRATION.md shows the binding.
+ *
+ * All arithmetic is IEEE FP64 on the GPU (hand-written sm_100a kernels, no tensor cores, no CPU
+ * fallback: every call fails with EKF_ERR_NO_DEVICE / EKF_ERR_CUDA when no B200 is usable).
+ *
+ * Conventions
+ *   - state x: [X, Y, Phi, L1x, L1y, L2x, L2y, ...], n = 3 + 2*n_landmarks (Update.cpp:106);
+ *   - covariance P: column-major, leading dimension `ld` >= n, bit-symmetric at call boundaries
+ *     (the reference symmetrises after every operation: Propagate.cpp:66-67, Update.cpp:193-194,
+ *     kalmanfilter.cpp:123-124);
+ *   - 2x2 matrices (R) are column-major: {R00, R10, R01, R11} (Eigen's data() order);
+ *   - a handle owns `n_filters` independent filters on one device; batched arrays are indexed
+ *     [filter] first; host pointers unless stated otherwise;
+ *   - calls are stream-ordered on the handle's stream and return after enqueueing unless they
+ *     have host outputs; ekf_sync() waits and reports sticky device-side errors;
+ *   - not thread-safe per handle; distinct handles (e.g. one per GPU) may be used concurrently.
+ */
+#ifndef EKF_SLAM_B200_H
+#define EKF_SLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define EKF_OK 0
+#define EKF_ERR_CUDA 1          /* a CUDA runtime call failed; see ekf_last_error()            */
+#define EKF_ERR_BAD_ARG 2
+#define EKF_ERR_CAPACITY 3      /* a "New" association arrived with the map full; it was dropped */
+#define EKF_ERR_NO_DEVICE 4     /* no CUDA device / not sm_100                                  */
+#define EKF_ERR_UNSUPPORTED 5
+
+/* ---- data-association decision codes (Update.cpp:152,181,191) ------------------------------ */
+#define EKF_DECISION_NONE (-1)  /* no measurement in this slot                                  */
+#define EKF_DECISION_NEW 0      /* Opt_i==0 || Mahal > Gamma_max : state augmented              */
+#define EKF_DECISION_OLD 1      /* Mahal < Gamma_min : gain + state + covariance update         */
+#define EKF_DECISION_IGNORE 2   /* Gamma_min <= Mahal <= Gamma_max                              */
+#define EKF_DECISION_DROPPED 3  /* would be New but the map is at capacity (EKF_ERR_CAPACITY)   */
+
+/* ---- regimes ----------------------------------------------------------------------------- */
+#define EKF_REGIME_AUTO 0
+#define EKF_REGIME_BATCH 1      /* one CTA per filter; covariance resident in shared memory     */
+#define EKF_REGIME_LARGE 2      /* whole grid per filter; covariance streamed from HBM          */
+
+typedef struct ekf_handle_s* ekf_handle;
+
+/* Every tuning constant of the reference is a literal; they become defaulted fields here
+ * (defaults are the reference literals, bit for bit). */
+typedef struct ekf_config {
+  double sigma_v;        /* 0.01          kalmanfilter.cpp:28  */
+  double sigma_w;        /* 0.04          kalmanfilter.cpp:29  */
+  double deg2rad_pi;     /* 3.141592654   kalmanfilter.cpp:19  */
+  double two_pi;         /* 6.283185307   kalmanfilter.cpp:99  */
+  double cond_max;       /* 80            Update.cpp:131       */
+  double mahal_init;     /* 999999999999  kalmanfilter.h:17    */
+  int32_t gamma_max;     /* 50            kalmanfilter.cpp:67  */
+  int32_t gamma_min;     /* 10            kalmanfilter.cpp:68  */
+  int32_t regime;        /* EKF_REGIME_*                        */
+  int32_t reserved;
+} ekf_config;
+
+void ekf_default_config(ekf_config* cfg);
+
+/* ---- step records (input of the fused multi-step path) -------------------------------------
+ * One record drives one iteration of slam.cpp:130-182 for one filter:
+ *   doPropagation(dt) with the robot reporting getVel()=vel_mm_s, getRotVel()=rotvel_deg_s
+ *   (kalmanfilter.cpp:17-20), then doUpdateCompass(compass_z, compass_R) if has_compass
+ *   (slam.cpp:144-147), then one doUpdate per measurement, in order (slam.cpp:150-171).
+ * Layout, in doubles:  [0] vel_mm_s [1] rotvel_deg_s [2] dt [3] compass_z [4] compass_R
+ *                      [5] n_z (0..max_meas) [6] has_compass (0/1) [7] reserved (0)
+ *                      then max_meas x { z0, z1, R00, R10, R01, R11 }
+ * Records are stored [filter][step][EKF_RECORD_LEN(max_meas)]. */
+#define EKF_RECORD_HEADER 8
+#define EKF_RECORD_LEN(max_meas) (EKF_RECORD_HEADER + 6 * (max_meas))
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Replaces KalmanFilter::KalmanFilter (kalmanfilter.cpp:4-12) for n_filters filters at once:
+ * x = 0 (3), P = 0 (3x3), no landmarks. max_landmarks is the per-filter capacity N_cap. */
+int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, const ekf_config* cfg);
+int ekf_destroy(ekf_handle h);
+int ekf_reset(ekf_handle h);                       /* back to kalmanfilter.cpp:7-11 */
+int ekf_n_filters(ekf_handle h);
+int ekf_max_landmarks(ekf_handle h);
+int ekf_regime(ekf_handle h);                      /* the regime actually selected */
+
+/* ---- state access (also checkpoint / state injection) -------------------------------------- */
+/* The reference keeps state/covariance private (kalmanfilter.h:37-38); these are the harness
+ * hooks SURVEY.md 8b asks for. P must be bit-symmetric (EKF_ERR_BAD_ARG otherwise). */
+int ekf_set_state(ekf_handle h, int filter, int n_landmarks, const double* x, const double* P, int ld);
+int ekf_get_state(ekf_handle h, int filter, int* n_landmarks, double* x, double* P, int ld);
+/* Public mirrors X, Y, Phi, Num_Landmarks (kalmanfilter.h:24-27) for every filter:
+ * xyphi[n_filters][3], n_landmarks[n_filters] (either may be NULL). Synchronises. */
+int ekf_get_pose(ekf_handle h, double* xyphi, int32_t* n_landmarks);
+
+/* ---- per-call surface (one launch per reference call, P goes through HBM) -------------------- */
+/* KalmanFilter::doPropagation (kalmanfilter.cpp:15-62 -> Propagate.cpp:15-75), minus the two
+ * ofstream side effects. Arrays of n_filters; dt may be a single value when dt_stride == 0. */
+int ekf_propagate(ekf_handle h, const double* vel_mm_s, const double* rotvel_deg_s, const double* dt,
+                  int dt_stride);
+/* KalmanFilter::doUpdate (kalmanfilter.cpp:64-90 -> Update.cpp:22-204) with n_z measurements per
+ * filter, processed sequentially as Update.cpp:80-195 does. z[n_filters][n_z][2],
+ * R[n_filters][n_z][4]. Optional outputs [n_filters][n_z] (NULL to skip; non-NULL synchronises):
+ * decision (EKF_DECISION_*), lm_index (state index Opt_i of the associated landmark, or of the
+ * new landmark for New), mahal (Mahal_dist after the gating loop). */
+int ekf_update(ekf_handle h, int n_z, const double* z, const double* R, int32_t* decision, int32_t* lm_index,
+               double* mahal);
+/* KalmanFilter::doUpdateCompass (kalmanfilter.cpp:96-130). z[n_filters], R[n_filters];
+ * valid[n_filters] may be NULL (= all valid). */
+int ekf_update_compass(ekf_handle h, const double* z, const double* R, const uint8_t* valid);
+
+/* ---- fused multi-step path (covariance stays on chip for all steps) --------------------------- */
+typedef struct ekf_run_outputs {
+  int32_t* decision;    /* [F][T][M] or NULL */
+  int32_t* lm_index;    /* [F][T][M] or NULL */
+  double* mahal;        /* [F][T][M] or NULL */
+  double* pose_trace;   /* [F][T][3] or NULL : X,Y,Phi after each step (slam.cpp:181)  */
+  double* final_pose;   /* [F][3]    or NULL */
+  int32_t* final_nlm;   /* [F]       or NULL */
+} ekf_run_outputs;
+
+/* End-to-end: copies `records` (host; pinned memory from ekf_host_alloc makes the copy async)
+ * to the device, runs n_steps iterations of the slam.cpp loop for every filter, copies the
+ * requested outputs back and synchronises. */
+int ekf_run(ekf_handle h, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out);
+/* Same, split so inputs can stay resident in HBM: upload once, run many times. */
+int ekf_upload_records(ekf_handle h, int n_steps, int max_meas, const double* records);
+int ekf_run_resident(ekf_handle h, int want_trace, int want_pose_trace);   /* enqueue only */
+int ekf_download_outputs(ekf_handle h, const ekf_run_outputs* out);      /* synchronises */
+
+/* ---- plumbing -------------------------------------------------------------------------------- */
+int ekf_sync(ekf_handle h);                         /* waits; returns sticky EKF_ERR_CAPACITY etc. */
+const char* ekf_last_error(ekf_handle h);           /* h may be NULL: last create() failure        */
+void* ekf_host_alloc(size_t bytes);                 /* pinned host memory (cudaMallocHost)         */
+void ekf_host_free(void* p);
+int ekf_timer_start(ekf_handle h);                  /* cudaEventRecord on the handle's stream      */
+int ekf_timer_stop(ekf_handle h, float* ms);        /* records, synchronises, elapsed milliseconds */
+long long ekf_kernel_launches(ekf_handle h);        /* kernels this handle has launched so far     */
+/* Average device time of the dominant kernel since the last call (ms) and how many launches that
+ * covers; measured with CUDA events around each launch on the handle's stream. */
+int ekf_kernel_time(ekf_handle h, float* avg_ms, int* n_launches);
+int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin,
+                    size_t* total_mem);
+/* DFMA-chain microbenchmark on `device`: achieved FP64 FLOP/s (2 flop per DFMA). Used as the
+ * measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+int ekf_measure_fp64_peak(int device, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKF_SLAM_B200_H */
