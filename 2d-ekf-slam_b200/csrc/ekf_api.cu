@@ -1,0 +1,554 @@
+// ekf_api.cu — the C ABI of include/ekf_slam_b200.h: handle lifetime, device memory, staging of
+// host buffers, stream-ordered launches of the regime A / regime B kernels. No arithmetic of the
+// filter happens on the host, and nothing here falls back to a CPU path: without a usable sm_100
+// device every entry point reports EKF_ERR_NO_DEVICE / EKF_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ekf_internal.h"
+#include "ekf_slam_b200.h"
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;   // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+constexpr int kTimingPairs = 64;
+
+}  // namespace
+
+struct ekf_handle_s {
+  int device = 0;
+  int regime = EKF_REGIME_BATCH;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  EkfConst k{};
+  ekf_config cfg{};
+  EkfState st{};
+  int grid_cap = 0;           // regime A: co-resident CTAs
+  EkfLargeWork wk{};          // regime B scratch
+  // staging
+  DevBuf<double> in;          // per-call inputs
+  DevBuf<int> o_dec, o_idx;
+  DevBuf<double> o_mah;
+  DevBuf<uint8_t> in_valid;
+  // fused path
+  DevBuf<double> records;
+  DevBuf<int> t_dec, t_idx;
+  DevBuf<double> t_mah, t_pose;
+  int rec_T = 0, rec_M = 0, rec_L = 0;
+  bool have_trace = false, have_pose_trace = false;
+  std::vector<uint8_t> flag_compass, flag_nz;   // host mirror [F][T] of record flags (regime B)
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // user timer
+  cudaEvent_t kev0[kTimingPairs], kev1[kTimingPairs];
+  int kev_used = 0;
+  EkfLargeTiming ltm{};
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(ekf_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define EKF_CK(h, call)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail(h, EKF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+int check_status(ekf_handle h) {
+  std::vector<int> s(h->st.F);
+  EKF_CK(h, cudaMemcpyAsync(s.data(), h->st.status, sizeof(int) * h->st.F, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  for (int f = 0; f < h->st.F; ++f)
+    if (s[f] & 1) return fail(h, EKF_ERR_CAPACITY, "filter " + std::to_string(f) + ": landmark capacity exceeded, a New association was dropped");
+  return EKF_OK;
+}
+
+void kernel_event_begin(ekf_handle h) {
+  if (h->kev_used < kTimingPairs) cudaEventRecord(h->kev0[h->kev_used], h->stream);
+}
+void kernel_event_end(ekf_handle h) {
+  if (h->kev_used < kTimingPairs) cudaEventRecord(h->kev1[h->kev_used++], h->stream);
+}
+
+int launch_run(ekf_handle h, bool want_trace, bool want_pose) {
+  if (!h->records.p || h->rec_T <= 0) return fail(h, EKF_ERR_BAD_ARG, "no records uploaded");
+  const size_t FT = (size_t)h->st.F * h->rec_T, FTM = FT * (h->rec_M > 0 ? h->rec_M : 1);
+  EkfRunIO io{};
+  io.records = h->records.p;
+  io.T = h->rec_T; io.M = h->rec_M; io.L = h->rec_L;
+  h->have_trace = want_trace;
+  h->have_pose_trace = want_pose;
+  if (want_trace) {
+    EKF_CK(h, h->t_dec.reserve(FTM));
+    EKF_CK(h, h->t_idx.reserve(FTM));
+    EKF_CK(h, h->t_mah.reserve(FTM));
+    io.decision = h->t_dec.p; io.index = h->t_idx.p; io.mahal = h->t_mah.p;
+    if (h->regime == EKF_REGIME_LARGE) {   // slots without a measurement are not visited by any kernel
+      EKF_CK(h, cudaMemsetAsync(h->t_dec.p, 0xFF, FTM * sizeof(int), h->stream));
+      EKF_CK(h, cudaMemsetAsync(h->t_idx.p, 0xFF, FTM * sizeof(int), h->stream));
+      EKF_CK(h, cudaMemsetAsync(h->t_mah.p, 0, FTM * sizeof(double), h->stream));
+    }
+  }
+  if (want_pose) {
+    EKF_CK(h, h->t_pose.reserve(FT * 3));
+    io.pose_trace = h->t_pose.p;
+  }
+  if (h->regime == EKF_REGIME_BATCH) {
+    kernel_event_begin(h);
+    EKF_CK(h, ekf_batch_run(h->st, io, h->k, h->grid_cap, h->stream));
+    kernel_event_end(h);
+    h->launches += 1;
+  } else {
+    for (int f = 0; f < h->st.F; ++f)
+      EKF_CK(h, ekf_large_run(h->st, f, io, h->flag_compass.data() + (size_t)f * h->rec_T,
+                              h->flag_nz.data() + (size_t)f * h->rec_T, h->k, h->wk, &h->ltm, h->stream,
+                              &h->launches));
+  }
+  return EKF_OK;
+}
+
+int download(ekf_handle h, const ekf_run_outputs* out) {
+  const size_t F = h->st.F, FT = F * h->rec_T, FTM = FT * (h->rec_M > 0 ? h->rec_M : 1);
+  if (out) {
+    if ((out->decision || out->lm_index || out->mahal) && !h->have_trace)
+      return fail(h, EKF_ERR_BAD_ARG, "trace requested but the run did not record one");
+    if (out->pose_trace && !h->have_pose_trace)
+      return fail(h, EKF_ERR_BAD_ARG, "pose trace requested but the run did not record one");
+    if (out->decision) EKF_CK(h, cudaMemcpyAsync(out->decision, h->t_dec.p, FTM * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (out->lm_index) EKF_CK(h, cudaMemcpyAsync(out->lm_index, h->t_idx.p, FTM * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (out->mahal) EKF_CK(h, cudaMemcpyAsync(out->mahal, h->t_mah.p, FTM * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out->pose_trace) EKF_CK(h, cudaMemcpyAsync(out->pose_trace, h->t_pose.p, FT * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out->final_pose)
+      EKF_CK(h, cudaMemcpy2DAsync(out->final_pose, 3 * sizeof(double), h->st.x, h->st.xs * sizeof(double),
+                                  3 * sizeof(double), F, cudaMemcpyDeviceToHost, h->stream));
+    if (out->final_nlm) EKF_CK(h, cudaMemcpyAsync(out->final_nlm, h->st.nlm, F * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  }
+  return check_status(h);
+}
+
+}  // namespace
+
+extern "C" {
+
+void ekf_default_config(ekf_config* cfg) {
+  cfg->sigma_v = 0.01;
+  cfg->sigma_w = 0.04;
+  cfg->deg2rad_pi = 3.141592654;
+  cfg->two_pi = 6.283185307;
+  cfg->cond_max = 80.0;
+  cfg->mahal_init = 999999999999.0;
+  cfg->gamma_max = 50;
+  cfg->gamma_min = 10;
+  cfg->regime = EKF_REGIME_AUTO;
+  cfg->reserved = 0;
+}
+
+int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin, size_t* total_mem) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return EKF_ERR_NO_DEVICE;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return EKF_ERR_CUDA;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (smem_optin) *smem_optin = p.sharedMemPerBlockOptin;
+  if (total_mem) *total_mem = p.totalGlobalMem;
+  return EKF_OK;
+}
+
+int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, const ekf_config* cfg_in) {
+  if (!out) return fail(nullptr, EKF_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  if (n_filters < 1 || max_landmarks < 1) return fail(nullptr, EKF_ERR_BAD_ARG, "n_filters and max_landmarks must be >= 1");
+  int sms = 0, maj = 0, mnr = 0;
+  size_t smem_optin = 0, total = 0;
+  int rc = ekf_device_info(device, &sms, &maj, &mnr, &smem_optin, &total);
+  if (rc != EKF_OK) return fail(nullptr, EKF_ERR_NO_DEVICE, "no usable CUDA device " + std::to_string(device) + " (this library has no CPU fallback)");
+  if (maj != 10) return fail(nullptr, EKF_ERR_NO_DEVICE, "device is sm_" + std::to_string(maj * 10 + mnr) + "; this library is built for sm_100a (B200) only");
+  ekf_config cfg;
+  if (cfg_in) cfg = *cfg_in;
+  else ekf_default_config(&cfg);
+
+  ekf_handle h = new ekf_handle_s();
+  h->device = device;
+  h->sm_count = sms;
+  h->cfg = cfg;
+  h->k = EkfConst{cfg.sigma_v, cfg.sigma_w, cfg.deg2rad_pi, cfg.two_pi, cfg.cond_max, cfg.mahal_init, cfg.gamma_max, cfg.gamma_min};
+  auto bail = [&](int code, const std::string& msg) {
+    g_create_error = msg;
+    ekf_destroy(h);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(EKF_ERR_CUDA, "cudaSetDevice failed");
+  const int fit = ekf_batch_max_landmarks(smem_optin);
+  int regime = cfg.regime;
+  if (regime == EKF_REGIME_AUTO) regime = max_landmarks <= fit ? EKF_REGIME_BATCH : EKF_REGIME_LARGE;
+  if (regime == EKF_REGIME_BATCH && max_landmarks > fit)
+    return bail(EKF_ERR_UNSUPPORTED, "max_landmarks " + std::to_string(max_landmarks) + " does not fit the shared-memory-resident regime (limit " + std::to_string(fit) + ")");
+  if (regime != EKF_REGIME_BATCH && regime != EKF_REGIME_LARGE) return bail(EKF_ERR_BAD_ARG, "bad regime");
+  h->regime = regime;
+
+  EkfState& st = h->st;
+  st.F = n_filters;
+  st.cap_lm = max_landmarks;
+  st.cap_n = 3 + 2 * max_landmarks;
+  // leading dimension: even (double2 rows); regime B pads columns to 128 bytes
+  st.ld = regime == EKF_REGIME_LARGE ? ((st.cap_n + 15) & ~15) : ((st.cap_n + 1) & ~1);
+  st.xs = (size_t)((st.cap_n + 1) & ~1);
+  st.slab = (size_t)st.cap_n * st.ld;
+  const size_t need = (size_t)n_filters * (st.slab + st.xs) * sizeof(double);
+  if (need > total) return bail(EKF_ERR_UNSUPPORTED, "state does not fit device memory");
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&st.x, (size_t)n_filters * st.xs * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&st.P, (size_t)n_filters * st.slab * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&st.nlm, (size_t)n_filters * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&st.status, (size_t)n_filters * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  for (int i = 0; i < kTimingPairs; ++i) {
+    cudaEventCreate(&h->kev0[i]);
+    cudaEventCreate(&h->kev1[i]);
+  }
+  if (regime == EKF_REGIME_BATCH) {
+    if ((e = ekf_batch_prepare(st.cap_n, st.ld, EKF_RECORD_LEN_MAX, sms, &h->grid_cap)) != cudaSuccess)
+      return bail(EKF_ERR_CUDA, std::string("ekf_batch_prepare: ") + cudaGetErrorString(e));
+  } else {
+    if ((e = ekf_large_prepare(sms, &h->wk.grid)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaMalloc(&h->wk.W, (size_t)(st.cap_n + 2) * sizeof(double2))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaMalloc(&h->wk.cand_val, (size_t)h->wk.grid * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaMalloc(&h->wk.cand_idx, (size_t)h->wk.grid * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaMalloc(&h->wk.small, ekf_large_small_doubles() * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    cudaMemset(h->wk.W, 0, (size_t)(st.cap_n + 2) * sizeof(double2));
+    h->ltm.ev0 = h->kev0;
+    h->ltm.ev1 = h->kev1;
+    h->ltm.cap = kTimingPairs;
+    h->ltm.every = 1;
+  }
+  rc = ekf_reset(h);
+  if (rc != EKF_OK) {
+    const std::string msg = h->err;
+    return bail(rc, msg);
+  }
+  *out = h;
+  return EKF_OK;
+}
+
+int ekf_destroy(ekf_handle h) {
+  if (!h) return EKF_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->st.x); cudaFree(h->st.P); cudaFree(h->st.nlm); cudaFree(h->st.status);
+  cudaFree(h->wk.W); cudaFree(h->wk.cand_val); cudaFree(h->wk.cand_idx); cudaFree(h->wk.small);
+  h->in.release(); h->o_dec.release(); h->o_idx.release(); h->o_mah.release(); h->in_valid.release();
+  h->records.release(); h->t_dec.release(); h->t_idx.release(); h->t_mah.release(); h->t_pose.release();
+  if (h->ev0) {
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    for (int i = 0; i < kTimingPairs; ++i) {
+      cudaEventDestroy(h->kev0[i]);
+      cudaEventDestroy(h->kev1[i]);
+    }
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return EKF_OK;
+}
+
+int ekf_reset(ekf_handle h) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const EkfState& st = h->st;
+  EKF_CK(h, cudaMemsetAsync(st.x, 0, (size_t)st.F * st.xs * sizeof(double), h->stream));
+  EKF_CK(h, cudaMemsetAsync(st.P, 0, (size_t)st.F * st.slab * sizeof(double), h->stream));
+  EKF_CK(h, cudaMemsetAsync(st.nlm, 0, (size_t)st.F * sizeof(int), h->stream));
+  EKF_CK(h, cudaMemsetAsync(st.status, 0, (size_t)st.F * sizeof(int), h->stream));
+  return EKF_OK;
+}
+
+int ekf_n_filters(ekf_handle h) { return h ? h->st.F : 0; }
+int ekf_max_landmarks(ekf_handle h) { return h ? h->st.cap_lm : 0; }
+int ekf_regime(ekf_handle h) { return h ? h->regime : 0; }
+
+int ekf_set_state(ekf_handle h, int filter, int n_landmarks, const double* x, const double* P, int ld) {
+  if (!h || !x || !P) return EKF_ERR_BAD_ARG;
+  const EkfState& st = h->st;
+  const int n = 3 + 2 * n_landmarks;
+  if (filter < 0 || filter >= st.F || n_landmarks < 0 || n_landmarks > st.cap_lm || ld < n)
+    return fail(h, EKF_ERR_BAD_ARG, "ekf_set_state: bad filter / n_landmarks / ld");
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < j; ++i) {
+      const double a = P[i + (size_t)j * ld], b = P[j + (size_t)i * ld];
+      if (!(a == b || (a != a && b != b)))
+        return fail(h, EKF_ERR_BAD_ARG, "ekf_set_state: P must be bit-symmetric (the reference symmetrises after every operation)");
+    }
+  cudaSetDevice(h->device);
+  EKF_CK(h, cudaMemcpyAsync(st.x + (size_t)filter * st.xs, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  EKF_CK(h, cudaMemcpy2DAsync(st.P + (size_t)filter * st.slab, (size_t)st.ld * sizeof(double), P, (size_t)ld * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
+  EKF_CK(h, cudaMemcpyAsync(st.nlm + filter, &n_landmarks, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
+int ekf_get_state(ekf_handle h, int filter, int* n_landmarks, double* x, double* P, int ld) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  const EkfState& st = h->st;
+  if (filter < 0 || filter >= st.F) return fail(h, EKF_ERR_BAD_ARG, "ekf_get_state: bad filter");
+  cudaSetDevice(h->device);
+  int nl = 0;
+  EKF_CK(h, cudaMemcpyAsync(&nl, st.nlm + filter, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  const int n = 3 + 2 * nl;
+  if (n_landmarks) *n_landmarks = nl;
+  if (x) EKF_CK(h, cudaMemcpyAsync(x, st.x + (size_t)filter * st.xs, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (P) {
+    if (ld < n) return fail(h, EKF_ERR_BAD_ARG, "ekf_get_state: ld < n");
+    EKF_CK(h, cudaMemcpy2DAsync(P, (size_t)ld * sizeof(double), st.P + (size_t)filter * st.slab, (size_t)st.ld * sizeof(double),
+                                (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
+int ekf_get_pose(ekf_handle h, double* xyphi, int32_t* n_landmarks) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  const EkfState& st = h->st;
+  cudaSetDevice(h->device);
+  if (xyphi)
+    EKF_CK(h, cudaMemcpy2DAsync(xyphi, 3 * sizeof(double), st.x, st.xs * sizeof(double), 3 * sizeof(double), st.F,
+                                cudaMemcpyDeviceToHost, h->stream));
+  if (n_landmarks) EKF_CK(h, cudaMemcpyAsync(n_landmarks, st.nlm, sizeof(int) * st.F, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
+int ekf_propagate(ekf_handle h, const double* vel_mm_s, const double* rotvel_deg_s, const double* dt, int dt_stride) {
+  if (!h || !vel_mm_s || !rotvel_deg_s || !dt) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t F = h->st.F;
+  EKF_CK(h, h->in.reserve(3 * F));
+  EKF_CK(h, cudaMemcpyAsync(h->in.p, vel_mm_s, F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EKF_CK(h, cudaMemcpyAsync(h->in.p + F, rotvel_deg_s, F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EKF_CK(h, cudaMemcpyAsync(h->in.p + 2 * F, dt, (dt_stride ? F : 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EkfPercallIO io{};
+  io.vel = h->in.p; io.rotvel = h->in.p + F; io.dt = h->in.p + 2 * F; io.dt_stride = dt_stride ? 1 : 0;
+  if (h->regime == EKF_REGIME_BATCH) {
+    EKF_CK(h, ekf_batch_percall(h->st, io, EKF_OP_PROPAGATE, h->k, h->stream));
+    h->launches += 1;
+  } else {
+    for (int f = 0; f < h->st.F; ++f) {
+      EKF_CK(h, ekf_large_percall(h->st, f, io, EKF_OP_PROPAGATE, h->k, h->wk, nullptr, h->stream));
+      h->launches += ekf_large_launches_per(EKF_OP_PROPAGATE);
+    }
+  }
+  // the staging buffer is reused by the next call: the copy above must have been consumed
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
+int ekf_update(ekf_handle h, int n_z, const double* z, const double* R, int32_t* decision, int32_t* lm_index, double* mahal) {
+  if (!h || n_z < 0 || (n_z > 0 && (!z || !R))) return EKF_ERR_BAD_ARG;
+  if (n_z == 0) return EKF_OK;
+  cudaSetDevice(h->device);
+  const size_t F = h->st.F, FZ = F * n_z;
+  std::vector<double> zr(FZ * 6);
+  for (size_t q = 0; q < FZ; ++q) {
+    zr[6 * q + 0] = z[2 * q + 0];
+    zr[6 * q + 1] = z[2 * q + 1];
+    for (int c = 0; c < 4; ++c) zr[6 * q + 2 + c] = R[4 * q + c];
+  }
+  EKF_CK(h, h->in.reserve(FZ * 6));
+  EKF_CK(h, h->o_dec.reserve(FZ));
+  EKF_CK(h, h->o_idx.reserve(FZ));
+  EKF_CK(h, h->o_mah.reserve(FZ));
+  EKF_CK(h, cudaMemcpyAsync(h->in.p, zr.data(), FZ * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EkfPercallIO io{};
+  io.n_z = n_z; io.zr = h->in.p;
+  io.decision = h->o_dec.p; io.index = h->o_idx.p; io.mahal = h->o_mah.p;
+  if (h->regime == EKF_REGIME_BATCH) {
+    EKF_CK(h, ekf_batch_percall(h->st, io, EKF_OP_UPDATE, h->k, h->stream));
+    h->launches += 1;
+  } else {
+    for (int f = 0; f < h->st.F; ++f) {
+      EKF_CK(h, ekf_large_percall(h->st, f, io, EKF_OP_UPDATE, h->k, h->wk, &h->ltm, h->stream));
+      h->launches += (long long)n_z * ekf_large_launches_per(EKF_OP_UPDATE);
+    }
+  }
+  if (decision) EKF_CK(h, cudaMemcpyAsync(decision, h->o_dec.p, FZ * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (lm_index) EKF_CK(h, cudaMemcpyAsync(lm_index, h->o_idx.p, FZ * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (mahal) EKF_CK(h, cudaMemcpyAsync(mahal, h->o_mah.p, FZ * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));   // zr (host) and the staging buffer are reusable
+  if (decision)
+    for (size_t q = 0; q < FZ; ++q)
+      if (decision[q] == EKF_DECISION_DROPPED) return fail(h, EKF_ERR_CAPACITY, "landmark capacity exceeded, a New association was dropped");
+  return EKF_OK;
+}
+
+int ekf_update_compass(ekf_handle h, const double* z, const double* R, const uint8_t* valid) {
+  if (!h || !z || !R) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t F = h->st.F;
+  EKF_CK(h, h->in.reserve(2 * F));
+  EKF_CK(h, cudaMemcpyAsync(h->in.p, z, F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EKF_CK(h, cudaMemcpyAsync(h->in.p + F, R, F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EkfPercallIO io{};
+  io.cz = h->in.p; io.cR = h->in.p + F;
+  if (valid) {
+    EKF_CK(h, h->in_valid.reserve(F));
+    EKF_CK(h, cudaMemcpyAsync(h->in_valid.p, valid, F, cudaMemcpyHostToDevice, h->stream));
+    io.cvalid = h->in_valid.p;
+  }
+  if (h->regime == EKF_REGIME_BATCH) {
+    EKF_CK(h, ekf_batch_percall(h->st, io, EKF_OP_COMPASS, h->k, h->stream));
+    h->launches += 1;
+  } else {
+    for (int f = 0; f < h->st.F; ++f) {
+      if (valid && !valid[f]) continue;
+      EKF_CK(h, ekf_large_percall(h->st, f, io, EKF_OP_COMPASS, h->k, h->wk, nullptr, h->stream));
+      h->launches += ekf_large_launches_per(EKF_OP_COMPASS);
+    }
+  }
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
+int ekf_upload_records(ekf_handle h, int n_steps, int max_meas, const double* records) {
+  if (!h || !records || n_steps < 1 || max_meas < 0 || max_meas > EKF_MAX_MEAS)
+    return fail(h, EKF_ERR_BAD_ARG, "ekf_upload_records: bad arguments (max_meas <= " + std::to_string(EKF_MAX_MEAS) + ")");
+  cudaSetDevice(h->device);
+  const int L = EKF_RECORD_LEN(max_meas);
+  const size_t count = (size_t)h->st.F * n_steps * L;
+  EKF_CK(h, h->records.reserve(count));
+  EKF_CK(h, cudaMemcpyAsync(h->records.p, records, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->rec_T = n_steps; h->rec_M = max_meas; h->rec_L = L;
+  if (h->regime == EKF_REGIME_LARGE) {
+    const size_t FT = (size_t)h->st.F * n_steps;
+    h->flag_compass.resize(FT);
+    h->flag_nz.resize(FT);
+    for (size_t q = 0; q < FT; ++q) {
+      const double* rec = records + q * L;
+      h->flag_compass[q] = rec[6] != 0.0;
+      int nz = (int)rec[5];
+      h->flag_nz[q] = (uint8_t)(nz < 0 ? 0 : nz > max_meas ? max_meas : nz);
+    }
+  }
+  return EKF_OK;
+}
+
+int ekf_run_resident(ekf_handle h, int want_trace, int want_pose_trace) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return launch_run(h, want_trace != 0, want_pose_trace != 0);
+}
+
+int ekf_download_outputs(ekf_handle h, const ekf_run_outputs* out) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return download(h, out);
+}
+
+int ekf_run(ekf_handle h, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out) {
+  int rc = ekf_upload_records(h, n_steps, max_meas, records);
+  if (rc != EKF_OK) return rc;
+  const bool want_trace = out && (out->decision || out->lm_index || out->mahal);
+  const bool want_pose = out && out->pose_trace;
+  rc = launch_run(h, want_trace, want_pose);
+  if (rc != EKF_OK) return rc;
+  return download(h, out);
+}
+
+int ekf_sync(ekf_handle h) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return check_status(h);
+}
+
+const char* ekf_last_error(ekf_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void* ekf_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void ekf_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int ekf_timer_start(ekf_handle h) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  EKF_CK(h, cudaEventRecord(h->ev0, h->stream));
+  return EKF_OK;
+}
+int ekf_timer_stop(ekf_handle h, float* ms) {
+  if (!h || !ms) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  EKF_CK(h, cudaEventRecord(h->ev1, h->stream));
+  EKF_CK(h, cudaEventSynchronize(h->ev1));
+  EKF_CK(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return EKF_OK;
+}
+
+long long ekf_kernel_launches(ekf_handle h) { return h ? h->launches : 0; }
+
+int ekf_kernel_time(ekf_handle h, float* avg_ms, int* n_launches) {
+  if (!h || !avg_ms || !n_launches) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  int& used = h->regime == EKF_REGIME_BATCH ? h->kev_used : h->ltm.used;
+  double sum = 0;
+  for (int i = 0; i < used; ++i) {
+    float ms = 0;
+    EKF_CK(h, cudaEventElapsedTime(&ms, h->kev0[i], h->kev1[i]));
+    sum += ms;
+  }
+  *n_launches = used;
+  *avg_ms = used ? (float)(sum / used) : 0.f;
+  used = 0;
+  h->ltm.seen = 0;
+  return EKF_OK;
+}
+
+int ekf_measure_fp64_peak(int device, double* flops_per_s) {
+  if (!flops_per_s) return EKF_ERR_BAD_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return EKF_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return EKF_ERR_CUDA;
+  return ekf_fp64_peak(flops_per_s, nullptr) == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// ekf_internal.h — host-side declarations shared by the C ABI (ekf_api.cu) and the kernel
+// translation units (ekf_batch.cu, ekf_large.cu). Not part of the public interface.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ekf_small.cuh"
+
+#define EKF_MAX_MEAS 16                              // record capacity the kernels are sized for
+#define EKF_RECORD_LEN_MAX (8 + 6 * EKF_MAX_MEAS)
+
+// Device-resident state of a handle. x: [F][xs], P: [F][slab] (column-major, leading dim ld).
+struct EkfState {
+  double* x;
+  double* P;
+  int* nlm;
+  int* status;      // sticky per-filter flags (bit 0: a New was dropped at capacity)
+  int F, cap_lm, cap_n, ld;
+  size_t xs;        // doubles per filter in x (cap_n rounded up to even)
+  size_t slab;      // doubles per filter in P (cap_n * ld)
+};
+
+// Step-record stream + optional trace outputs of the fused path (all device pointers).
+struct EkfRunIO {
+  const double* records;   // [F][T][L]
+  int T, M, L;
+  int* decision;           // [F][T][M] or null
+  int* index;              // [F][T][M] or null
+  double* mahal;           // [F][T][M] or null
+  double* pose_trace;      // [F][T][3] or null
+};
+
+struct EkfPercallIO {
+  // propagate
+  const double* vel; const double* rotvel; const double* dt; int dt_stride;
+  // update: zr [F][n_z][6] = {z0,z1,R00,R10,R01,R11} (the record's measurement slot layout);
+  // outputs [F][n_z] or null
+  int n_z; const double* zr;
+  int* decision; int* index; double* mahal;
+  // compass
+  const double* cz; const double* cR; const uint8_t* cvalid;
+};
+
+enum EkfOp { EKF_OP_PROPAGATE = 0, EKF_OP_UPDATE = 1, EKF_OP_COMPASS = 2 };
+
+// ---- regime A: one CTA per filter (ekf_batch.cu) ------------------------------------------------
+size_t ekf_batch_smem_bytes(int cap_n, int ld, int L);
+// Largest landmark capacity whose covariance fits in one CTA's shared memory on `device`.
+int ekf_batch_max_landmarks(size_t smem_optin);
+cudaError_t ekf_batch_prepare(int cap_n, int ld, int max_L, int sm_count, int* grid_cap);
+cudaError_t ekf_batch_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int grid_cap,
+                          cudaStream_t stream);
+cudaError_t ekf_batch_percall(const EkfState& st, const EkfPercallIO& io, EkfOp op, const EkfConst& k,
+                              cudaStream_t stream);
+
+// ---- regime B: whole grid per filter, covariance streamed from HBM (ekf_large.cu) ---------------
+struct EkfLargeWork {      // device scratch owned by the handle
+  double2* W;              // [cap_n + 2]  downdate vectors
+  double* cand_val;        // [grid]   per-CTA gating minima
+  int* cand_idx;           // [grid]
+  double* small;           // LargeSmall (setup, winner, decision), ekf_large_small_doubles() doubles
+  int grid;                // CTAs of the downdate sweep (multiple of the SM count)
+};
+// Optional CUDA-event sampling of the dominant (downdate) kernel: every `every`-th launch is
+// bracketed by ev0[k]/ev1[k] until `cap` pairs are used.
+struct EkfLargeTiming {
+  cudaEvent_t* ev0;
+  cudaEvent_t* ev1;
+  int cap, used, every, seen;
+};
+cudaError_t ekf_large_prepare(int sm_count, int* grid);
+size_t ekf_large_small_doubles();
+int ekf_large_launches_per(EkfOp op);
+cudaError_t ekf_large_percall(const EkfState& st, int filter, const EkfPercallIO& io, EkfOp op, const EkfConst& k,
+                              const EkfLargeWork& wk, EkfLargeTiming* tm, cudaStream_t stream);
+// has_compass / n_z: host mirrors [T] of the record flags of this filter.
+cudaError_t ekf_large_run(const EkfState& st, int filter, const EkfRunIO& io, const uint8_t* has_compass,
+                          const uint8_t* n_z, const EkfConst& k, const EkfLargeWork& wk, EkfLargeTiming* tm,
+                          cudaStream_t stream, long long* launches);
+
+// ---- misc ---------------------------------------------------------------------------------------
+cudaError_t ekf_fp64_peak(double* flops_per_s, cudaStream_t stream);

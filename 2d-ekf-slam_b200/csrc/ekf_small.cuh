@@ -1,0 +1,236 @@
+// ekf_small.cuh — per-thread small-matrix arithmetic of the EKF-SLAM filter core (FP64).
+//
+// Everything here follows the OPERATION ORDER of the reference expressions it replaces
+// (kentsommer/2D-EKF-SLAM, odometry/Update.cpp:85-148, Propagate.cpp:33-53,
+// kalmanfilter.cpp:26-37,96-118): chained matrix products associate left-to-right and every
+// inner sum is sequential, seeded with its first product. This translation unit is compiled
+// with -fmad=false, so a*b + c*d is DMUL, DMUL, DADD exactly as written: the data-association
+// decisions (cond >= 80, Mahalanobis argmin, Gamma thresholds) are computed from the same
+// rounded intermediates the reference produces; only cos/sin (CUDA libdevice vs glibc, <= 2 ulp)
+// can differ. The O(n^2) covariance work is elsewhere (ekf_cta.cuh) and uses explicit fma().
+#pragma once
+#include <cstdint>
+
+struct EkfConst {
+  double sigma_v, sigma_w, deg2rad_pi, two_pi, cond_max, mahal_init;
+  int gamma_max, gamma_min;
+};
+
+// Per-update quantities that do not depend on the landmark (Update.cpp:89-95,113-114), built
+// once per measurement by one thread and broadcast through shared memory.
+struct UpdateSetup {
+  double c, s;          // cos(phi), sin(phi)
+  double Ct[4];         // H_Li = C^T          column-major {(0,0),(1,0),(0,1),(1,1)}
+  double mCt[4];        // -1.0*C^T            (first two columns of every H_R)
+  double mCtJ[4];       // (-1.0*C^T)*J
+  double PRR[9];        // P_min.block(0,0,3,3), column-major
+  double q[6];          // HR(:,0:2)*PRR(0:2,:) partial sums: q(i,j)=mCt(i,0)*PRR(0,j)+mCt(i,1)*PRR(1,j)
+  double x0, x1;        // G_pR_hat
+  double z0, z1;        // measurement
+  double R[4];          // measurement covariance, column-major
+};
+
+__device__ __forceinline__ void ekf_build_setup(UpdateSetup& u, double phi, double x0, double x1, const double* PRR,
+                                                double z0, double z1, const double* R) {
+  double s, c;
+  sincos(phi, &s, &c);
+  u.c = c; u.s = s;
+  // C << cos,-sin,sin,cos (Update.cpp:90); C^T
+  u.Ct[0] = c;  u.Ct[1] = -s; u.Ct[2] = s;  u.Ct[3] = c;
+  for (int k = 0; k < 4; ++k) u.mCt[k] = -1.0 * u.Ct[k];
+  // J << 0,-1,1,0 (Update.cpp:73): J(0,0)=0 J(1,0)=1 J(0,1)=-1 J(1,1)=0
+  const double J00 = 0.0, J10 = 1.0, J01 = -1.0, J11 = 0.0;
+  u.mCtJ[0] = u.mCt[0] * J00 + u.mCt[2] * J10;
+  u.mCtJ[1] = u.mCt[1] * J00 + u.mCt[3] * J10;
+  u.mCtJ[2] = u.mCt[0] * J01 + u.mCt[2] * J11;
+  u.mCtJ[3] = u.mCt[1] * J01 + u.mCt[3] * J11;
+  for (int k = 0; k < 9; ++k) u.PRR[k] = PRR[k];
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 2; ++i) u.q[i + 2 * j] = u.mCt[i] * PRR[0 + 3 * j] + u.mCt[i + 2] * PRR[1 + 3 * j];
+  u.x0 = x0; u.x1 = x1; u.z0 = z0; u.z1 = z1;
+  for (int k = 0; k < 4; ++k) u.R[k] = R[k];
+}
+
+struct GateResult {
+  double res0, res1;    // z - z_hat
+  double S[4];          // symmetrised innovation covariance, column-major
+  double h3_0, h3_1;    // third column of H_R
+  double cond;
+  double d2;            // res^T S^-1 res (only meaningful when !skipped)
+};
+
+// One iteration of the landmark loop, Update.cpp:103-136. p[0..5] = P(Li+r, j) for r=0..1, j=0..2
+// stored as p[r + 2*j] (this is P_LiR; P_RLi is its exact transpose because P is bit-symmetric);
+// pll = {P(Li,Li), P(Li+1,Li), P(Li,Li+1), P(Li+1,Li+1)}.
+__device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double lx, double ly, const double* p,
+                                                  const double* pll, GateResult& g) {
+  const double d0 = lx - u.x0, d1 = ly - u.x1;
+  const double zh0 = u.Ct[0] * d0 + u.Ct[2] * d1;
+  const double zh1 = u.Ct[1] * d0 + u.Ct[3] * d1;
+  g.res0 = u.z0 - zh0;
+  g.res1 = u.z1 - zh1;
+  const double h30 = u.mCtJ[0] * d0 + u.mCtJ[2] * d1;
+  const double h31 = u.mCtJ[1] * d0 + u.mCtJ[3] * d1;
+  g.h3_0 = h30; g.h3_1 = h31;
+  // H_R (2x3) column-major
+  const double HR[6] = {u.mCt[0], u.mCt[1], u.mCt[2], u.mCt[3], h30, h31};
+  // a1 = H_R*P_RR (2x3): ((HR(i,0)*P(0,j) + HR(i,1)*P(1,j)) + HR(i,2)*P(2,j))
+  double a1[6];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    a1[0 + 2 * j] = u.q[0 + 2 * j] + h30 * u.PRR[2 + 3 * j];
+    a1[1 + 2 * j] = u.q[1 + 2 * j] + h31 * u.PRR[2 + 3 * j];
+  }
+  double t1[4], t2[4], t3[4], t4[4];
+  // t1 = a1*H_R^T (2x2): t(i,j) = a(i,0)*HR(j,0) + a(i,1)*HR(j,1) + a(i,2)*HR(j,2)
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      t1[i + 2 * j] = (a1[i] * HR[j] + a1[i + 2] * HR[j + 2]) + a1[i + 4] * HR[j + 4];
+  // a2 = H_Li*P_LiR (2x3), P_LiR(r,j) = p[r + 2*j]
+  double a2[6];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a2[i + 2 * j] = u.Ct[i] * p[0 + 2 * j] + u.Ct[i + 2] * p[1 + 2 * j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      t2[i + 2 * j] = (a2[i] * HR[j] + a2[i + 2] * HR[j + 2]) + a2[i + 4] * HR[j + 4];
+  // a3 = H_R*P_RLi (2x2), P_RLi(r,j) = P(r, Li+j) = p[j + 2*r]
+  double a3[4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      a3[i + 2 * j] = (HR[i] * p[j + 0] + HR[i + 2] * p[j + 2]) + HR[i + 4] * p[j + 4];
+  // t3 = a3*H_Li^T ; H_Li^T = C, C(k,j): C(0,0)=c C(1,0)=s C(0,1)=-s C(1,1)=c = {Ct[0],Ct[2],Ct[1],Ct[3]}
+  const double Cm[4] = {u.Ct[0], u.Ct[2], u.Ct[1], u.Ct[3]};
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) t3[i + 2 * j] = a3[i] * Cm[0 + 2 * j] + a3[i + 2] * Cm[1 + 2 * j];
+  // a4 = H_Li*P_LiLi ; t4 = a4*H_Li^T
+  double a4[4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a4[i + 2 * j] = u.Ct[i] * pll[0 + 2 * j] + u.Ct[i + 2] * pll[1 + 2 * j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) t4[i + 2 * j] = a4[i] * Cm[0 + 2 * j] + a4[i + 2] * Cm[1 + 2 * j];
+  double S[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) S[k] = (((t1[k] + t2[k]) + t3[k]) + t4[k]) + u.R[k];
+  // S = 0.5*(S + S^T) (Update.cpp:123-124)
+  const double s01 = 0.5 * (S[2] + S[1]);
+  const double s10 = 0.5 * (S[1] + S[2]);
+  g.S[0] = 0.5 * (S[0] + S[0]);
+  g.S[3] = 0.5 * (S[3] + S[3]);
+  g.S[2] = s01;
+  g.S[1] = s10;
+  // condition number via 2x2 singular values (Update.cpp:127-128)
+  const double a = g.S[0], c = g.S[1], b = g.S[2], d = g.S[3];
+  const double E = (a + d) * 0.5, F = (a - d) * 0.5, G = (c + b) * 0.5, H = (c - b) * 0.5;
+  const double Q = sqrt(E * E + H * H), Rr = sqrt(F * F + G * G);
+  g.cond = (Q + Rr) / fabs(Q - Rr);
+  // Mahalanobis distance (Update.cpp:135-136)
+  const double det = a * d - b * c;
+  const double invdet = 1.0 / det;
+  const double i00 = d * invdet, i10 = -c * invdet, i01 = -b * invdet, i11 = a * invdet;
+  const double r0 = g.res0 * i00 + g.res1 * i10;
+  const double r1 = g.res0 * i01 + g.res1 * i11;
+  g.d2 = r0 * g.res0 + r1 * g.res1;
+}
+
+__device__ __forceinline__ void ekf_inv2(const double* S, double* Si) {
+  const double a = S[0], c = S[1], b = S[2], d = S[3];
+  const double det = a * d - b * c;
+  const double invdet = 1.0 / det;
+  Si[0] = d * invdet;
+  Si[1] = -c * invdet;
+  Si[2] = -b * invdet;
+  Si[3] = a * invdet;
+}
+
+// Three-way decision, Update.cpp:152,181,191. 0 = New, 1 = Old, 2 = Ignore.
+__device__ __forceinline__ int ekf_decide(int opt_i, double mahal, const EkfConst& k) {
+  if (opt_i == 0 || mahal > (double)k.gamma_max) return 0;
+  if (mahal < (double)k.gamma_min) return 1;
+  return 2;
+}
+
+// Odometry read + Q (kalmanfilter.cpp:17-37) and the scalars of Propagate.cpp:33-48.
+struct PropSetup {
+  double v, w, dt;
+  double Q[4];       // column-major
+  double c, s;       // cos/sin of the pre-propagation heading
+  double phi02, phi12;  // Phi_R(0,2), Phi_R(1,2)
+  double g00, g10, g21; // G(0,0), G(1,0), G(2,1)
+};
+
+__device__ __forceinline__ void ekf_build_prop(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,
+                                               double ori, const EkfConst& k) {
+  const double RTV = rotvel_deg_s * k.deg2rad_pi / 180.0;   // kalmanfilter.cpp:19
+  p.v = vel_mm_s / 1000.0;                                   // :26
+  p.w = RTV;
+  p.dt = dt;
+  // Q = (v*v)*Q0*Q0 with Q0 = [sigma_v 0; 0 sigma_w] (kalmanfilter.cpp:35-37)
+  const double vv = p.v * p.v;
+  const double Q0[4] = {k.sigma_v, 0.0, 0.0, k.sigma_w};
+  double A[4];
+  for (int i = 0; i < 4; ++i) A[i] = vv * Q0[i];
+  for (int j = 0; j < 2; ++j)
+    for (int i = 0; i < 2; ++i) p.Q[i + 2 * j] = A[i] * Q0[0 + 2 * j] + A[i + 2] * Q0[1 + 2 * j];
+  sincos(ori, &p.s, &p.c);
+  p.phi02 = -dt * p.v * p.s;   // Propagate.cpp:42
+  p.phi12 = dt * p.v * p.c;    // :43
+  p.g00 = -dt * p.c;           // :46
+  p.g10 = -dt * p.s;           // :47
+  p.g21 = -dt;                 // :48
+}
+
+// P_RR <- Phi*P_RR*Phi^T + G*Q*G^T, then the 3x3 part of 0.5*(P+P^T) (Propagate.cpp:53,66-67).
+// PRR column-major 3x3, in place.
+__device__ __forceinline__ void ekf_prop_prr(const PropSetup& p, double* PRR) {
+  const double Phi[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, p.phi02, p.phi12, 1.0};
+  const double G[6] = {p.g00, p.g10, 0.0, 0.0, 0.0, p.g21};
+  double T1[9], T2[9], T3[6], T4[9];
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i)
+      T1[i + 3 * j] = (Phi[i] * PRR[3 * j] + Phi[i + 3] * PRR[1 + 3 * j]) + Phi[i + 6] * PRR[2 + 3 * j];
+  for (int j = 0; j < 3; ++j)   // T2 = T1*Phi^T: T2(i,j) = sum_k T1(i,k)*Phi(j,k)
+    for (int i = 0; i < 3; ++i)
+      T2[i + 3 * j] = (T1[i] * Phi[j] + T1[i + 3] * Phi[j + 3]) + T1[i + 6] * Phi[j + 6];
+  for (int j = 0; j < 2; ++j)   // T3 = G*Q (3x2)
+    for (int i = 0; i < 3; ++i) T3[i + 3 * j] = G[i] * p.Q[2 * j] + G[i + 3] * p.Q[1 + 2 * j];
+  for (int j = 0; j < 3; ++j)   // T4 = T3*G^T: T4(i,j) = T3(i,0)*G(j,0) + T3(i,1)*G(j,1)
+    for (int i = 0; i < 3; ++i) T4[i + 3 * j] = T3[i] * G[j] + T3[i + 3] * G[j + 3];
+  double M[9];
+  for (int k = 0; k < 9; ++k) M[k] = T2[k] + T4[k];
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) PRR[i + 3 * j] = 0.5 * (M[i + 3 * j] + M[j + 3 * i]);
+}
+
+// One column of P_RL <- Phi*P_RL (Propagate.cpp:56), literal 3-term sums with the 1/0 entries.
+__device__ __forceinline__ void ekf_prop_col(const PropSetup& p, double& a0, double& a1, double& a2) {
+  const double o0 = (1.0 * a0 + 0.0 * a1) + p.phi02 * a2;
+  const double o1 = (0.0 * a0 + 1.0 * a1) + p.phi12 * a2;
+  const double o2 = (0.0 * a0 + 0.0 * a1) + 1.0 * a2;
+  a0 = o0; a1 = o1; a2 = o2;
+}
+
+// Compass residual selection, kalmanfilter.cpp:98-110.
+__device__ __forceinline__ double ekf_compass_residual(double phi, double z, const EkfConst& k) {
+  double z_hat = phi;
+  z_hat -= k.two_pi * floor(z_hat / k.two_pi);
+  const double res1 = z - z_hat;
+  const double res2 = z - k.two_pi - z_hat;
+  const double res3 = z + k.two_pi - z_hat;
+  if ((fabs(res1) <= fabs(res2)) && (fabs(res1) <= fabs(res3))) return res1;
+  if (fabs(res2) <= fabs(res3)) return res2;
+  return res3;
+}

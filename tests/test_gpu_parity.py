@@ -1,0 +1,243 @@
+"""GPU parity tests (pytest -m gpu): the CUDA filter core, called through the C ABI, against the
+CPU oracle on the same seeded step records. Decisions / landmark indices must be bit-exact,
+state and covariance within 1e-9 relative (tests/parity.py)."""
+import numpy as np
+import pytest
+
+from parity import TOL, assert_state_close, assert_trace_equal, injected_state, rel_cov, rel_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _final_states(fb, F):
+    return [fb.get_state(f) for f in range(F)]
+
+
+def _oracle_states(want, F):
+    out = []
+    for f in range(F):
+        n = 3 + 2 * int(want["final_nlm"][f])
+        out.append((want["final_x"][f, :n].copy(), want["final_P"][f, :n, :n].T.copy()))
+    return out
+
+
+def _run_both(ekf, checker, N, F, T, cap, M=1, laps=1, regime=0, **synth_kw):
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=M, **synth_kw)
+    lap = syn.generate(F, T)
+    rec = np.ascontiguousarray(np.concatenate([lap] * laps, axis=1))
+    fb = ekf.FilterBatch(F, cap, regime=regime)
+    got = fb.run(rec, M, trace=True, pose_trace=True)
+    want = checker.run_batch(rec, M, cap, pose_trace=True, final_state=True)
+    assert not want["bad"]
+    return fb, got, want
+
+
+@pytest.mark.parametrize("N,F,cap", [(20, 6, 24), (50, 4, 56)])
+def test_fused_run_matches_oracle(ekf, oracle, N, F, cap):
+    """BASELINE config 1 shape (N=20, 1,000 steps) and the N=50 headline shape, two laps."""
+    T = 1000
+    fb, got, want = _run_both(ekf, oracle, N, F, T, cap, laps=2)
+    assert_trace_equal(got, want, "fused run")
+    assert np.array_equal(got["final_nlm"], want["final_nlm"])
+    assert (got["final_nlm"] == N).all()
+    assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL
+    for f, ((x, P), (xr, Pr)) in enumerate(zip(_final_states(fb, F), _oracle_states(want, F))):
+        assert_state_close(x, P, xr, Pr, "filter %d" % f)
+        assert np.array_equal(P, P.T), "covariance must stay bit-symmetric"
+    fb.close()
+
+
+def test_fused_run_matches_reference_build(ekf, ref):
+    """Same comparison against the reference's own translation units (oracle/_ref)."""
+    fb, got, want = _run_both(ekf, ref, 20, 3, 600, 24, laps=2)
+    assert_trace_equal(got, want, "fused run vs reference")
+    for f, ((x, P), (xr, Pr)) in enumerate(zip(_final_states(fb, 3), _oracle_states(want, 3))):
+        assert_state_close(x, P, xr, Pr, "filter %d" % f)
+    fb.close()
+
+
+def test_multi_measurement_and_compass(ekf, oracle):
+    """n_z > 1 per step (Update.cpp:80-195 processes them sequentially) plus doUpdateCompass."""
+    fb, got, want = _run_both(ekf, oracle, 20, 5, 500, 24, M=3, laps=2, compass_every=5)
+    assert (got["decision"] >= 0).sum() > 1000
+    assert_trace_equal(got, want, "M=3 + compass")
+    assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL
+    for f, ((x, P), (xr, Pr)) in enumerate(zip(_final_states(fb, 5), _oracle_states(want, 5))):
+        assert_state_close(x, P, xr, Pr, "filter %d" % f)
+    fb.close()
+
+
+@pytest.mark.parametrize("regime", [1, 2])
+def test_percall_surface_matches_oracle(ekf, oracle, regime):
+    """doPropagation / doUpdateCompass / doUpdate one call at a time, state checked every step."""
+    N, F, T, cap = 12, 3, 160, 16
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=2, compass_every=7)
+    rec = syn.generate(F, T)
+    fb = ekf.FilterBatch(F, cap, regime=regime)
+    assert fb.regime == regime
+    filters = [oracle.new_filter(cap) for _ in range(F)]
+    for t in range(T):
+        r = rec[:, t]
+        fb.propagate(r[:, 0], r[:, 1], r[:, 2])
+        for f in range(F):
+            filters[f].propagate(r[f, 0], r[f, 1], r[f, 2])
+        if r[0, 6] != 0:
+            fb.update_compass(r[:, 3], r[:, 4])
+            for f in range(F):
+                filters[f].update_compass(r[f, 3], r[f, 4])
+        nz = int(r[0, 5])
+        assert (r[:, 5] == nz).all()
+        if nz:
+            zr = r[:, 8:8 + 6 * nz].reshape(F, nz, 6)
+            dec, idx, mah = fb.update(zr[:, :, :2], zr[:, :, 2:])
+            for f in range(F):
+                for m in range(nz):
+                    n_before = filters[f].n
+                    tr = filters[f].update(zr[f, m, :2], zr[f, m, 2:])
+                    assert dec[f, m] == tr.decision
+                    assert idx[f, m] == (n_before if tr.decision == 0 else tr.opt_i)
+                    assert abs(mah[f, m] - tr.mahal) <= TOL * max(1.0, abs(tr.mahal))
+        if t % 10 == 0 or t == T - 1:
+            for f in range(F):
+                x, P = fb.get_state(f)
+                xr, Pr = filters[f].get_state()
+                assert_state_close(x, P, xr, Pr, "step %d filter %d" % (t, f))
+    pose, nlm = fb.get_pose()
+    for f in range(F):
+        assert nlm[f] == filters[f].num_landmarks
+        assert rel_state(pose[f], filters[f].pose()) <= TOL
+    fb.close()
+
+
+def test_large_regime_fused_run(ekf, oracle):
+    """Regime B kernels on a map small enough to compare every step."""
+    fb, got, want = _run_both(ekf, oracle, 16, 2, 300, 20, M=2, laps=2, regime=2, compass_every=9)
+    assert fb.regime == 2
+    assert_trace_equal(got, want, "large regime")
+    assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL
+    for f, ((x, P), (xr, Pr)) in enumerate(zip(_final_states(fb, 2), _oracle_states(want, 2))):
+        assert_state_close(x, P, xr, Pr, "filter %d" % f)
+        assert np.array_equal(P, P.T)
+    fb.close()
+
+
+@pytest.mark.parametrize("N,steps", [(300, 40), (2000, 4)])
+def test_large_map_injected_state(ekf, oracle, N, steps):
+    """BASELINE config 4 shape: state injected, then Old-updates streamed from HBM."""
+    syn = ekf.Synth(N, steps_per_lap=20000, max_meas=1)
+    rec = syn.generate(1, steps)
+    x0, P0 = injected_state(syn.world(), seed=N)
+    fb = ekf.FilterBatch(1, N + 2)
+    assert fb.regime == 2
+    fb.set_state(0, x0, P0)
+    of = oracle.new_filter(N + 2).set_state(x0, P0)
+    n_old = 0
+    for t in range(steps):
+        r = rec[0, t]
+        fb.propagate(r[0], r[1], r[2])
+        of.propagate(r[0], r[1], r[2])
+        dec, idx, mah = fb.update(r[8:10], r[10:14])
+        n_before = of.n
+        tr = of.update(r[8:10], r[10:14])
+        assert dec[0, 0] == tr.decision and idx[0, 0] == (n_before if tr.decision == 0 else tr.opt_i)
+        assert abs(mah[0, 0] - tr.mahal) <= TOL * max(1.0, abs(tr.mahal))
+        n_old += tr.decision == 1
+    assert n_old >= steps // 2, "the injected state should mostly re-observe known landmarks"
+    x, P = fb.get_state(0)
+    xr, Pr = of.get_state()
+    assert_state_close(x, P, xr, Pr, "N=%d" % N)
+    assert np.array_equal(P, P.T)
+    fb.close()
+
+
+def test_capacity_overflow_is_reported(ekf):
+    N, F, T, cap = 12, 2, 200, 5
+    rec = ekf.Synth(N, steps_per_lap=T).generate(F, T)
+    fb = ekf.FilterBatch(F, cap)
+    with pytest.raises(ekf.EkfError) as ei:
+        fb.run(rec, 1)
+    assert ei.value.code == ekf.ERR_CAPACITY
+    got = fb.run(rec, 1, allow_capacity=True)
+    assert (got["decision"] == ekf.DECISION_DROPPED).any()
+    assert (got["final_nlm"] == cap).all()
+    x, P = fb.get_state(0)
+    assert np.isfinite(x).all() and np.isfinite(P).all()
+    fb.close()
+
+
+def test_set_get_state_roundtrip_and_validation(ekf):
+    fb = ekf.FilterBatch(3, 10)
+    rng = np.random.default_rng(1)
+    n = 3 + 2 * 7
+    x = rng.normal(size=n)
+    A = rng.normal(size=(n, n))
+    P = A @ A.T
+    P = 0.5 * (P + P.T)
+    fb.set_state(1, x, P)
+    x2, P2 = fb.get_state(1)
+    assert np.array_equal(x, x2) and np.array_equal(P, P2)
+    x0, P0 = fb.get_state(0)
+    assert len(x0) == 3 and not P0.any()
+    Pbad = P.copy()
+    Pbad[0, 1] += 1e-12
+    with pytest.raises(ekf.EkfError) as ei:
+        fb.set_state(1, x, Pbad)
+    assert ei.value.code == ekf.ERR_BAD_ARG
+    fb.reset()
+    x3, P3 = fb.get_state(1)
+    assert len(x3) == 3 and not x3.any() and not P3.any()
+    fb.close()
+
+
+def test_run_is_deterministic_and_independent_of_batch_position(ekf):
+    """The same filter must give identical bits wherever it sits in a batch (this is what makes
+    sharding a batch across GPUs by filter range exact)."""
+    N, T, cap = 20, 400, 24
+    syn = ekf.Synth(N, steps_per_lap=T)
+    rec = syn.generate(700, T)            # more filters than co-resident CTAs
+    fb = ekf.FilterBatch(700, cap)
+    a = fb.run(rec, 1, pose_trace=True)
+    fb.reset()
+    b = fb.run(rec, 1, pose_trace=True)
+    for k in ("decision", "index", "mahal", "pose_trace", "final_pose", "final_nlm"):
+        assert np.array_equal(a[k], b[k]), k
+    fb.close()
+    sub = np.ascontiguousarray(rec[500:516])
+    fs = ekf.FilterBatch(16, cap)
+    c = fs.run(sub, 1, pose_trace=True)
+    for k in ("decision", "index", "mahal", "pose_trace", "final_pose", "final_nlm"):
+        assert np.array_equal(a[k][500:516], c[k]), k
+    fs.close()
+
+
+def test_headline_config_properties_and_sampled_parity(ekf, oracle):
+    """BASELINE config 2 at full size: 4,096 filters x 50 landmarks x 1,000 steps (+ a warm-up lap),
+    checked through size-independent properties and a sampled comparison with the oracle."""
+    N, F, T, cap = 50, 4096, 1000, 56
+    syn = ekf.Synth(N, steps_per_lap=T)
+    rec = syn.generate(F, T)
+    fb = ekf.FilterBatch(F, cap)
+    fb.upload_records(rec, 1)
+    fb.run_resident(trace=False)
+    fb.run_resident(trace=True, pose_trace=True)        # second lap: full maps
+    got = fb.download_outputs(trace=True, pose_trace=True)
+    assert (got["final_nlm"] == N).all()
+    d = got["decision"]
+    assert ((d == 1) | (d == 2)).all(), "lap 2 must only re-observe known landmarks"
+    assert (d == 1).mean() > 0.95
+    truth = np.array([syn.true_pose(t + 1)[:2] for t in range(T)])
+    err = np.abs(got["pose_trace"][:, :, :2] - truth[None]).max()
+    assert err < 1.0, "filters diverged from the true trajectory: %g m" % err
+    sample = [0, 1, 777, 2048, 4095]
+    rec2 = np.ascontiguousarray(np.concatenate([rec[sample]] * 2, axis=1))
+    want = oracle.run_batch(rec2, 1, cap, pose_trace=True, final_state=True)
+    for s, f in enumerate(sample):
+        assert np.array_equal(d[f], want["decision"][s, T:])
+        assert np.array_equal(got["index"][f], want["index"][s, T:])
+        assert rel_state(got["pose_trace"][f], want["pose_trace"][s, T:]) <= TOL
+        x, P = fb.get_state(f)
+        n = len(x)
+        assert np.array_equal(P, P.T)
+        assert np.linalg.eigvalsh(P).min() > -1e-12
+        assert_state_close(x, P, want["final_x"][s, :n], want["final_P"][s, :n, :n].T, "filter %d" % f)
+    fb.close()
