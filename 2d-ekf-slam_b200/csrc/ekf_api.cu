@@ -126,8 +126,12 @@ int launch_run(ekf_handle h, bool want_trace, bool want_pose) {
     io.pose_trace = h->t_pose.p;
   }
   if (h->regime == EKF_REGIME_BATCH) {
+    const bool tile = h->cfg.batch_kernel != EKF_BATCH_KERNEL_SMEM && h->st.cap_lm <= ekf_tile_max_landmarks();
+    if (h->cfg.batch_kernel == EKF_BATCH_KERNEL_TILE && !tile)
+      return fail(h, EKF_ERR_UNSUPPORTED, "register-tile kernel supports max_landmarks <= " + std::to_string(ekf_tile_max_landmarks()));
     kernel_event_begin(h);
-    EKF_CK(h, ekf_batch_run(h->st, io, h->k, h->grid_cap, h->stream));
+    if (tile) EKF_CK(h, ekf_tile_run(h->st, io, h->k, h->sm_count, h->stream));
+    else EKF_CK(h, ekf_batch_run(h->st, io, h->k, h->grid_cap, h->stream));
     kernel_event_end(h);
     h->launches += 1;
   } else {
@@ -172,7 +176,7 @@ void ekf_default_config(ekf_config* cfg) {
   cfg->gamma_max = 50;
   cfg->gamma_min = 10;
   cfg->regime = EKF_REGIME_AUTO;
-  cfg->reserved = 0;
+  cfg->batch_kernel = EKF_BATCH_KERNEL_AUTO;
 }
 
 int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin, size_t* total_mem) {

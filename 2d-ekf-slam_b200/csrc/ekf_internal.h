@@ -52,6 +52,10 @@ cudaError_t ekf_batch_run(const EkfState& st, const EkfRunIO& io, const EkfConst
 cudaError_t ekf_batch_percall(const EkfState& st, const EkfPercallIO& io, EkfOp op, const EkfConst& k,
                               cudaStream_t stream);
 
+// Register-tile variant of the fused path (ekf_tile.cu): covariance half in registers as 8x8 tiles.
+int ekf_tile_max_landmarks();
+cudaError_t ekf_tile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
+
 // ---- regime B: whole grid per filter, covariance streamed from HBM (ekf_large.cu) ---------------
 struct EkfLargeWork {      // device scratch owned by the handle
   double2* W;              // [cap_n + 2]  downdate vectors

@@ -15,6 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 OK, ERR_CUDA, ERR_BAD_ARG, ERR_CAPACITY, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(6)
 DECISION_NONE, DECISION_NEW, DECISION_OLD, DECISION_IGNORE, DECISION_DROPPED = -1, 0, 1, 2, 3
 REGIME_AUTO, REGIME_BATCH, REGIME_LARGE = 0, 1, 2
+BATCH_KERNEL_AUTO, BATCH_KERNEL_SMEM, BATCH_KERNEL_TILE = 0, 1, 2
 RECORD_HEADER = 8
 
 c_dp = C.POINTER(C.c_double)
@@ -43,7 +44,7 @@ class Config(C.Structure):
     _fields_ = [("sigma_v", C.c_double), ("sigma_w", C.c_double), ("deg2rad_pi", C.c_double),
                 ("two_pi", C.c_double), ("cond_max", C.c_double), ("mahal_init", C.c_double),
                 ("gamma_max", C.c_int32), ("gamma_min", C.c_int32), ("regime", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("batch_kernel", C.c_int32)]
 
 
 class RunOutputs(C.Structure):
@@ -204,11 +205,15 @@ class FilterBatch:
         self.F = n_filters
         self.cap_lm = max_landmarks
         self.cap_n = 3 + 2 * max_landmarks
+        self._pinned = []
 
     def close(self):
         if getattr(self, "h", None):
             self.L.ekf_destroy(self.h)
             self.h = None
+            for pa in self._pinned:
+                pa.free()
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -231,10 +236,13 @@ class FilterBatch:
     def sync(self):
         self._chk(self.L.ekf_sync(self.h))
 
-    def set_state(self, filt, x, P):
+    def set_state(self, filt, x, P, symmetric=False):
+        """x (n), P (n x n, numpy row-major). symmetric=True skips the transpose copy to column-major
+        (P must equal P.T bit for bit anyway; the C ABI checks)."""
         x = np.ascontiguousarray(x, np.float64)
         n = len(x)
-        Pc = np.ascontiguousarray(np.asarray(P, np.float64).T)  # column-major
+        Pa = np.asarray(P, np.float64)
+        Pc = np.ascontiguousarray(Pa if symmetric else Pa.T)  # column-major
         self._chk(self.L.ekf_set_state(self.h, filt, (n - 3) // 2, _dp(x), _dp(Pc), n))
 
     def get_state(self, filt):
@@ -284,25 +292,37 @@ class FilterBatch:
             vp = valid.ctypes.data_as(C.POINTER(C.c_uint8))
         self._chk(self.L.ekf_update_compass(self.h, _dp(z), _dp(R), vp))
 
-    def _outputs(self, T, M, trace, pose_trace):
+    def alloc_outputs(self, T, M, trace=True, pose_trace=False, pinned=False):
+        """Host output buffers for run()/download_outputs(); pinned=True uses cudaMallocHost memory."""
+        def mk(shape, dtype):
+            if pinned:
+                pa = PinnedArray(shape, dtype)
+                self._pinned.append(pa)
+                return pa.array
+            return np.zeros(shape, dtype)
+        M = max(M, 1)
         o = {
-            "decision": np.zeros((self.F, T, M), np.int32) if trace else None,
-            "index": np.zeros((self.F, T, M), np.int32) if trace else None,
-            "mahal": np.zeros((self.F, T, M)) if trace else None,
-            "pose_trace": np.zeros((self.F, T, 3)) if pose_trace else None,
-            "final_pose": np.zeros((self.F, 3)),
-            "final_nlm": np.zeros(self.F, np.int32),
+            "decision": mk((self.F, T, M), np.int32) if trace else None,
+            "index": mk((self.F, T, M), np.int32) if trace else None,
+            "mahal": mk((self.F, T, M), np.float64) if trace else None,
+            "pose_trace": mk((self.F, T, 3), np.float64) if pose_trace else None,
+            "final_pose": mk((self.F, 3), np.float64),
+            "final_nlm": mk((self.F,), np.int32),
         }
-        ro = RunOutputs(_ip(o["decision"]), _ip(o["index"]), _dp(o["mahal"]), _dp(o["pose_trace"]),
-                        _dp(o["final_pose"]), _ip(o["final_nlm"]))
-        return o, ro
+        o["_c"] = RunOutputs(_ip(o["decision"]), _ip(o["index"]), _dp(o["mahal"]), _dp(o["pose_trace"]),
+                             _dp(o["final_pose"]), _ip(o["final_nlm"]))
+        return o
 
-    def run(self, records, max_meas, trace=True, pose_trace=False, allow_capacity=False):
+    @staticmethod
+    def output_bytes(o):
+        return int(sum(v.nbytes for k, v in o.items() if k != "_c" and v is not None))
+
+    def run(self, records, max_meas, trace=True, pose_trace=False, allow_capacity=False, outputs=None):
         """End-to-end fused run: H2D records, T steps per filter, D2H outputs."""
         F, T, L = records.shape
         assert F == self.F and L == record_len(max_meas) and records.dtype == np.float64
-        o, ro = self._outputs(T, max_meas, trace, pose_trace)
-        rc = self.L.ekf_run(self.h, T, max_meas, _dp(records), C.byref(ro))
+        o = outputs if outputs is not None else self.alloc_outputs(T, max_meas, trace, pose_trace)
+        rc = self.L.ekf_run(self.h, T, max_meas, _dp(records), C.byref(o["_c"]))
         if not (allow_capacity and rc == ERR_CAPACITY):
             self._chk(rc)
         return o
@@ -316,10 +336,10 @@ class FilterBatch:
     def run_resident(self, trace=False, pose_trace=False):
         self._chk(self.L.ekf_run_resident(self.h, int(trace), int(pose_trace)))
 
-    def download_outputs(self, trace=True, pose_trace=False):
+    def download_outputs(self, trace=True, pose_trace=False, outputs=None):
         T, M = self._rec_shape
-        o, ro = self._outputs(T, M, trace, pose_trace)
-        self._chk(self.L.ekf_download_outputs(self.h, C.byref(ro)))
+        o = outputs if outputs is not None else self.alloc_outputs(T, M, trace, pose_trace)
+        self._chk(self.L.ekf_download_outputs(self.h, C.byref(o["_c"])))
         return o
 
     def timer_start(self):

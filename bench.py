@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py - filter-steps/s of the batched EKF-SLAM filter core (N=50 landmarks) on B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA core
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU code (oracle/_ref)
+
+One bench "step" is one pass of the hot path over one batch: every filter of the rank's shard
+runs one full lap (1,000 iterations of the slam.cpp:130-182 loop: doPropagation + one doUpdate)
+with its 50-landmark map already built during warm-up, so every timed filter-step is a full-size
+(n = 103) propagate + gating + update. `value` = filter-steps/s with the step records resident in
+HBM; `e2e` = the same through ekf_run() with pinned HOST buffers (H2D of the records and D2H of the
+decisions inside the timed region). Ranks own disjoint filter ranges, no data-path collective
+(weak scaling); torch.distributed is only used for the barrier and the max-over-ranks reduction.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "filter-steps/sec (batched EKF, N=50)"
+UNIT = "filter-steps/s"
+N_LM = 50
+CAP_LM = 50          # landmark capacity per filter: 13x13 register tiles, 2 CTAs (filters) per SM
+T_LAP = 1000
+MAX_MEAS = 1
+
+
+def load_product():
+    spec = importlib.util.spec_from_file_location("ekf_b200", os.path.join(ROOT, "2d-ekf-slam_b200", "ekf_b200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ekf_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ---- algorithmic work (DESIGN.md "Algorithmic flops / bytes"; SURVEY.md 8d F_min) ------------------
+def fmin_flops(n_lm, decision):
+    """Minimum FP64 flops of one filter-step with n_lm landmarks in the map."""
+    n = 3 + 2 * n_lm
+    f = 8 * n_lm + 170                      # propagate
+    f += 150 * n_lm                         # gating: H, S, cond, Mahalanobis per landmark
+    if decision == 1:                       # Old: gain + state + symmetric rank-2 downdate
+        f += 2 * n * n + 42 * n
+    return f
+
+
+def large_bytes(n_lm):
+    n = 3 + 2 * n_lm
+    return 16 * n * n + 56 * n + 96 * n_lm   # per Old update, regime B
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize(local)
+
+
+def max_over_ranks(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def cpu_baseline(records_one_lap, kind_pref="reference", seconds_target=12.0):
+    """The reference's CPU filter on the box's host cores: a bounded sample of the same workload
+    (same records), one filter per task, all hardware threads, timed on the full-map lap only."""
+    from oracle_lib import Oracle, Ref
+    if kind_pref == "reference" and Ref.available():
+        chk, kind = Ref(), "reference"
+    else:
+        chk, kind = Oracle(), "port"
+    cores = os.cpu_count() or 1
+    T = records_one_lap.shape[1]
+    # calibrate on one filter, then size the sample for ~seconds_target of wall time
+    one = np.ascontiguousarray(np.concatenate([records_one_lap[:1]] * 2, axis=1))
+    t0 = time.perf_counter()
+    chk.run_batch(one, MAX_MEAS, CAP_LM, n_threads=1, trace=False)
+    per_filter = max(time.perf_counter() - t0, 1e-3)          # 2 laps, 1 thread
+    n_f = int(max(cores, min(records_one_lap.shape[0], cores * max(1.0, seconds_target / per_filter))))
+    n_f = max(cores, (n_f // cores) * cores)
+    n_f = min(n_f, records_one_lap.shape[0])
+    rec = np.ascontiguousarray(np.concatenate([records_one_lap[:n_f]] * 2, axis=1))
+    r = chk.run_batch(rec, MAX_MEAS, CAP_LM, n_threads=cores, trace=False, warm_steps=T)
+    assert not r["bad"]
+    assert (r["final_nlm"] == N_LM).all()
+    val = n_f * T / r["seconds"]
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d filters x %d full-map steps (after an untimed %d-step map-building lap), "
+                      "one filter per task over %d host threads; %s" %
+                      (n_f, T, T, cores,
+                       "reference odometry/*.cpp compiled unmodified over the stand-in Eigen, -O2" if kind == "reference"
+                       else "C restatement oracle/ekf_oracle.c, -O2")}, chk
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ekf = load_product()
+    cores = os.cpu_count() or 1
+    syn = ekf.Synth(N_LM, steps_per_lap=T_LAP, max_meas=MAX_MEAS)
+    n_f = max(cores, 2 * cores)
+    lap = syn.generate(n_f, T_LAP)
+    from oracle_lib import Oracle, Ref
+    chk, kind = (Ref(), "reference") if Ref.available() else (Oracle(), "port")
+    rec = np.ascontiguousarray(np.concatenate([lap] * 2, axis=1))
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = chk.run_batch(rec, MAX_MEAS, CAP_LM, n_threads=cores, trace=False, warm_steps=T_LAP)
+        assert not r["bad"]
+        if i >= args.warmup:
+            times.append(r["seconds"])
+    total = sum(times)
+    val = n_f * T_LAP * args.steps / total
+    sample = ("each step: %d filters x %d full-map steps (after an untimed map-building lap) over %d host "
+              "threads" % (n_f, T_LAP, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, 1), "filters_per_step_sample": n_f,
+                       "landmarks": N_LM, "steps_per_lap": T_LAP},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, world):
+    return ("%d filters x %d landmarks x %d steps per GPU, chip-resident covariance (BASELINE configs[1]%s)"
+            % (args.filters_per_gpu, N_LM, T_LAP, "" if world == 1 else ", %d GPUs, disjoint filter ranges" % world))
+
+
+def large_map_leg(ekf, n_lm, steps, hbm_peak, device):
+    """BASELINE configs[3]/[4]: one large map, covariance in HBM, Old-updates from an injected state."""
+    from parity import injected_state
+    # a (nearly) stationary robot: the same few visible landmarks are re-observed, every update is
+    # an Old-update over the full n x n covariance
+    syn = ekf.Synth(n_lm, steps_per_lap=10 ** 7, max_meas=1)
+    rec = syn.generate(1, steps)
+    x0, P0 = injected_state(syn.world(), seed=n_lm)
+    fb = ekf.FilterBatch(1, n_lm + 2, device=device)
+    fb.set_state(0, x0, P0, symmetric=True)
+    fb.upload_records(rec, 1)
+    fb.run_resident(trace=True)            # warm-up pass
+    fb.sync()
+    fb.set_state(0, x0, P0, symmetric=True)   # timed pass starts from the same injected state
+    del P0
+    fb.kernel_time()
+    l0 = fb.kernel_launches()
+    fb.timer_start()
+    fb.run_resident(trace=True)
+    ms = fb.timer_stop()
+    l1 = fb.kernel_launches()
+    out = fb.download_outputs(trace=True)
+    kms, kn = fb.kernel_time()
+    n_old = int((out["decision"] == 1).sum())
+    fb.close()
+    alg = large_bytes(n_lm)
+    res = {"workload": "1 map x %d landmarks (n=%d, P=%.2f GB), %d update steps" %
+                       (n_lm, 3 + 2 * n_lm, 8.0 * (3 + 2 * n_lm) ** 2 / 1e9, steps),
+           "old_updates": n_old, "steps": steps, "ms_per_step": ms / steps,
+           "update_steps_per_s": steps / (ms * 1e-3), "gpu_launches": int(l1 - l0),
+           "roofline": {"bound": "hbm", "kernel": "large_downdate<2>", "achieved": alg / (kms * 1e-3) / 1e9 if kn else None,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": (alg / (kms * 1e-3) / 1e9) / hbm_peak if kn else None,
+                        "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_kernel_ms": kms,
+                        "launches_timed": kn},
+           "step_gbs": alg * n_old / (ms * 1e-3) / 1e9}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--filters-per-gpu", type=int, default=4096)
+    ap.add_argument("--large-map", default="2000,10000", help="comma list of landmark counts for the regime-B leg ('' = skip)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    ekf = load_product()
+    rank, world, local, dist = dist_setup(args.gpus)
+    F = args.filters_per_gpu
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    # ---- inputs: this rank's filter range, generated once on the host into pinned memory ------------
+    syn = ekf.Synth(N_LM, steps_per_lap=T_LAP, max_meas=MAX_MEAS)
+    L = syn.record_len
+    pinned = ekf.PinnedArray((F, T_LAP, L))
+    syn.generate(F, T_LAP, f0=rank * F, out=pinned.array)
+    rec = pinned.array
+    fb = ekf.FilterBatch(F, CAP_LM, device=local)
+    outs = fb.alloc_outputs(T_LAP, MAX_MEAS, trace=True, pose_trace=False, pinned=True)
+
+    # ---- device-resident throughput ("value") -------------------------------------------------------
+    fb.upload_records(rec, MAX_MEAS)
+    for _ in range(args.warmup):           # lap 0 builds the 50-landmark maps; later laps are full size
+        fb.run_resident(trace=True)
+    fb.sync()
+    fb.kernel_time()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier(dist, local)
+    l0 = fb.kernel_launches()
+    fb.timer_start()
+    for _ in range(args.steps):
+        fb.run_resident(trace=True)
+    ms = fb.timer_stop()
+    barrier(dist, local)
+    l1 = fb.kernel_launches()
+    kms, kn = fb.kernel_time()
+    ms_max = max_over_ranks(dist, local, ms)
+    last = fb.download_outputs(trace=True, outputs=outs)
+    assert (last["final_nlm"] == N_LM).all(), "maps must be complete in the timed laps"
+    dec = last["decision"]
+    n_old = int((dec == 1).sum())
+    n_steps_lap = F * T_LAP
+    flops_per_launch = n_old * fmin_flops(N_LM, 1) + (n_steps_lap - n_old) * fmin_flops(N_LM, 2)
+    value = world * F * T_LAP * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end through the C ABI with host buffers ("e2e") ---------------------------------------
+    for _ in range(2):
+        fb.run(rec, MAX_MEAS, outputs=outs)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fb.run(rec, MAX_MEAS, outputs=outs)
+    e2e_s = time.perf_counter() - t0
+    barrier(dist, local)
+    e2e_s = max_over_ranks(dist, local, e2e_s)
+    clocks = sampler.stop()
+    e2e_val = world * F * T_LAP * args.steps / e2e_s
+    h2d = int(rec.nbytes)
+    d2h = fb.output_bytes(outs)
+    fb.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused batch kernel, FP64 pipe) ------------------------------
+    fp64_peak = ekf.measure_fp64_peak(local)
+    achieved = flops_per_launch / (kms * 1e-3) if kn else None
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json")))
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "kernel": "ekf_batch_tile_kernel<13>",
+                "achieved": achieved / 1e12 if achieved else None, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak if achieved else None,
+                "traffic": prof.get("batch_traffic_bytes_per_launch"),
+                "algorithmic_flops_per_launch": flops_per_launch, "avg_kernel_ms": kms, "launches_timed": kn,
+                "peak_source": "measured live: DFMA-chain microbenchmark (ekf_measure_fp64_peak); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "note": "no dense contraction on this path -> tensor cores unused; graded flops are F_min "
+                        "(SURVEY 8d): 150/landmark gated + 2n^2+42n per Old update + 8N+170 per propagate"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "filters_per_gpu": F, "landmarks": N_LM,
+                       "landmark_capacity": CAP_LM, "steps_per_lap": T_LAP, "measurements_per_step": MAX_MEAS,
+                       "old_fraction": n_old / n_steps_lap,
+                       "l2": "inputs larger than L2: %.0f MB of step records + %.0f MB of covariance per pass"
+                             % (rec.nbytes / 1e6, F * (3 + 2 * CAP_LM) * (4 + 2 * CAP_LM) * 8 / 1e6)},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(l1 - l0), "clocks": clocks, "roofline": roofline}
+
+    if world == 1 and args.large_map:
+        legs = []
+        for tok in args.large_map.split(","):
+            n_lm = int(tok)
+            steps = 400 if n_lm <= 2000 else 30
+            legs.append(large_map_leg(ekf, n_lm, steps, hbm_peak, local))
+        line["large_map"] = legs
+        line["roofline_hbm"] = dict(legs[-1]["roofline"], peak_source=hbm_src)
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(rec)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,11 @@ extern "C" {
 #define EKF_REGIME_BATCH 1      /* one CTA per filter; covariance resident in shared memory     */
 #define EKF_REGIME_LARGE 2      /* whole grid per filter; covariance streamed from HBM          */
 
+/* ---- fused-kernel variants of the batch regime (same arithmetic, bit-identical results) ------- */
+#define EKF_BATCH_KERNEL_AUTO 0   /* register tiles when max_landmarks <= 62, else shared memory */
+#define EKF_BATCH_KERNEL_SMEM 1   /* covariance resident in shared memory                         */
+#define EKF_BATCH_KERNEL_TILE 2   /* covariance's lower block triangle resident in registers      */
+
 typedef struct ekf_handle_s* ekf_handle;
 
 /* Every tuning constant of the reference is a literal; they become defaulted fields here
@@ -66,7 +71,7 @@ typedef struct ekf_config {
   int32_t gamma_max;     /* 50            kalmanfilter.cpp:67  */
   int32_t gamma_min;     /* 10            kalmanfilter.cpp:68  */
   int32_t regime;        /* EKF_REGIME_*                        */
-  int32_t reserved;
+  int32_t batch_kernel;  /* EKF_BATCH_KERNEL_* : which fused kernel the batch regime runs */
 } ekf_config;
 
 void ekf_default_config(ekf_config* cfg);

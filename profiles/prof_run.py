@@ -1,0 +1,53 @@
+"""Short, fixed workloads for ncu (one GPU). Usage:
+    python profiles/prof_run.py batch [F] [T]      # fused batch kernel: F filters x T steps, 3 launches
+    python profiles/prof_run.py large [N] [steps]  # regime B: injected N-landmark map, update steps
+The first launch(es) build the maps; profile the LAST launch (ncu -s/-c as in profiles/README.md).
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+spec = importlib.util.spec_from_file_location("ekf_b200", os.path.join(ROOT, "2d-ekf-slam_b200", "ekf_b200.py"))
+ekf = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(ekf)
+
+
+def batch(F=592, T=250):
+    syn = ekf.Synth(50, steps_per_lap=T)
+    rec = syn.generate(F, T)
+    fb = ekf.FilterBatch(F, 56)
+    fb.upload_records(rec, 1)
+    for _ in range(3):                     # lap 0 builds the maps, laps 1-2 are full size
+        fb.run_resident(trace=True)
+    out = fb.download_outputs(trace=True)
+    assert (out["final_nlm"] == 50).all()
+    ms, n = fb.kernel_time()
+    print("batch: F=%d T=%d avg kernel %.3f ms over %d launches -> %.3e filter-steps/s"
+          % (F, T, ms, n, F * T / (ms * 1e-3)))
+    fb.close()
+
+
+def large(N=2000, steps=20):
+    from parity import injected_state
+    syn = ekf.Synth(N, steps_per_lap=10 ** 7, max_meas=1)
+    rec = syn.generate(1, steps)
+    x0, P0 = injected_state(syn.world(), seed=N)
+    fb = ekf.FilterBatch(1, N + 2)
+    fb.set_state(0, x0, P0, symmetric=True)
+    fb.upload_records(rec, 1)
+    fb.run_resident(trace=True)
+    out = fb.download_outputs(trace=True)
+    ms, n = fb.kernel_time()
+    print("large: N=%d steps=%d old=%d avg downdate %.4f ms over %d launches"
+          % (N, steps, int((out["decision"] == 1).sum()), ms, n))
+    fb.close()
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "batch"
+    a = [int(v) for v in sys.argv[2:]]
+    (batch if mode == "batch" else large)(*a)

@@ -60,7 +60,7 @@ class Oracle:
         L.ekf_oracle_update_compass.argtypes = [C.c_int, c_dp, c_dp, C.c_int, C.c_double, C.c_double]
         L.ekf_oracle_measurement_from_feature.argtypes = [C.c_double, C.c_double, c_dp, c_dp]
         L.ekf_oracle_run_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_dp,
-                                           c_dp, c_dp, c_ip, c_dp, c_dp, C.c_int]
+                                           c_dp, c_dp, c_ip, c_dp, c_dp, C.c_int, C.c_int]
         L.ekf_oracle_run_batch.restype = C.c_double
 
     def new_filter(self, cap_lm):
@@ -72,14 +72,15 @@ class Oracle:
         self.lib.ekf_oracle_measurement_from_feature(fx_mm, fy_mm, _dp(z), _dp(R))
         return z, R
 
-    def run_batch(self, records, max_meas, cap_lm, n_threads=1, trace=True, pose_trace=False, final_state=False):
+    def run_batch(self, records, max_meas, cap_lm, n_threads=1, trace=True, pose_trace=False, final_state=False,
+                  warm_steps=0):
         F, T, L = records.shape
         assert L == record_len(max_meas) and records.dtype == np.float64 and records.flags.c_contiguous
         out = _alloc_batch_outputs(F, T, max_meas, 3 + 2 * cap_lm, trace, pose_trace, final_state)
         secs = self.lib.ekf_oracle_run_batch(F, T, max_meas, cap_lm, _dp(records), n_threads,
                                              _ip(out["decision"]), _ip(out["index"]), _dp(out["mahal"]),
                                              _dp(out["pose_trace"]), _dp(out["final_pose"]), _ip(out["final_nlm"]),
-                                             _dp(out["final_x"]), _dp(out["final_P"]), out["ld"])
+                                             _dp(out["final_x"]), _dp(out["final_P"]), out["ld"], warm_steps)
         out["seconds"] = abs(secs)
         out["bad"] = secs < 0
         return out
@@ -183,7 +184,7 @@ class Ref:
         L.ref_call_update.restype = C.c_int
         L.ref_measurement_from_feature.argtypes = [C.c_double, C.c_double, c_dp, c_dp]
         L.ref_run_batch.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_dp, c_dp, c_dp, c_ip,
-                                    c_dp, c_dp, C.c_int]
+                                    c_dp, c_dp, C.c_int, C.c_int]
         L.ref_run_batch.restype = C.c_double
         L.ref_hardware_threads.restype = C.c_int
 
@@ -213,14 +214,15 @@ class Ref:
         n2 = self.lib.ref_call_update(n, _dp(xb), _dp(Pb), n_z, _dp(zc), _dp(Rc), gamma_max, gamma_min)
         return xb[:n2].copy(), Pb[:n2 * n2].reshape(n2, n2).T.copy()
 
-    def run_batch(self, records, max_meas, cap_lm, n_threads=1, trace=True, pose_trace=False, final_state=False):
+    def run_batch(self, records, max_meas, cap_lm, n_threads=1, trace=True, pose_trace=False, final_state=False,
+                  warm_steps=0):
         F, T, L = records.shape
         assert L == record_len(max_meas) and records.dtype == np.float64 and records.flags.c_contiguous
         out = _alloc_batch_outputs(F, T, max_meas, 3 + 2 * cap_lm, trace, pose_trace, final_state)
         secs = self.lib.ref_run_batch(F, T, max_meas, _dp(records), n_threads,
                                       _ip(out["decision"]), _ip(out["index"]), _dp(out["mahal"]),
                                       _dp(out["pose_trace"]), _dp(out["final_pose"]), _ip(out["final_nlm"]),
-                                      _dp(out["final_x"]), _dp(out["final_P"]), out["ld"])
+                                      _dp(out["final_x"]), _dp(out["final_P"]), out["ld"], warm_steps)
         out["seconds"] = abs(secs)
         out["bad"] = secs < 0
         return out

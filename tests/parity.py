@@ -47,7 +47,14 @@ def injected_state(world_xy, seed, pose=(0.0, 0.0, 0.0), lm_sigma=0.02, rank=8):
     U = rng.normal(0, 0.01, (n, rank))
     D = rng.uniform(0.5, 1.5, n) * (lm_sigma ** 2)
     D[:3] = [1e-4, 1e-4, 1e-5]
-    P = U @ U.T + np.diag(D)
-    P = 0.5 * (P + P.T)
-    assert np.array_equal(P, P.T)
+    P = U @ U.T
+    P[np.arange(n), np.arange(n)] += D
+    B = 2048                                   # mirror the upper triangle in place (n can be 20,003)
+    for j0 in range(0, n, B):
+        j1 = min(n, j0 + B)
+        P[j0:j1, :j0] = P[:j0, j0:j1].T
+        blk = P[j0:j1, j0:j1]
+        P[j0:j1, j0:j1] = np.triu(blk) + np.triu(blk, 1).T
+    if n <= 5000:
+        assert np.array_equal(P, P.T)
     return x, P
