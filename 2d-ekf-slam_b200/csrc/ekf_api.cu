@@ -347,6 +347,20 @@ int ekf_get_state(ekf_handle h, int filter, int* n_landmarks, double* x, double*
   return EKF_OK;
 }
 
+int ekf_get_cov_block(ekf_handle h, int filter, int r0, int c0, int nr, int nc, double* out, int ld_out) {
+  if (!h || !out) return EKF_ERR_BAD_ARG;
+  const EkfState& st = h->st;
+  if (filter < 0 || filter >= st.F || r0 < 0 || c0 < 0 || nr < 1 || nc < 1 || r0 + nr > st.cap_n || c0 + nc > st.cap_n ||
+      ld_out < nr)
+    return fail(h, EKF_ERR_BAD_ARG, "ekf_get_cov_block: bad block");
+  cudaSetDevice(h->device);
+  EKF_CK(h, cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(double),
+                              st.P + (size_t)filter * st.slab + r0 + (size_t)c0 * st.ld, (size_t)st.ld * sizeof(double),
+                              (size_t)nr * sizeof(double), nc, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
 int ekf_get_pose(ekf_handle h, double* xyphi, int32_t* n_landmarks) {
   if (!h) return EKF_ERR_BAD_ARG;
   const EkfState& st = h->st;

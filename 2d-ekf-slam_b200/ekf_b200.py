@@ -99,6 +99,7 @@ def core_lib():
         L.ekf_set_state.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, C.c_int]
         L.ekf_get_state.argtypes = [H, C.c_int, C.POINTER(C.c_int), c_dp, c_dp, C.c_int]
         L.ekf_get_pose.argtypes = [H, c_dp, c_ip]
+        L.ekf_get_cov_block.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int]
         L.ekf_propagate.argtypes = [H, c_dp, c_dp, c_dp, C.c_int]
         L.ekf_update.argtypes = [H, C.c_int, c_dp, c_dp, c_ip, c_ip, c_dp]
         L.ekf_update_compass.argtypes = [H, c_dp, c_dp, C.POINTER(C.c_uint8)]
@@ -252,6 +253,11 @@ class FilterBatch:
         self._chk(self.L.ekf_get_state(self.h, filt, C.byref(nl), _dp(x), _dp(P), self.cap_n))
         n = 3 + 2 * nl.value
         return x[:n].copy(), P[:n, :n].T.copy()
+
+    def get_cov_block(self, filt, r0, c0, nr, nc):
+        out = np.zeros((nc, nr))
+        self._chk(self.L.ekf_get_cov_block(self.h, filt, r0, c0, nr, nc, _dp(out), nr))
+        return out.T.copy()
 
     def get_pose(self):
         p = np.zeros((self.F, 3))

@@ -1,0 +1,69 @@
+// slam_synthetic.cpp — the reference's SLAM loop (slam.cpp:127-182) driving the GPU filter core
+// through the drop-in KalmanFilter class, with the robot / laser I/O replaced by the synthetic
+// driver (include/ekf_synth.h). Everything between "Enter SLAM loop" and the odometry log line is
+// the reference's call sequence: doPropagation, optional doUpdateCompass, one doUpdate per
+// feature with R built from the feature as slam.cpp:158-167 does.
+//
+// Build (tests/test_dropin.py does this; any <Eigen/Dense> + Aria.h pair works, here the
+// stand-ins under oracle/shim are used because real Eigen / ARIA are not installed):
+//   g++ -std=c++11 -O2 -Ioracle/shim -I2d-ekf-slam_b200/host -Iinclude examples/slam_synthetic.cpp \
+//       -L2d-ekf-slam_b200/lib -lekf_slam_b200 -lekf_synth -o slam_synthetic
+// Usage: slam_synthetic [n_landmarks] [n_steps] [max_landmarks]  -> one line per step on stdout:
+//   "Update: <tokens><Num_Landmarks>" lines as slam.cpp:169-171 prints, then "odom X Y Phi".
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "ekf_synth.h"
+#include "kalmanfilter.h"
+
+int main(int argc, char** argv) {
+  const int n_landmarks = argc > 1 ? std::atoi(argv[1]) : 20;
+  const int n_steps = argc > 2 ? std::atoi(argv[2]) : 200;
+  const int max_landmarks = argc > 3 ? std::atoi(argv[3]) : n_landmarks + 4;
+
+  ekf_synth_config cfg;
+  ekf_synth_default_config(&cfg, n_landmarks);
+  cfg.steps_per_lap = n_steps;
+  cfg.max_meas = 2;
+  cfg.compass_every = 10;
+  const int L = ekf_synth_record_len(&cfg);
+  std::vector<double> rec(static_cast<size_t>(n_steps) * L);
+  ekf_synth_generate(&cfg, 0, 1, 0, n_steps, rec.data(), nullptr, 1);
+
+  ArRobot robot;
+  std::ofstream covFile, knownfeaturesFile;   // left closed, as in the parity harness
+  std::cout.precision(17);
+
+  // Initialize the kalman filter (slam.cpp:127)
+  KalmanFilter* ekf = new KalmanFilter(&robot, max_landmarks, 0);
+
+  // Enter SLAM loop (slam.cpp:130)
+  for (int t = 0; t < n_steps; ++t) {
+    const double* r = &rec[static_cast<size_t>(t) * L];
+    robot.vel_mm_s = r[0];
+    robot.rotvel_deg_s = r[1];
+    double dt = r[2];
+    ekf->doPropagation(dt, covFile, knownfeaturesFile);              // slam.cpp:136
+
+    if (r[6] != 0.0) ekf->doUpdateCompass(r[3], r[4]);               // slam.cpp:144-147
+
+    const int nz = static_cast<int>(r[5]);
+    for (int i = 0; i < nz; i++) {                                   // slam.cpp:150-171
+      const double* zr = r + 8 + 6 * i;
+      Eigen::MatrixXd z_chunk(2, 1);
+      Eigen::MatrixXd R_chunk(2, 2);
+      z_chunk << zr[0], zr[1];
+      R_chunk << zr[2], zr[4], zr[3], zr[5];   // row-major fill of the column-major record slot
+      std::cout << "Update: ";
+      ekf->doUpdate(z_chunk, R_chunk);
+      std::cout << ekf->Num_Landmarks << std::endl;
+    }
+    std::cout << "odom " << ekf->X << " " << ekf->Y << " " << ekf->Phi << std::endl;   // slam.cpp:181
+  }
+  delete ekf;
+  return 0;
+}

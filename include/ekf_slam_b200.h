@@ -103,6 +103,9 @@ int ekf_regime(ekf_handle h);                      /* the regime actually select
  * hooks SURVEY.md 8b asks for. P must be bit-symmetric (EKF_ERR_BAD_ARG otherwise). */
 int ekf_set_state(ekf_handle h, int filter, int n_landmarks, const double* x, const double* P, int ld);
 int ekf_get_state(ekf_handle h, int filter, int* n_landmarks, double* x, double* P, int ld);
+/* A sub-block P(r0:r0+nr, c0:c0+nc) of one filter's covariance, column-major into out (ld_out >= nr).
+ * Used by the drop-in class for the covRun.txt row the reference writes (kalmanfilter.cpp:51). */
+int ekf_get_cov_block(ekf_handle h, int filter, int r0, int c0, int nr, int nc, double* out, int ld_out);
 /* Public mirrors X, Y, Phi, Num_Landmarks (kalmanfilter.h:24-27) for every filter:
  * xyphi[n_filters][3], n_landmarks[n_filters] (either may be NULL). Synchronises. */
 int ekf_get_pose(ekf_handle h, double* xyphi, int32_t* n_landmarks);

@@ -1,0 +1,44 @@
+"""GPU test: the reference's SLAM loop (slam.cpp:127-182 call sequence, examples/slam_synthetic.cpp)
+driving the CUDA core through the drop-in KalmanFilter class (2d-ekf-slam_b200/host/kalmanfilter.h),
+checked line by line against the oracle on the same records."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOKENS = {"New": 0, "Old": 1, "Ignore": 2, "Full": 3}
+
+
+def test_slam_loop_through_the_dropin_class(ekf, oracle, tmp_path):
+    exe = str(tmp_path / "slam_synthetic")
+    lib = os.path.join(ROOT, "2d-ekf-slam_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "oracle", "shim"),
+                    "-I" + os.path.join(ROOT, "2d-ekf-slam_b200", "host"), "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "slam_synthetic.cpp"), "-L" + lib, "-lekf_slam_b200",
+                    "-lekf_synth", "-Wl,-rpath," + lib, "-o", exe], check=True)
+    N, T = 12, 240
+    for cap in (16, 300):          # batch regime kernels, then the large-map (HBM) kernels
+        out = subprocess.run([exe, str(N), str(T), str(cap)], stdout=subprocess.PIPE, text=True, check=True).stdout
+        syn = ekf.Synth(N, steps_per_lap=T, max_meas=2, compass_every=10)
+        rec = syn.generate(1, T)
+        want = oracle.run_batch(rec, 2, N + 4, pose_trace=True)
+        lines = out.strip().split("\n")
+        dec, nlm, odom = [], [], []
+        for ln in lines:
+            if ln.startswith("Update:"):
+                m = re.match(r"Update: (\w+) (\d+)$", ln)
+                dec.append(TOKENS[m.group(1)])
+                nlm.append(int(m.group(2)))
+            else:
+                odom.append([float(v) for v in ln.split()[1:]])
+        wd = want["decision"][0].reshape(-1)
+        assert dec == [d for d in wd if d >= 0]
+        assert nlm[-1] == N
+        odom = np.array(odom)
+        assert odom.shape == (T, 3)
+        err = np.abs(odom - want["pose_trace"][0]).max() / np.abs(want["pose_trace"][0]).max()
+        assert err <= 1e-9, err
