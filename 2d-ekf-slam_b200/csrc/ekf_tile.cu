@@ -22,6 +22,7 @@
 //                   (Update.cpp:188,193-194 in the bit-symmetric form described in ekf_cta.cuh)
 // Arithmetic is shared with the other kernels (ekf_small.cuh), so results are bit-identical to
 // the shared-memory-resident kernel in ekf_batch.cu.
+#include <cstdlib>
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
 
@@ -59,6 +60,8 @@ struct RunArgs {
   EkfState st;
   EkfRunIO io;
   EkfConst k;
+  int* sm_slots;   // [>= number of SMs], zeroed before the launch: arrival order of CTAs per SM
+  int rot;         // role rotation (in warps) applied to every second CTA of an SM
 };
 
 __device__ __forceinline__ int ext_index(int r) { return r < 3 ? r : r - 1; }   // internal -> external
@@ -127,7 +130,19 @@ template <int NT>
 __global__ void __launch_bounds__(TileCfg<NT>::THREADS, TileCfg<NT>::MINB) ekf_batch_tile_kernel(const RunArgs a) {
   using C = TileCfg<NT>;
   __shared__ __align__(16) TileSmem<NT> sm;
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int s_slot;
+  // Warp w of a CTA issues on sub-partition w % 4. The helper warp carries most of the FP64
+  // issue slots of a step (scalar chains + gating), so co-resident CTAs rotate their warp roles:
+  // their helper warps then sit on different sub-partitions.
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_slot = atomicAdd(&a.sm_slots[smid], 1);
+  }
+  __syncthreads();
+  constexpr int NW = TileCfg<NT>::THREADS / 32;
+  const int vwarp = ((threadIdx.x >> 5) + ((s_slot & 1) ? a.rot : 0)) % NW;
+  const int tid = vwarp * 32 + (threadIdx.x & 31), lane = tid & 31;
   const bool is_tile = tid < C::NTILES;
   const bool is_helper = tid >= C::TW;
   int I = 0, J = 0;
@@ -460,9 +475,22 @@ __global__ void __launch_bounds__(TileCfg<NT>::THREADS, TileCfg<NT>::MINB) ekf_b
 }
 
 template <int NT>
-cudaError_t launch_tile(const RunArgs& a, int sm_count, cudaStream_t stream) {
+cudaError_t launch_tile(RunArgs a, int sm_count, cudaStream_t stream) {
   using C = TileCfg<NT>;
   static int grid_cap = 0;
+  static int* slots = nullptr;
+  static int rot = -1;
+  if (!slots) {
+    cudaError_t e = cudaMalloc(&slots, 1024 * sizeof(int));
+    if (e != cudaSuccess) return e;
+  }
+  if (rot < 0) {
+    const char* env = getenv("EKF_TILE_ROT");
+    rot = env ? atoi(env) : 2;
+  }
+  cudaMemsetAsync(slots, 0, 1024 * sizeof(int), stream);
+  a.sm_slots = slots;
+  a.rot = rot;
   if (!grid_cap) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_batch_tile_kernel<NT>, C::THREADS, 0);
@@ -480,7 +508,7 @@ cudaError_t launch_tile(const RunArgs& a, int sm_count, cudaStream_t stream) {
 int ekf_tile_max_landmarks() { return TileCfg<16>::MAX_LM; }
 
 cudaError_t ekf_tile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream) {
-  RunArgs a{st, io, k};
+  RunArgs a{st, io, k, nullptr, 0};
   if (st.cap_lm <= TileCfg<13>::MAX_LM) return launch_tile<13>(a, sm_count, stream);
   if (st.cap_lm <= TileCfg<14>::MAX_LM) return launch_tile<14>(a, sm_count, stream);
   if (st.cap_lm <= TileCfg<15>::MAX_LM) return launch_tile<15>(a, sm_count, stream);
