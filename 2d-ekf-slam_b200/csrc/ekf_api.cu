@@ -561,6 +561,10 @@ int ekf_kernel_time(ekf_handle h, float* avg_ms, int* n_launches) {
   return EKF_OK;
 }
 
+int ekf_debug_phase_cycles(long long* out8) {
+  return ekf_tile_phase_cycles(out8) == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
+}
+
 int ekf_measure_fp64_peak(int device, double* flops_per_s) {
   if (!flops_per_s) return EKF_ERR_BAD_ARG;
   int n = 0;

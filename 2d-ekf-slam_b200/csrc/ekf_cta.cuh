@@ -214,8 +214,8 @@ __device__ __forceinline__ UpdateOut cta_update(double* __restrict__ P, int ld, 
     pll[2] = P[Li + (size_t)(Li + 1) * ld];
     pll[3] = P[Li + 1 + (size_t)(Li + 1) * ld];
     GateResult g;
-    ekf_gate_landmark(sc->upd, xs[Li], xs[Li + 1], p, pll, g);
-    const bool valid = !(g.cond >= k.cond_max) && (k.mahal_init > g.d2);   // :131, :140 vs INF
+    ekf_gate_landmark(sc->upd, xs[Li], xs[Li + 1], p, pll, k.cond_max, g);
+    const bool valid = !g.skip && (k.mahal_init > g.d2);   // :131, :140 vs INF
     if (valid && g.d2 < best) {
       best = g.d2; best_idx = Li;
       b_res0 = g.res0; b_res1 = g.res1;

@@ -54,6 +54,7 @@ cudaError_t ekf_batch_percall(const EkfState& st, const EkfPercallIO& io, EkfOp 
 
 // Register-tile variant of the fused path (ekf_tile.cu): covariance half in registers as 8x8 tiles.
 int ekf_tile_max_landmarks();
+cudaError_t ekf_tile_phase_cycles(long long* out);   // profiling aid, see ekf_tile.cu
 cudaError_t ekf_tile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
 
 // ---- regime B: whole grid per filter, covariance streamed from HBM (ekf_large.cu) ---------------

@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const 
     double p[6], pll[4];
     load_gate_inputs(P, ld, Li, p, pll);
     GateResult g;
-    ekf_gate_landmark(sc.upd, x[Li], x[Li + 1], p, pll, g);
-    const bool valid = !(g.cond >= a.k.cond_max) && (a.k.mahal_init > g.d2);
+    ekf_gate_landmark(sc.upd, x[Li], x[Li + 1], p, pll, a.k.cond_max, g);
+    const bool valid = !g.skip && (a.k.mahal_init > g.d2);
     if (valid && g.d2 < best) { best = g.d2; best_idx = Li; }
   }
   cta_argmin(best, best_idx, &sc);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
     double p[6], pll[4];
     load_gate_inputs(P, ld, opt_i, p, pll);
     GateResult g;
-    ekf_gate_landmark(u, x[opt_i], x[opt_i + 1], p, pll, g);   // same bits as the gating pass
+    ekf_gate_landmark(u, x[opt_i], x[opt_i + 1], p, pll, a.k.cond_max, g);   // same bits as the gating pass
     sm->res[0] = g.res0; sm->res[1] = g.res1;
     for (int q = 0; q < 4; ++q) sm->S[q] = g.S[q];
     sm->h3[0] = g.h3_0; sm->h3[1] = g.h3_1;

@@ -30,20 +30,32 @@ struct UpdateSetup {
   double R[4];          // measurement covariance, column-major
 };
 
-__device__ __forceinline__ void ekf_build_setup(UpdateSetup& u, double phi, double x0, double x1, const double* PRR,
-                                                double z0, double z1, const double* R) {
+// The heading-dependent part of UpdateSetup (one sincos), separable so a kernel can compute it
+// once per measurement on one thread and let every gating lane complete the rest.
+struct UpdateTrig {
+  double c, s;
+  double Ct[4], mCt[4], mCtJ[4];
+};
+
+__device__ __forceinline__ void ekf_build_trig(UpdateTrig& t, double phi) {
   double s, c;
   sincos(phi, &s, &c);
-  u.c = c; u.s = s;
+  t.c = c; t.s = s;
   // C << cos,-sin,sin,cos (Update.cpp:90); C^T
-  u.Ct[0] = c;  u.Ct[1] = -s; u.Ct[2] = s;  u.Ct[3] = c;
-  for (int k = 0; k < 4; ++k) u.mCt[k] = -1.0 * u.Ct[k];
+  t.Ct[0] = c;  t.Ct[1] = -s; t.Ct[2] = s;  t.Ct[3] = c;
+  for (int k = 0; k < 4; ++k) t.mCt[k] = -1.0 * t.Ct[k];
   // J << 0,-1,1,0 (Update.cpp:73): J(0,0)=0 J(1,0)=1 J(0,1)=-1 J(1,1)=0
   const double J00 = 0.0, J10 = 1.0, J01 = -1.0, J11 = 0.0;
-  u.mCtJ[0] = u.mCt[0] * J00 + u.mCt[2] * J10;
-  u.mCtJ[1] = u.mCt[1] * J00 + u.mCt[3] * J10;
-  u.mCtJ[2] = u.mCt[0] * J01 + u.mCt[2] * J11;
-  u.mCtJ[3] = u.mCt[1] * J01 + u.mCt[3] * J11;
+  t.mCtJ[0] = t.mCt[0] * J00 + t.mCt[2] * J10;
+  t.mCtJ[1] = t.mCt[1] * J00 + t.mCt[3] * J10;
+  t.mCtJ[2] = t.mCt[0] * J01 + t.mCt[2] * J11;
+  t.mCtJ[3] = t.mCt[1] * J01 + t.mCt[3] * J11;
+}
+
+__device__ __forceinline__ void ekf_complete_setup(UpdateSetup& u, const UpdateTrig& t, double x0, double x1,
+                                                   const double* PRR, double z0, double z1, const double* R) {
+  u.c = t.c; u.s = t.s;
+  for (int k = 0; k < 4; ++k) { u.Ct[k] = t.Ct[k]; u.mCt[k] = t.mCt[k]; u.mCtJ[k] = t.mCtJ[k]; }
   for (int k = 0; k < 9; ++k) u.PRR[k] = PRR[k];
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 2; ++i) u.q[i + 2 * j] = u.mCt[i] * PRR[0 + 3 * j] + u.mCt[i + 2] * PRR[1 + 3 * j];
@@ -51,19 +63,31 @@ __device__ __forceinline__ void ekf_build_setup(UpdateSetup& u, double phi, doub
   for (int k = 0; k < 4; ++k) u.R[k] = R[k];
 }
 
+__device__ __forceinline__ void ekf_build_setup(UpdateSetup& u, double phi, double x0, double x1, const double* PRR,
+                                                double z0, double z1, const double* R) {
+  UpdateTrig t;
+  ekf_build_trig(t, phi);
+  ekf_complete_setup(u, t, x0, x1, PRR, z0, z1, R);
+}
+
 struct GateResult {
   double res0, res1;    // z - z_hat
   double S[4];          // symmetrised innovation covariance, column-major
   double h3_0, h3_1;    // third column of H_R
-  double cond;
-  double d2;            // res^T S^-1 res (only meaningful when !skipped)
+  bool skip;            // cond >= cond_max (Update.cpp:131)
+  double d2;            // res^T S^-1 res (only meaningful when !skip)
 };
 
-// One iteration of the landmark loop, Update.cpp:103-136. p[0..5] = P(Li+r, j) for r=0..1, j=0..2
-// stored as p[r + 2*j] (this is P_LiR; P_RLi is its exact transpose because P is bit-symmetric);
-// pll = {P(Li,Li), P(Li+1,Li), P(Li,Li+1), P(Li+1,Li+1)}.
-__device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double lx, double ly, const double* p,
-                                                  const double* pll, GateResult& g) {
+// ---- one iteration of the landmark loop, Update.cpp:103-136, in four separable pieces ------------
+// p[0..5] = P(Li+r, j) for r=0..1, j=0..2 stored as p[r + 2*j] (this is P_LiR; P_RLi is its exact
+// transpose because P is bit-symmetric); pll = {P(Li,Li), P(Li+1,Li), P(Li,Li+1), P(Li+1,Li+1)}.
+// S = (((t1 + t2) + t3) + t4) + R in exactly that order; the pieces can run on different lanes.
+struct GatePre {
+  double res0, res1;   // z - z_hat
+  double HR[6];        // H_R (2x3), column-major
+};
+
+__device__ __forceinline__ void ekf_gate_prelude(const UpdateSetup& u, double lx, double ly, GatePre& g) {
   const double d0 = lx - u.x0, d1 = ly - u.x1;
   const double zh0 = u.Ct[0] * d0 + u.Ct[2] * d1;
   const double zh1 = u.Ct[1] * d0 + u.Ct[3] * d1;
@@ -71,9 +95,14 @@ __device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double l
   g.res1 = u.z1 - zh1;
   const double h30 = u.mCtJ[0] * d0 + u.mCtJ[2] * d1;
   const double h31 = u.mCtJ[1] * d0 + u.mCtJ[3] * d1;
-  g.h3_0 = h30; g.h3_1 = h31;
-  // H_R (2x3) column-major
-  const double HR[6] = {u.mCt[0], u.mCt[1], u.mCt[2], u.mCt[3], h30, h31};
+  g.HR[0] = u.mCt[0]; g.HR[1] = u.mCt[1]; g.HR[2] = u.mCt[2]; g.HR[3] = u.mCt[3];
+  g.HR[4] = h30; g.HR[5] = h31;
+}
+
+// t12 = H_R*P_RR*H_R^T + H_Li*P_LiR*H_R^T
+__device__ __forceinline__ void ekf_gate_terms12(const UpdateSetup& u, const GatePre& g, const double* p, double* t12) {
+  const double* HR = g.HR;
+  const double h30 = HR[4], h31 = HR[5];
   // a1 = H_R*P_RR (2x3): ((HR(i,0)*P(0,j) + HR(i,1)*P(1,j)) + HR(i,2)*P(2,j))
   double a1[6];
 #pragma unroll
@@ -81,7 +110,7 @@ __device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double l
     a1[0 + 2 * j] = u.q[0 + 2 * j] + h30 * u.PRR[2 + 3 * j];
     a1[1 + 2 * j] = u.q[1 + 2 * j] + h31 * u.PRR[2 + 3 * j];
   }
-  double t1[4], t2[4], t3[4], t4[4];
+  double t1[4], t2[4];
   // t1 = a1*H_R^T (2x2): t(i,j) = a(i,0)*HR(j,0) + a(i,1)*HR(j,1) + a(i,2)*HR(j,2)
 #pragma unroll
   for (int j = 0; j < 2; ++j)
@@ -99,6 +128,14 @@ __device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double l
 #pragma unroll
     for (int i = 0; i < 2; ++i)
       t2[i + 2 * j] = (a2[i] * HR[j] + a2[i + 2] * HR[j + 2]) + a2[i + 4] * HR[j + 4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t12[k] = t1[k] + t2[k];
+}
+
+// t3 = H_R*P_RLi*H_Li^T, t4 = H_Li*P_LiLi*H_Li^T
+__device__ __forceinline__ void ekf_gate_terms34(const UpdateSetup& u, const GatePre& g, const double* p,
+                                                 const double* pll, double* t3, double* t4) {
+  const double* HR = g.HR;
   // a3 = H_R*P_RLi (2x2), P_RLi(r,j) = P(r, Li+j) = p[j + 2*r]
   double a3[4];
 #pragma unroll
@@ -122,9 +159,15 @@ __device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double l
   for (int j = 0; j < 2; ++j)
 #pragma unroll
     for (int i = 0; i < 2; ++i) t4[i + 2 * j] = a4[i] * Cm[0 + 2 * j] + a4[i + 2] * Cm[1 + 2 * j];
+}
+
+__device__ __forceinline__ void ekf_gate_finish(const UpdateSetup& u, const GatePre& pre, const double* t12,
+                                                const double* t3, const double* t4, double cond_max, GateResult& g) {
+  g.res0 = pre.res0; g.res1 = pre.res1;
+  g.h3_0 = pre.HR[4]; g.h3_1 = pre.HR[5];
   double S[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) S[k] = (((t1[k] + t2[k]) + t3[k]) + t4[k]) + u.R[k];
+  for (int k = 0; k < 4; ++k) S[k] = ((t12[k] + t3[k]) + t4[k]) + u.R[k];
   // S = 0.5*(S + S^T) (Update.cpp:123-124)
   const double s01 = 0.5 * (S[2] + S[1]);
   const double s10 = 0.5 * (S[1] + S[2]);
@@ -132,11 +175,30 @@ __device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double l
   g.S[3] = 0.5 * (S[3] + S[3]);
   g.S[2] = s01;
   g.S[1] = s10;
-  // condition number via 2x2 singular values (Update.cpp:127-128)
+  // condition number via 2x2 singular values (Update.cpp:127-128): cond = (Q+R)/|Q-R| with
+  // Q = sqrt(q2), R = sqrt(r2). Only the comparison cond >= cond_max is ever used (Update.cpp:131).
+  // With rho2 = min(q2,r2)/max(q2,r2), cond >= c  <=>  rho2 >= ((c-1)/(c+1))^2; far from that
+  // boundary (relative margin 1e-9, ~1e6 times the rounding error of the exact evaluation) the
+  // comparison is decided from q2, r2 alone; inside the band, and for NaN / zero radicands, the
+  // reference's sqrt/sqrt/divide sequence is evaluated. The outcome is the same either way.
   const double a = g.S[0], c = g.S[1], b = g.S[2], d = g.S[3];
   const double E = (a + d) * 0.5, F = (a - d) * 0.5, G = (c + b) * 0.5, H = (c - b) * 0.5;
-  const double Q = sqrt(E * E + H * H), Rr = sqrt(F * F + G * G);
-  g.cond = (Q + Rr) / fabs(Q - Rr);
+  const double q2 = E * E + H * H, r2 = F * F + G * G;
+  {
+    const bool ordered = (q2 == q2) && (r2 == r2) && cond_max > 1.0;   // NaN goes down the exact path
+    const double lo = fmin(q2, r2), hi = fmax(q2, r2);
+    const double rr = (cond_max - 1.0) / (cond_max + 1.0);   // uniform: hoisted out of the landmark loop
+    const double thr = rr * rr;
+    if (ordered && lo < (thr * (1.0 - 1e-9)) * hi) {
+      g.skip = false;
+    } else if (ordered && lo > (thr * (1.0 + 1e-9)) * hi) {
+      g.skip = true;
+    } else {
+      const double Q = sqrt(q2), Rr = sqrt(r2);
+      const double cond = (Q + Rr) / fabs(Q - Rr);
+      g.skip = cond >= cond_max;
+    }
+  }
   // Mahalanobis distance (Update.cpp:135-136)
   const double det = a * d - b * c;
   const double invdet = 1.0 / det;
@@ -144,6 +206,16 @@ __device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double l
   const double r0 = g.res0 * i00 + g.res1 * i10;
   const double r1 = g.res0 * i01 + g.res1 * i11;
   g.d2 = r0 * g.res0 + r1 * g.res1;
+}
+
+__device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double lx, double ly, const double* p,
+                                                  const double* pll, double cond_max, GateResult& g) {
+  GatePre pre;
+  double t12[4], t3[4], t4[4];
+  ekf_gate_prelude(u, lx, ly, pre);
+  ekf_gate_terms12(u, pre, p, t12);
+  ekf_gate_terms34(u, pre, p, pll, t3, t4);
+  ekf_gate_finish(u, pre, t12, t3, t4, cond_max, g);
 }
 
 __device__ __forceinline__ void ekf_inv2(const double* S, double* Si) {
@@ -193,24 +265,34 @@ __device__ __forceinline__ void ekf_build_prop(PropSetup& p, double vel_mm_s, do
   p.g21 = -dt;                 // :48
 }
 
+// One element M(i,j) of Phi*P_RR*Phi^T + G*Q*G^T (Propagate.cpp:53), with Phi (3x3), G (3x2),
+// Q (2x2) and the old P_RR (3x3) given column-major. The same expression whether one thread
+// evaluates all nine elements or nine lanes evaluate one each.
+__device__ __forceinline__ double ekf_prop_prr_elem(const double* Phi, const double* G, const double* Q,
+                                                    const double* PRR, int i, int j) {
+  // T1(i,k) = (Phi*PRR)(i,k), k = 0..2
+  const double t10 = (Phi[i] * PRR[0] + Phi[i + 3] * PRR[1]) + Phi[i + 6] * PRR[2];
+  const double t11 = (Phi[i] * PRR[3] + Phi[i + 3] * PRR[4]) + Phi[i + 6] * PRR[5];
+  const double t12 = (Phi[i] * PRR[6] + Phi[i + 3] * PRR[7]) + Phi[i + 6] * PRR[8];
+  // T2(i,j) = sum_k T1(i,k)*Phi(j,k)
+  const double t2 = (t10 * Phi[j] + t11 * Phi[j + 3]) + t12 * Phi[j + 6];
+  // T3(i,c) = (G*Q)(i,c); T4(i,j) = T3(i,0)*G(j,0) + T3(i,1)*G(j,1)
+  const double t30 = G[i] * Q[0] + G[i + 3] * Q[1];
+  const double t31 = G[i] * Q[2] + G[i + 3] * Q[3];
+  const double t4 = t30 * G[j] + t31 * G[j + 3];
+  return t2 + t4;
+}
+
 // P_RR <- Phi*P_RR*Phi^T + G*Q*G^T, then the 3x3 part of 0.5*(P+P^T) (Propagate.cpp:53,66-67).
 // PRR column-major 3x3, in place.
 __device__ __forceinline__ void ekf_prop_prr(const PropSetup& p, double* PRR) {
   const double Phi[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, p.phi02, p.phi12, 1.0};
   const double G[6] = {p.g00, p.g10, 0.0, 0.0, 0.0, p.g21};
-  double T1[9], T2[9], T3[6], T4[9];
-  for (int j = 0; j < 3; ++j)
-    for (int i = 0; i < 3; ++i)
-      T1[i + 3 * j] = (Phi[i] * PRR[3 * j] + Phi[i + 3] * PRR[1 + 3 * j]) + Phi[i + 6] * PRR[2 + 3 * j];
-  for (int j = 0; j < 3; ++j)   // T2 = T1*Phi^T: T2(i,j) = sum_k T1(i,k)*Phi(j,k)
-    for (int i = 0; i < 3; ++i)
-      T2[i + 3 * j] = (T1[i] * Phi[j] + T1[i + 3] * Phi[j + 3]) + T1[i + 6] * Phi[j + 6];
-  for (int j = 0; j < 2; ++j)   // T3 = G*Q (3x2)
-    for (int i = 0; i < 3; ++i) T3[i + 3 * j] = G[i] * p.Q[2 * j] + G[i + 3] * p.Q[1 + 2 * j];
-  for (int j = 0; j < 3; ++j)   // T4 = T3*G^T: T4(i,j) = T3(i,0)*G(j,0) + T3(i,1)*G(j,1)
-    for (int i = 0; i < 3; ++i) T4[i + 3 * j] = T3[i] * G[j] + T3[i + 3] * G[j + 3];
   double M[9];
-  for (int k = 0; k < 9; ++k) M[k] = T2[k] + T4[k];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) M[i + 3 * j] = ekf_prop_prr_elem(Phi, G, p.Q, PRR, i, j);
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 3; ++i) PRR[i + 3 * j] = 0.5 * (M[i + 3 * j] + M[j + 3 * i]);
 }

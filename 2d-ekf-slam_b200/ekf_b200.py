@@ -121,6 +121,7 @@ def core_lib():
         L.ekf_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.ekf_measure_fp64_peak.argtypes = [C.c_int, c_dp]
+        L.ekf_debug_phase_cycles.argtypes = [C.POINTER(C.c_longlong)]
         _core = L
     return _core
 
@@ -374,6 +375,16 @@ def device_info(device=0):
     if rc:
         raise EkfError(rc, "ekf_device_info failed (no CUDA device?)")
     return {"sm_count": sm.value, "cc": (maj.value, mnr.value), "smem_optin": smem.value, "total_mem": mem.value}
+
+
+def debug_phase_cycles(read=True):
+    """Per-phase cycle counters of the register-tile kernel (CTA 0); first call enables them."""
+    if not read:
+        core_lib().ekf_debug_phase_cycles(None)
+        return None
+    buf = (C.c_longlong * 8)()
+    core_lib().ekf_debug_phase_cycles(buf)
+    return list(buf)
 
 
 def measure_fp64_peak(device=0):

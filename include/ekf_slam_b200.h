@@ -161,6 +161,11 @@ int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, siz
 /* DFMA-chain microbenchmark on `device`: achieved FP64 FLOP/s (2 flop per DFMA). Used as the
  * measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int ekf_measure_fp64_peak(int device, double* flops_per_s);
+/* Profiling aid for the register-tile fused kernel: the first call (out8 may be NULL) enables
+ * per-phase cycle accumulation by CTA 0 of every following launch; later calls read and clear the
+ * eight counters {scalar chains, covariance propagate, gating, column publish, gain rows, downdate,
+ * step epilogue, unused}. */
+int ekf_debug_phase_cycles(long long* out8);
 
 #ifdef __cplusplus
 }

@@ -21,9 +21,21 @@ def batch(F=592, T=1000, cap=50):
     rec = syn.generate(F, T)
     fb = ekf.FilterBatch(F, cap)
     fb.upload_records(rec, 1)
-    for _ in range(3):                     # lap 0 builds the maps, laps 1-2 are full size
+    for lap in range(3):                   # lap 0 builds the maps, laps 1-2 are full size
+        if lap == 2 and os.environ.get("EKF_PHASES"):
+            fb.sync()
+            ekf.debug_phase_cycles(read=False)
         fb.run_resident(trace=True)
     out = fb.download_outputs(trace=True)
+    if os.environ.get("EKF_PHASES"):
+        cyc = ekf.debug_phase_cycles()
+        names = ["scalar chains", "cov propagate+publish", "gating", "decision+column publish", "gain rows",
+                 "downdate+publish", "step epilogue", "-"]
+        per = -(-F // (2 * 148))           # filters CTA 0 processed
+        print("phase cycles per step (CTA 0, %d filter(s) x %d steps):" % (per, T))
+        for n, c in zip(names, cyc):
+            print("  %-26s %8.0f" % (n, c / (per * T)))
+        print("  %-26s %8.0f" % ("total", sum(cyc) / (per * T)))
     assert (out["final_nlm"] == 50).mean() > 0.99
     ms, n = fb.kernel_time()
     print("batch: F=%d T=%d avg kernel %.3f ms over %d launches -> %.3e filter-steps/s"
