@@ -305,6 +305,11 @@ int ekf_reset(ekf_handle h) {
 int ekf_n_filters(ekf_handle h) { return h ? h->st.F : 0; }
 int ekf_max_landmarks(ekf_handle h) { return h ? h->st.cap_lm : 0; }
 int ekf_regime(ekf_handle h) { return h ? h->regime : 0; }
+int ekf_set_batch_kernel(ekf_handle h, int batch_kernel) {
+  if (!h || batch_kernel < EKF_BATCH_KERNEL_AUTO || batch_kernel > EKF_BATCH_KERNEL_TILE) return EKF_ERR_BAD_ARG;
+  h->cfg.batch_kernel = batch_kernel;
+  return EKF_OK;
+}
 
 int ekf_set_state(ekf_handle h, int filter, int n_landmarks, const double* x, const double* P, int ld) {
   if (!h || !x || !P) return EKF_ERR_BAD_ARG;

@@ -194,6 +194,20 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
   const bool timing = a.phase_cycles != nullptr && blockIdx.x == 0 && tid == 0;
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = 0;
+#ifdef EKF_FINE_TIMING
+  long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long fprev = 0;
+#define EKF_FINE0 if (timing) fprev = clock64();
+#define EKF_FINE(i)                                   \
+  if (timing) {                                       \
+    const long long now = clock64();                  \
+    facc[i] += now - fprev;                           \
+    fprev = now;                                      \
+  }
+#else
+#define EKF_FINE0
+#define EKF_FINE(i)
+#endif
 #define EKF_PHASE(i)                                  \
   if (timing) {                                       \
     const long long now = clock64();                  \
@@ -347,6 +361,7 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
           }
           setup_valid = false;  // whatever happens next, a further measurement needs a fresh set-up
           // ---- gating: group A (warps 0..GA-1) and group B (warps GA..2GA-1), one landmark per lane --
+          EKF_FINE0
           if (warp < 2 * C::GA) {
             const bool groupA = warp < C::GA;
             const int lm = (groupA ? warp : warp - C::GA) * 32 + lane;
@@ -361,6 +376,7 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
               pp[4] = sm.s2[Li]; pp[5] = sm.s2[Li + 1];
               ekf_gate_prelude(u, sm.xs[Li], sm.xs[Li + 1], pre);
             }
+            EKF_FINE(0)   // loads + prelude
             double t12[4];
             if (groupA) {
               if (have) ekf_gate_terms12(u, pre, pp, t12);
@@ -372,7 +388,9 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
 #pragma unroll
               for (int q = 0; q < 4; ++q) { sm.t34[q][lm] = t3[q]; sm.t34[4 + q][lm] = t4[q]; }
             }
+            EKF_FINE(1)   // terms
             named_barrier(1, 2 * C::GA * 32);
+            EKF_FINE(2)   // group barrier
             if (groupA) {
               double val = INFINITY;
               int idx = INT_MAX;
@@ -385,6 +403,7 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
                 const bool valid = !g.skip && (k.mahal_init > g.d2);   // Update.cpp:131,140
                 if (valid) { val = g.d2; idx = Li; }
               }
+              EKF_FINE(3)   // finish
               const int my_idx = idx;
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) {     // lowest index wins ties (Update.cpp:140)
@@ -392,6 +411,7 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
                 const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
                 if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
               }
+              EKF_FINE(4)   // warp argmin
               Candidate& cd = sm.cand[warp];
               if (idx == INT_MAX) {
                 if (lane == 0) { cd.val = INFINITY; cd.idx = INT_MAX; }
@@ -403,7 +423,9 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
               }
             }
           }
+          EKF_FINE(5)   // candidate store
           __syncthreads();
+          EKF_FINE(6)   // CTA barrier
           EKF_PHASE(2)   // gating
           // ---- decision (Update.cpp:152,181,191), uniform over the CTA -----------------------------
           int wsel = 0;
@@ -585,6 +607,10 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
     }
     if (timing)
       for (int i = 0; i < 8; ++i) a.phase_cycles[i] += tacc[i];
+#ifdef EKF_FINE_TIMING
+    if (timing)
+      for (int i = 0; i < 8; ++i) a.phase_cycles[8 + i] += facc[i];
+#endif
 
     // ---- write back to HBM (external layout, both triangles) -------------------------------------
     {
@@ -639,14 +665,14 @@ int ekf_tile_max_landmarks() { return TileCfg<16>::MAX_LM; }
 // the eight counters back. Passing out == nullptr only enables.
 cudaError_t ekf_tile_phase_cycles(long long* out) {
   if (!g_phase_cycles) {
-    cudaError_t e = cudaMalloc(&g_phase_cycles, 8 * sizeof(long long));
+    cudaError_t e = cudaMalloc(&g_phase_cycles, 16 * sizeof(long long));
     if (e != cudaSuccess) return e;
-    cudaMemset(g_phase_cycles, 0, 8 * sizeof(long long));
+    cudaMemset(g_phase_cycles, 0, 16 * sizeof(long long));
   }
   if (out) {
-    cudaError_t e = cudaMemcpy(out, g_phase_cycles, 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(out, g_phase_cycles, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return e;
-    cudaMemset(g_phase_cycles, 0, 8 * sizeof(long long));
+    cudaMemset(g_phase_cycles, 0, 16 * sizeof(long long));
   }
   return cudaSuccess;
 }

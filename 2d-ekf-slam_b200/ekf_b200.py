@@ -96,6 +96,7 @@ def core_lib():
         L.ekf_n_filters.argtypes = [H]
         L.ekf_max_landmarks.argtypes = [H]
         L.ekf_regime.argtypes = [H]
+        L.ekf_set_batch_kernel.argtypes = [H, C.c_int]
         L.ekf_set_state.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, C.c_int]
         L.ekf_get_state.argtypes = [H, C.c_int, C.POINTER(C.c_int), c_dp, c_dp, C.c_int]
         L.ekf_get_pose.argtypes = [H, c_dp, c_ip]
@@ -231,6 +232,9 @@ class FilterBatch:
     @property
     def regime(self):
         return self.L.ekf_regime(self.h)
+
+    def set_batch_kernel(self, kernel):
+        self._chk(self.L.ekf_set_batch_kernel(self.h, kernel))
 
     def reset(self):
         self._chk(self.L.ekf_reset(self.h))
@@ -382,7 +386,7 @@ def debug_phase_cycles(read=True):
     if not read:
         core_lib().ekf_debug_phase_cycles(None)
         return None
-    buf = (C.c_longlong * 8)()
+    buf = (C.c_longlong * 16)()
     core_lib().ekf_debug_phase_cycles(buf)
     return list(buf)
 

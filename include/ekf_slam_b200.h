@@ -97,6 +97,7 @@ int ekf_reset(ekf_handle h);                       /* back to kalmanfilter.cpp:7
 int ekf_n_filters(ekf_handle h);
 int ekf_max_landmarks(ekf_handle h);
 int ekf_regime(ekf_handle h);                      /* the regime actually selected */
+int ekf_set_batch_kernel(ekf_handle h, int batch_kernel);   /* EKF_BATCH_KERNEL_*, for later fused runs */
 
 /* ---- state access (also checkpoint / state injection) -------------------------------------- */
 /* The reference keeps state/covariance private (kalmanfilter.h:37-38); these are the harness
@@ -163,9 +164,9 @@ int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, siz
 int ekf_measure_fp64_peak(int device, double* flops_per_s);
 /* Profiling aid for the register-tile fused kernel: the first call (out8 may be NULL) enables
  * per-phase cycle accumulation by CTA 0 of every following launch; later calls read and clear the
- * eight counters {scalar chains, covariance propagate, gating, column publish, gain rows, downdate,
- * step epilogue, unused}. */
-int ekf_debug_phase_cycles(long long* out8);
+ * sixteen counters {scalar chains, covariance propagate, gating, column publish, gain rows,
+ * downdate, step epilogue, unused, then eight finer gating probes (only in -DEKF_FINE_TIMING builds)}. */
+int ekf_debug_phase_cycles(long long* out16);
 
 #ifdef __cplusplus
 }

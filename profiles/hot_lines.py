@@ -23,3 +23,16 @@ print("total samples %d, total warp-instructions %d" % (tot, toti))
 for s, ie, f, ln, src, st in sorted(lines, key=lambda l: -l[0])[:top]:
     top3 = ", ".join("%s %d%%" % (k, 100 * v // max(s, 1)) for k, v in sorted(st.items(), key=lambda x: -x[1])[:3])
     print("%5.1f%% smp %5.1f%% inst  %-14s:%-4s %-90s [%s]" % (100.0 * s / tot, 100.0 * ie / toti, f, ln, src, top3))
+
+# ---- stall mix of the gating / set-up arithmetic (ekf_small.cuh), i.e. of the warps others wait for ---
+import collections
+agg = collections.defaultdict(collections.Counter)
+inst = collections.Counter()
+for s_, ie, f, ln, src, st in lines:
+    if f == "ekf_small.cuh":
+        r = "small:gating(85-225)" if 85 <= int(ln) <= 225 else "small:prop/setup"
+        agg[r].update(st)
+        inst[r] += ie
+for r, c in agg.items():
+    t = sum(c.values()) or 1
+    print("%-22s samples %6d inst %.2e :" % (r, t, inst[r]), ", ".join("%s %d%%" % (k, 100 * v // t) for k, v in c.most_common(6)))

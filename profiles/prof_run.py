@@ -21,7 +21,11 @@ def batch(F=592, T=1000, cap=50):
     rec = syn.generate(F, T)
     fb = ekf.FilterBatch(F, cap)
     fb.upload_records(rec, 1)
+    if os.environ.get("EKF_BUILD_WITH_SMEM"):   # experiment builds of the tile kernel without the New path
+        fb.set_batch_kernel(1)
     for lap in range(3):                   # lap 0 builds the maps, laps 1-2 are full size
+        if lap == 1:
+            fb.set_batch_kernel(0)
         if lap == 2 and os.environ.get("EKF_PHASES"):
             fb.sync()
             ekf.debug_phase_cycles(read=False)
@@ -33,9 +37,14 @@ def batch(F=592, T=1000, cap=50):
                  "downdate+publish", "step epilogue", "-"]
         per = -(-F // (2 * 148))           # filters CTA 0 processed
         print("phase cycles per step (CTA 0, %d filter(s) x %d steps):" % (per, T))
-        for n, c in zip(names, cyc):
+        for n, c in zip(names, cyc[:8]):
             print("  %-26s %8.0f" % (n, c / (per * T)))
-        print("  %-26s %8.0f" % ("total", sum(cyc) / (per * T)))
+        print("  %-26s %8.0f" % ("total", sum(cyc[:8]) / (per * T)))
+        if any(cyc[8:]):
+            fine = ["gate: loads+prelude", "gate: S terms", "gate: group barrier", "gate: finish", "gate: warp argmin",
+                    "gate: candidate store", "gate: CTA barrier", "-"]
+            for n, c in zip(fine, cyc[8:]):
+                print("    %-24s %8.0f" % (n, c / (per * T)))
     assert (out["final_nlm"] == 50).mean() > 0.99
     ms, n = fb.kernel_time()
     print("batch: F=%d T=%d avg kernel %.3f ms over %d launches -> %.3e filter-steps/s"
