@@ -37,6 +37,7 @@ struct DevBuf {
 };
 
 constexpr int kTimingPairs = 64;
+constexpr int kMaxChunks = 16;
 
 }  // namespace
 
@@ -45,6 +46,8 @@ struct ekf_handle_s {
   int regime = EKF_REGIME_BATCH;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy engines of the pipelined end-to-end path
+  cudaEvent_t ev_in[kMaxChunks], ev_k[kMaxChunks], ev_done = nullptr;
   EkfConst k{};
   ekf_config cfg{};
   EkfState st{};
@@ -242,6 +245,13 @@ int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, co
   if ((e = cudaMalloc(&st.status, (size_t)n_filters * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+  for (int i = 0; i < kMaxChunks; ++i) {
+    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
+  }
   for (int i = 0; i < kTimingPairs; ++i) {
     cudaEventCreate(&h->kev0[i]);
     cudaEventCreate(&h->kev1[i]);
@@ -281,6 +291,13 @@ int ekf_destroy(ekf_handle h) {
   if (h->ev0) {
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev_done);
+    for (int i = 0; i < kMaxChunks; ++i) {
+      cudaEventDestroy(h->ev_in[i]);
+      cudaEventDestroy(h->ev_k[i]);
+    }
+    cudaStreamDestroy(h->s_in);
+    cudaStreamDestroy(h->s_out);
     for (int i = 0; i < kTimingPairs; ++i) {
       cudaEventDestroy(h->kev0[i]);
       cudaEventDestroy(h->kev1[i]);
@@ -503,7 +520,79 @@ int ekf_download_outputs(ekf_handle h, const ekf_run_outputs* out) {
   return download(h, out);
 }
 
+// End-to-end run of the batch regime, pipelined over chunks of filters: the H2D copy of chunk c+1
+// and the D2H copy of chunk c-1 overlap the kernel of chunk c (three streams, two copy engines).
+// Filters are independent, so a chunk is just a sub-range of the batch.
+static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out) {
+  const EkfState& st = h->st;
+  const int L = EKF_RECORD_LEN(max_meas), M = max_meas > 0 ? max_meas : 1, T = n_steps;
+  const size_t F = st.F, FT = F * T, FTM = FT * M;
+  EKF_CK(h, h->records.reserve(FT * L));
+  h->rec_T = T; h->rec_M = max_meas; h->rec_L = L;
+  const bool want_trace = out && (out->decision || out->lm_index || out->mahal);
+  const bool want_pose = out && out->pose_trace;
+  h->have_trace = want_trace;
+  h->have_pose_trace = want_pose;
+  if (want_trace) {
+    EKF_CK(h, h->t_dec.reserve(FTM));
+    EKF_CK(h, h->t_idx.reserve(FTM));
+    EKF_CK(h, h->t_mah.reserve(FTM));
+  }
+  if (want_pose) EKF_CK(h, h->t_pose.reserve(FT * 3));
+  const bool tile = h->cfg.batch_kernel != EKF_BATCH_KERNEL_SMEM && st.cap_lm <= ekf_tile_max_landmarks();
+  // chunk = a multiple of the co-resident CTA count (2 filters per CTA), at most kMaxChunks chunks
+  const size_t wave = (size_t)(tile ? 2 * h->sm_count : h->grid_cap);
+  size_t chunk = 2 * wave;
+  while ((F + chunk - 1) / chunk > (size_t)kMaxChunks) chunk += wave;
+  const int n_chunks = (int)((F + chunk - 1) / chunk);
+  EKF_CK(h, cudaEventRecord(h->ev_done, h->stream));          // order after earlier work on the handle
+  EKF_CK(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t f0 = (size_t)c * chunk, nf = (f0 + chunk <= F) ? chunk : F - f0;
+    EKF_CK(h, cudaMemcpyAsync(h->records.p + f0 * T * L, records + f0 * T * L, nf * T * L * sizeof(double),
+                              cudaMemcpyHostToDevice, h->s_in));
+    EKF_CK(h, cudaEventRecord(h->ev_in[c], h->s_in));
+    EKF_CK(h, cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+    EkfState sub = st;
+    sub.F = (int)nf;
+    sub.x = st.x + f0 * st.xs;
+    sub.P = st.P + f0 * st.slab;
+    sub.nlm = st.nlm + f0;
+    sub.status = st.status + f0;
+    EkfRunIO io{};
+    io.records = h->records.p + f0 * T * L;
+    io.T = T; io.M = max_meas; io.L = L;
+    if (want_trace) { io.decision = h->t_dec.p + f0 * T * M; io.index = h->t_idx.p + f0 * T * M; io.mahal = h->t_mah.p + f0 * T * M; }
+    if (want_pose) io.pose_trace = h->t_pose.p + f0 * T * 3;
+    kernel_event_begin(h);
+    if (tile) EKF_CK(h, ekf_tile_run(sub, io, h->k, h->sm_count, h->stream));
+    else EKF_CK(h, ekf_batch_run(sub, io, h->k, h->grid_cap, h->stream));
+    kernel_event_end(h);
+    h->launches += 1;
+    EKF_CK(h, cudaEventRecord(h->ev_k[c], h->stream));
+    EKF_CK(h, cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+    if (out) {
+      cudaStream_t so = h->s_out;
+      if (out->decision) EKF_CK(h, cudaMemcpyAsync(out->decision + f0 * T * M, h->t_dec.p + f0 * T * M, nf * T * M * sizeof(int), cudaMemcpyDeviceToHost, so));
+      if (out->lm_index) EKF_CK(h, cudaMemcpyAsync(out->lm_index + f0 * T * M, h->t_idx.p + f0 * T * M, nf * T * M * sizeof(int), cudaMemcpyDeviceToHost, so));
+      if (out->mahal) EKF_CK(h, cudaMemcpyAsync(out->mahal + f0 * T * M, h->t_mah.p + f0 * T * M, nf * T * M * sizeof(double), cudaMemcpyDeviceToHost, so));
+      if (out->pose_trace) EKF_CK(h, cudaMemcpyAsync(out->pose_trace + f0 * T * 3, h->t_pose.p + f0 * T * 3, nf * T * 3 * sizeof(double), cudaMemcpyDeviceToHost, so));
+      if (out->final_pose)
+        EKF_CK(h, cudaMemcpy2DAsync(out->final_pose + f0 * 3, 3 * sizeof(double), st.x + f0 * st.xs, st.xs * sizeof(double),
+                                    3 * sizeof(double), nf, cudaMemcpyDeviceToHost, so));
+      if (out->final_nlm) EKF_CK(h, cudaMemcpyAsync(out->final_nlm + f0, st.nlm + f0, nf * sizeof(int), cudaMemcpyDeviceToHost, so));
+    }
+  }
+  EKF_CK(h, cudaStreamSynchronize(h->s_out));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  return check_status(h);
+}
+
 int ekf_run(ekf_handle h, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out) {
+  if (h && records && h->regime == EKF_REGIME_BATCH && n_steps >= 1 && max_meas >= 0 && max_meas <= EKF_MAX_MEAS) {
+    cudaSetDevice(h->device);
+    return run_pipelined(h, n_steps, max_meas, records, out);
+  }
   int rc = ekf_upload_records(h, n_steps, max_meas, records);
   if (rc != EKF_OK) return rc;
   const bool want_trace = out && (out->decision || out->lm_index || out->mahal);
