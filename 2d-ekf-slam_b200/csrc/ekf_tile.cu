@@ -191,9 +191,14 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
   const int ld = a.st.ld, L = a.io.L, T = a.io.T, M = a.io.M;
   const EkfConst& k = a.k;
   double p[4][8];
+#ifdef EKF_TILE_TIMING   // profiling builds only (make EXTRA=-DEKF_TILE_TIMING): the probes cost registers
   const bool timing = a.phase_cycles != nullptr && blockIdx.x == 0 && tid == 0;
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = 0;
+#else
+  constexpr bool timing = false;
+  (void)timing;
+#endif
 #ifdef EKF_FINE_TIMING
   long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long fprev = 0;
@@ -208,12 +213,16 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
 #define EKF_FINE0
 #define EKF_FINE(i)
 #endif
+#ifdef EKF_TILE_TIMING
 #define EKF_PHASE(i)                                  \
   if (timing) {                                       \
     const long long now = clock64();                  \
     tacc[i] += now - tprev;                           \
     tprev = now;                                      \
   }
+#else
+#define EKF_PHASE(i)
+#endif
 
   for (int f = blockIdx.x; f < a.st.F; f += gridDim.x) {
     double* gP = a.st.P + (size_t)f * a.st.slab;
@@ -240,18 +249,13 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
     }
     __syncthreads();
 
-    if (timing) tprev = clock64();
-    for (int t = 0; t < T; ++t) {
-      const double* cur = sm.rec[t & 1];
-      if (t + 1 < T) {
-        const double* g = grec + (size_t)(t + 1) * L;
-        for (int i = tid; i < L; i += C::THREADS) cp_async8(&sm.rec[(t + 1) & 1][i], g + i);
-      }
-      // ---- doPropagation (slam.cpp:136): the two scalar chains run on different warps ------------
-      const int nz = (int)cur[5];
+    // Scalar chains of one step (kalmanfilter.cpp:17-37, Propagate.cpp:33-48, Update.cpp:89-95):
+    // thread sc_prop builds Q, Phi, G and the propagated pose, thread sc_trig the rotation blocks
+    // for the post-propagation heading and the first measurement of the step.
+    auto scalar_chains = [&](const double* rec) {
       if (sc_prop) {
         PropSetup ps;
-        ekf_build_prop(ps, cur[0], cur[1], cur[2], sm.xs[2], k);
+        ekf_build_prop(ps, rec[0], rec[1], rec[2], sm.xs[2], k);
         sm.prop = ps;
         sm.PhiS[0] = 1.0; sm.PhiS[1] = 0.0; sm.PhiS[2] = 0.0;           // Propagate.cpp:42-44
         sm.PhiS[3] = 0.0; sm.PhiS[4] = 1.0; sm.PhiS[5] = 0.0;
@@ -265,20 +269,40 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
       }
       if (sc_trig) {
         // the heading the update will see: same expression as above, so the same bits
-        const double RTV = cur[1] * k.deg2rad_pi / 180.0;
-        const double phi_new = sm.xs[2] + cur[2] * RTV;
+        const double RTV = rec[1] * k.deg2rad_pi / 180.0;
+        const double phi_new = sm.xs[2] + rec[2] * RTV;
         UpdateTrig tg;
         ekf_build_trig(tg, phi_new);
         UpdateSetup& u = sm.upd;
         u.c = tg.c; u.s = tg.s;
         for (int q = 0; q < 4; ++q) { u.Ct[q] = tg.Ct[q]; u.mCt[q] = tg.mCt[q]; u.mCtJ[q] = tg.mCtJ[q]; }
-        if (nz > 0) {                                  // first measurement of the step
-          u.z0 = cur[8]; u.z1 = cur[9];
-          for (int q = 0; q < 4; ++q) u.R[q] = cur[10 + q];
+        if ((int)rec[5] > 0) {                         // first measurement of the step
+          u.z0 = rec[8]; u.z1 = rec[9];
+          for (int q = 0; q < 4; ++q) u.R[q] = rec[10 + q];
         }
       }
-      __syncthreads();
-      EKF_PHASE(0)   // scalar chains
+    };
+    bool scalar_done = false;
+
+#ifdef EKF_TILE_TIMING
+    if (timing) tprev = clock64();
+#endif
+    for (int t = 0; t < T; ++t) {
+      const double* cur = sm.rec[t & 1];
+      if (t + 1 < T) {
+        const double* g = grec + (size_t)(t + 1) * L;
+        for (int i = tid; i < L; i += C::THREADS) cp_async8(&sm.rec[(t + 1) & 1][i], g + i);
+      }
+      // ---- doPropagation (slam.cpp:136): the two scalar chains run on different warps. They only
+      // need the final state of the previous step and the record, so when the previous step ended
+      // with an Old update they have already run, overlapped with that step's covariance downdate.
+      const int nz = (int)cur[5];
+      if (!scalar_done) {
+        scalar_chains(cur);
+        __syncthreads();
+      }
+      scalar_done = false;
+      EKF_PHASE(0)   // scalar chains (when not overlapped)
       if (sc_prop) {
         sm.xs[0] = sm.xnew[0]; sm.xs[1] = sm.xnew[1]; sm.xs[2] = sm.xnew[2];
         sm.upd.x0 = sm.xnew[0]; sm.upd.x1 = sm.xnew[1];
@@ -404,14 +428,19 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
                 if (valid) { val = g.d2; idx = Li; }
               }
               EKF_FINE(3)   // finish
+              // warp argmin with lowest-index tie break (Update.cpp:140) on an order-preserving integer
+              // key of the distance: three REDUX operations instead of five shuffle rounds.
               const int my_idx = idx;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {     // lowest index wins ties (Update.cpp:140)
-                const double ov = __shfl_xor_sync(0xffffffffu, val, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-                if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+              {
+                const double v = val + 0.0;                        // -0 -> +0 (they compare equal)
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+                const unsigned long long key = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+                const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+                const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+                const bool best = hi == mhi && lo == mlo;
+                idx = (int)__reduce_min_sync(0xffffffffu, best ? (unsigned)my_idx : (unsigned)INT_MAX);
               }
-              EKF_FINE(4)   // warp argmin
               Candidate& cd = sm.cand[warp];
               if (idx == INT_MAX) {
                 if (lane == 0) { cd.val = INFINITY; cd.idx = INT_MAX; }
@@ -509,8 +538,15 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
                 sm.W[widx<NB>(r)] = w;
               }
             }
+            cp_async_wait_all();   // next step's record (prefetched at step start) is visible after the barrier
             __syncthreads();
             EKF_PHASE(4)   // gain rows
+            // x is final for this step if this was its last measurement: run the next step's scalar
+            // chains now, on two threads, while every warp does its covariance downdate.
+            if (m == nz - 1 && t + 1 < T) {
+              scalar_chains(sm.rec[(t + 1) & 1]);
+              scalar_done = true;
+            }
             // ---- covariance downdate in registers (Update.cpp:188,193-194) -------------------------
             if (is_tile && 4 * I < 4 + 2 * n_lm) tile_downdate<NB, 2>(sm, p, I, J, sm.post.m0, sm.post.m1);
             publish<NB>(sm, p, is_tile, I, J);
@@ -605,8 +641,10 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
       __syncthreads();
       EKF_PHASE(6)   // trace output, record prefetch wait, end-of-step barrier
     }
+#ifdef EKF_TILE_TIMING
     if (timing)
       for (int i = 0; i < 8; ++i) a.phase_cycles[i] += tacc[i];
+#endif
 #ifdef EKF_FINE_TIMING
     if (timing)
       for (int i = 0; i < 8; ++i) a.phase_cycles[8 + i] += facc[i];

@@ -386,7 +386,7 @@ def debug_phase_cycles(read=True):
     if not read:
         core_lib().ekf_debug_phase_cycles(None)
         return None
-    buf = (C.c_longlong * 16)()
+    buf = (C.c_longlong * 32)()
     core_lib().ekf_debug_phase_cycles(buf)
     return list(buf)
 

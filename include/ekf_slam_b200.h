@@ -164,9 +164,9 @@ int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, siz
 int ekf_measure_fp64_peak(int device, double* flops_per_s);
 /* Profiling aid for the register-tile fused kernel: the first call (out8 may be NULL) enables
  * per-phase cycle accumulation by CTA 0 of every following launch; later calls read and clear the
- * sixteen counters {scalar chains, covariance propagate, gating, column publish, gain rows,
- * downdate, step epilogue, unused, then eight finer gating probes (only in -DEKF_FINE_TIMING builds)}. */
-int ekf_debug_phase_cycles(long long* out16);
+ * 32 counters {scalar chains, covariance propagate, gating, column publish, gain rows,
+ * downdate, step epilogue, unused, then 24 finer probes along thread 0 (only in -DEKF_FINE_TIMING builds)}. */
+int ekf_debug_phase_cycles(long long* out32);
 
 #ifdef __cplusplus
 }

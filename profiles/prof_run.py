@@ -42,7 +42,10 @@ def batch(F=592, T=1000, cap=50):
         print("  %-26s %8.0f" % ("total", sum(cyc[:8]) / (per * T)))
         if any(cyc[8:]):
             fine = ["gate: loads+prelude", "gate: S terms", "gate: group barrier", "gate: finish", "gate: warp argmin",
-                    "gate: candidate store", "gate: CTA barrier", "-"]
+                    "gate: candidate store", "gate: CTA barrier", "decision", "col publish (own)", "barrier (post thread)",
+                    "gain row (own)", "barrier", "downdate (own tile)", "publish (own)", "barrier", "trace stores",
+                    "cp.async wait", "end-of-step barrier", "step start (own)", "barrier (scalar chains)",
+                    "propagate (own)", "barrier (robot block/strip)", "-", "-"]
             for n, c in zip(fine, cyc[8:]):
                 print("    %-24s %8.0f" % (n, c / (per * T)))
     assert (out["final_nlm"] == 50).mean() > 0.99
