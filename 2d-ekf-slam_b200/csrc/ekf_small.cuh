@@ -37,9 +37,7 @@ struct UpdateTrig {
   double Ct[4], mCt[4], mCtJ[4];
 };
 
-__device__ __forceinline__ void ekf_build_trig(UpdateTrig& t, double phi) {
-  double s, c;
-  sincos(phi, &s, &c);
+__device__ __forceinline__ void ekf_build_trig_sc(UpdateTrig& t, double s, double c) {
   t.c = c; t.s = s;
   // C << cos,-sin,sin,cos (Update.cpp:90); C^T
   t.Ct[0] = c;  t.Ct[1] = -s; t.Ct[2] = s;  t.Ct[3] = c;
@@ -50,6 +48,12 @@ __device__ __forceinline__ void ekf_build_trig(UpdateTrig& t, double phi) {
   t.mCtJ[1] = t.mCt[1] * J00 + t.mCt[3] * J10;
   t.mCtJ[2] = t.mCt[0] * J01 + t.mCt[2] * J11;
   t.mCtJ[3] = t.mCt[1] * J01 + t.mCt[3] * J11;
+}
+
+__device__ __forceinline__ void ekf_build_trig(UpdateTrig& t, double phi) {
+  double s, c;
+  sincos(phi, &s, &c);
+  ekf_build_trig_sc(t, s, c);
 }
 
 __device__ __forceinline__ void ekf_complete_setup(UpdateSetup& u, const UpdateTrig& t, double x0, double x1,
@@ -244,8 +248,9 @@ struct PropSetup {
   double g00, g10, g21; // G(0,0), G(1,0), G(2,1)
 };
 
-__device__ __forceinline__ void ekf_build_prop(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,
-                                               double ori, const EkfConst& k) {
+// (s, c) = sincos of the pre-propagation heading, computed by the caller.
+__device__ __forceinline__ void ekf_build_prop_sc(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,
+                                                  double s, double c, const EkfConst& k) {
   const double RTV = rotvel_deg_s * k.deg2rad_pi / 180.0;   // kalmanfilter.cpp:19
   p.v = vel_mm_s / 1000.0;                                   // :26
   p.w = RTV;
@@ -257,12 +262,19 @@ __device__ __forceinline__ void ekf_build_prop(PropSetup& p, double vel_mm_s, do
   for (int i = 0; i < 4; ++i) A[i] = vv * Q0[i];
   for (int j = 0; j < 2; ++j)
     for (int i = 0; i < 2; ++i) p.Q[i + 2 * j] = A[i] * Q0[0 + 2 * j] + A[i + 2] * Q0[1 + 2 * j];
-  sincos(ori, &p.s, &p.c);
+  p.s = s; p.c = c;
   p.phi02 = -dt * p.v * p.s;   // Propagate.cpp:42
   p.phi12 = dt * p.v * p.c;    // :43
   p.g00 = -dt * p.c;           // :46
   p.g10 = -dt * p.s;           // :47
   p.g21 = -dt;                 // :48
+}
+
+__device__ __forceinline__ void ekf_build_prop(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,
+                                               double ori, const EkfConst& k) {
+  double s, c;
+  sincos(ori, &s, &c);
+  ekf_build_prop_sc(p, vel_mm_s, rotvel_deg_s, dt, s, c, k);
 }
 
 // One element M(i,j) of Phi*P_RR*Phi^T + G*Q*G^T (Propagate.cpp:53), with Phi (3x3), G (3x2),

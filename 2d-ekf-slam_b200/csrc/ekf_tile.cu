@@ -180,8 +180,11 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
   __shared__ __align__(16) TileSmem<NB> sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_tile = tid < C::NTILES;
-  const bool sc_prop = tid == (C::NW - 1) * 32;     // scalar chain 1: propagate set-up
-  const bool sc_trig = tid == (C::NW - 2) * 32;     // scalar chain 2: heading trig for the update
+  // The last warp has THREADS - NTILES >= 10 lanes without a tile: they carry the scalar work.
+  constexpr int SP0 = C::NTILES - (C::NW - 1) * 32;           // first spare lane of the last warp
+  const bool helper_warp = warp == C::NW - 1;
+  const bool sc_prop = helper_warp && lane == SP0;            // scalar chain 1: propagate set-up
+  const bool sc_trig = helper_warp && lane == SP0 + 1;        // scalar chain 2: heading trig for the update
   int I = 0, J = 0;
   if (is_tile) {                                    // tid = sum_{i<I}(i/2+1) + J
     int t = tid;
@@ -253,32 +256,37 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
     // thread sc_prop builds Q, Phi, G and the propagated pose, thread sc_trig the rotation blocks
     // for the post-propagation heading and the first measurement of the step.
     auto scalar_chains = [&](const double* rec) {
-      if (sc_prop) {
-        PropSetup ps;
-        ekf_build_prop(ps, rec[0], rec[1], rec[2], sm.xs[2], k);
-        sm.prop = ps;
-        sm.PhiS[0] = 1.0; sm.PhiS[1] = 0.0; sm.PhiS[2] = 0.0;           // Propagate.cpp:42-44
-        sm.PhiS[3] = 0.0; sm.PhiS[4] = 1.0; sm.PhiS[5] = 0.0;
-        sm.PhiS[6] = ps.phi02; sm.PhiS[7] = ps.phi12; sm.PhiS[8] = 1.0;
-        sm.GS[0] = ps.g00; sm.GS[1] = ps.g10; sm.GS[2] = 0.0;            // :46-48
-        sm.GS[3] = 0.0; sm.GS[4] = 0.0; sm.GS[5] = ps.g21;
-        const double xm0 = ps.v * ps.c, xm1 = ps.v * ps.s, xm2 = ps.w;   // Propagate.cpp:33-37
-        sm.xnew[0] = sm.xs[0] + ps.dt * xm0;
-        sm.xnew[1] = sm.xs[1] + ps.dt * xm1;
-        sm.xnew[2] = sm.xs[2] + ps.dt * xm2;
-      }
-      if (sc_trig) {
-        // the heading the update will see: same expression as above, so the same bits
+      if (sc_prop || sc_trig) {
+        // the two lanes share one sincos instruction stream: lane SP0 takes the pre-propagation
+        // heading, lane SP0+1 the heading the update will see (same expression as the pose
+        // update below, so the same bits)
         const double RTV = rec[1] * k.deg2rad_pi / 180.0;
-        const double phi_new = sm.xs[2] + rec[2] * RTV;
-        UpdateTrig tg;
-        ekf_build_trig(tg, phi_new);
-        UpdateSetup& u = sm.upd;
-        u.c = tg.c; u.s = tg.s;
-        for (int q = 0; q < 4; ++q) { u.Ct[q] = tg.Ct[q]; u.mCt[q] = tg.mCt[q]; u.mCtJ[q] = tg.mCtJ[q]; }
-        if ((int)rec[5] > 0) {                         // first measurement of the step
-          u.z0 = rec[8]; u.z1 = rec[9];
-          for (int q = 0; q < 4; ++q) u.R[q] = rec[10 + q];
+        const double phi = sc_prop ? sm.xs[2] : sm.xs[2] + rec[2] * RTV;
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        if (sc_prop) {
+          PropSetup ps;
+          ekf_build_prop_sc(ps, rec[0], rec[1], rec[2], sn, cs, k);
+          sm.prop = ps;
+          sm.PhiS[0] = 1.0; sm.PhiS[1] = 0.0; sm.PhiS[2] = 0.0;           // Propagate.cpp:42-44
+          sm.PhiS[3] = 0.0; sm.PhiS[4] = 1.0; sm.PhiS[5] = 0.0;
+          sm.PhiS[6] = ps.phi02; sm.PhiS[7] = ps.phi12; sm.PhiS[8] = 1.0;
+          sm.GS[0] = ps.g00; sm.GS[1] = ps.g10; sm.GS[2] = 0.0;            // :46-48
+          sm.GS[3] = 0.0; sm.GS[4] = 0.0; sm.GS[5] = ps.g21;
+          const double xm0 = ps.v * ps.c, xm1 = ps.v * ps.s, xm2 = ps.w;   // Propagate.cpp:33-37
+          sm.xnew[0] = sm.xs[0] + ps.dt * xm0;
+          sm.xnew[1] = sm.xs[1] + ps.dt * xm1;
+          sm.xnew[2] = sm.xs[2] + ps.dt * xm2;
+        } else {
+          UpdateTrig tg;
+          ekf_build_trig_sc(tg, sn, cs);
+          UpdateSetup& u = sm.upd;
+          u.c = tg.c; u.s = tg.s;
+          for (int q = 0; q < 4; ++q) { u.Ct[q] = tg.Ct[q]; u.mCt[q] = tg.mCt[q]; u.mCtJ[q] = tg.mCtJ[q]; }
+          if ((int)rec[5] > 0) {                         // first measurement of the step
+            u.z0 = rec[8]; u.z1 = rec[9];
+            for (int q = 0; q < 4; ++q) u.R[q] = rec[10 + q];
+          }
         }
       }
     };
@@ -307,33 +315,35 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
         sm.xs[0] = sm.xnew[0]; sm.xs[1] = sm.xnew[1]; sm.xs[2] = sm.xnew[2];
         sm.upd.x0 = sm.xnew[0]; sm.upd.x1 = sm.xnew[1];
       }
-      if (warp == C::NW - 2) {
-        // 3x3 robot block, one element per lane (Propagate.cpp:53, then :66-67), straight from and
-        // back to the shared-memory strip; the q partial sums of the update follow by shuffle.
-        const int e = lane % 9, i = e % 3, j = e / 3;
+      if (helper_warp) {
+        // 3x3 robot block, one element per spare lane (Propagate.cpp:53, then :66-67), straight from
+        // and back to the shared-memory strip; the q partial sums of the update follow by shuffle.
+        const int e = (lane + 36 - SP0) % 9, i = e % 3, j = e / 3;   // lanes SP0..SP0+8 map to e = 0..8
         double PRR[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r) { PRR[r] = sm.s0[r]; PRR[r + 3] = sm.s1[r]; PRR[r + 6] = sm.s2[r]; }
         const double mij = ekf_prop_prr_elem(sm.PhiS, sm.GS, sm.prop.Q, PRR, i, j);
-        const double mji = __shfl_sync(0xffffffffu, mij, j + 3 * i);
+        const double mji = __shfl_sync(0xffffffffu, mij, SP0 + j + 3 * i);
         const double pn = 0.5 * (mij + mji);
         // q(qi,qj) = mCt(qi,0)*P(0,qj) + mCt(qi,1)*P(1,qj)   (ekf_complete_setup)
-        const int qe = lane % 6, qi = qe % 2, qj = qe / 2;
-        const double p0j = __shfl_sync(0xffffffffu, pn, 0 + 3 * qj);
-        const double p1j = __shfl_sync(0xffffffffu, pn, 1 + 3 * qj);
+        const int qe = e % 6, qi = qe % 2, qj = qe / 2;
+        const double p0j = __shfl_sync(0xffffffffu, pn, SP0 + 0 + 3 * qj);
+        const double p1j = __shfl_sync(0xffffffffu, pn, SP0 + 1 + 3 * qj);
         const double qv = sm.upd.mCt[qi] * p0j + sm.upd.mCt[qi + 2] * p1j;
-        if (lane < 9) {
+        if (lane >= SP0 && lane < SP0 + 9) {
           sm.prr_new[e] = pn;
           sm.upd.PRR[e] = pn;
           double* col = j == 0 ? sm.s0 : (j == 1 ? sm.s1 : sm.s2);
           col[i] = pn;
+          if (e < 6) sm.upd.q[qe] = qv;
         }
-        if (lane < 6) sm.upd.q[qe] = qv;
       }
-      if (is_tile && J == 0 && I > 0) {
-#pragma unroll
-        for (int aa = 0; aa < 4; ++aa) ekf_prop_col(sm.prop, p[aa][0], p[aa][1], p[aa][2]);   // Propagate.cpp:56-60
-        publish_strip<NB>(sm, p, I);
+      // P_RL <- Phi*P_RL (Propagate.cpp:56-60), one strip row per thread, in shared memory; the
+      // column-0 tiles take the result back into their registers after the barrier.
+      for (int r = 4 + tid; r < C::NI; r += C::THREADS) {
+        double a0 = sm.s0[r], a1 = sm.s1[r], a2 = sm.s2[r];
+        ekf_prop_col(sm.prop, a0, a1, a2);
+        sm.s0[r] = a0; sm.s1[r] = a1; sm.s2[r] = a2;
       }
       __syncthreads();
       EKF_PHASE(1)   // covariance propagate + publish
@@ -342,6 +352,13 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
         for (int j = 0; j < 3; ++j)
 #pragma unroll
           for (int i = 0; i < 3; ++i) p[i][j] = sm.prr_new[i + 3 * j];
+      } else if (is_tile && J == 0) {   // the other column-0 tiles take their propagated strip rows
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa) {
+          p[aa][0] = sm.s0[4 * I + aa];
+          p[aa][1] = sm.s1[4 * I + aa];
+          p[aa][2] = sm.s2[4 * I + aa];
+        }
       }
       bool setup_valid = true;   // sm.upd describes the current state and measurement 0
 
