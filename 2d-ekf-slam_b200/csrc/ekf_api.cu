@@ -98,6 +98,24 @@ int check_status(ekf_handle h) {
   return EKF_OK;
 }
 
+// Which fused kernel a batch-regime run uses: 1 = shared-memory full matrix, 2 = register tiles,
+// 3 = shared-memory tiled triangle.
+int pick_batch_kernel(ekf_handle h) {
+  const int want = h->cfg.batch_kernel;
+  const int cap = h->st.cap_lm;
+  if (want == EKF_BATCH_KERNEL_SMEM) return 1;
+  if (want == EKF_BATCH_KERNEL_TILE) return cap <= ekf_tile_max_landmarks() ? 2 : -1;
+  if (want == EKF_BATCH_KERNEL_STILE) return cap <= ekf_stile_max_landmarks() ? 3 : -1;
+  if (cap <= ekf_stile_max_landmarks()) return 3;
+  return 1;
+}
+
+cudaError_t launch_batch_kernel(ekf_handle h, int kern, const EkfState& st, const EkfRunIO& io) {
+  if (kern == 3) return ekf_stile_run(st, io, h->k, h->sm_count, h->stream);
+  if (kern == 2) return ekf_tile_run(st, io, h->k, h->sm_count, h->stream);
+  return ekf_batch_run(st, io, h->k, h->grid_cap, h->stream);
+}
+
 void kernel_event_begin(ekf_handle h) {
   if (h->kev_used < kTimingPairs) cudaEventRecord(h->kev0[h->kev_used], h->stream);
 }
@@ -129,12 +147,11 @@ int launch_run(ekf_handle h, bool want_trace, bool want_pose) {
     io.pose_trace = h->t_pose.p;
   }
   if (h->regime == EKF_REGIME_BATCH) {
-    const bool tile = h->cfg.batch_kernel != EKF_BATCH_KERNEL_SMEM && h->st.cap_lm <= ekf_tile_max_landmarks();
-    if (h->cfg.batch_kernel == EKF_BATCH_KERNEL_TILE && !tile)
-      return fail(h, EKF_ERR_UNSUPPORTED, "register-tile kernel supports max_landmarks <= " + std::to_string(ekf_tile_max_landmarks()));
+    const int kern = pick_batch_kernel(h);
+    if (kern < 0)
+      return fail(h, EKF_ERR_UNSUPPORTED, "the tiled fused kernels support max_landmarks <= " + std::to_string(ekf_tile_max_landmarks()));
     kernel_event_begin(h);
-    if (tile) EKF_CK(h, ekf_tile_run(h->st, io, h->k, h->sm_count, h->stream));
-    else EKF_CK(h, ekf_batch_run(h->st, io, h->k, h->grid_cap, h->stream));
+    EKF_CK(h, launch_batch_kernel(h, kern, h->st, io));
     kernel_event_end(h);
     h->launches += 1;
   } else {
@@ -323,7 +340,7 @@ int ekf_n_filters(ekf_handle h) { return h ? h->st.F : 0; }
 int ekf_max_landmarks(ekf_handle h) { return h ? h->st.cap_lm : 0; }
 int ekf_regime(ekf_handle h) { return h ? h->regime : 0; }
 int ekf_set_batch_kernel(ekf_handle h, int batch_kernel) {
-  if (!h || batch_kernel < EKF_BATCH_KERNEL_AUTO || batch_kernel > EKF_BATCH_KERNEL_TILE) return EKF_ERR_BAD_ARG;
+  if (!h || batch_kernel < EKF_BATCH_KERNEL_AUTO || batch_kernel > EKF_BATCH_KERNEL_STILE) return EKF_ERR_BAD_ARG;
   h->cfg.batch_kernel = batch_kernel;
   return EKF_OK;
 }
@@ -539,9 +556,12 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
     EKF_CK(h, h->t_mah.reserve(FTM));
   }
   if (want_pose) EKF_CK(h, h->t_pose.reserve(FT * 3));
-  const bool tile = h->cfg.batch_kernel != EKF_BATCH_KERNEL_SMEM && st.cap_lm <= ekf_tile_max_landmarks();
+  const int kern = pick_batch_kernel(h);
+  if (kern < 0)
+    return fail(h, EKF_ERR_UNSUPPORTED, "the tiled fused kernels support max_landmarks <= " + std::to_string(ekf_tile_max_landmarks()));
   // chunk = a multiple of the co-resident CTA count (2 filters per CTA), at most kMaxChunks chunks
-  const size_t wave = (size_t)(tile ? 2 * h->sm_count : h->grid_cap);
+  const size_t wave = (size_t)(kern == 3 ? ekf_stile_ctas_per_sm(st.cap_lm) * h->sm_count
+                                         : (kern == 2 ? 2 * h->sm_count : h->grid_cap));
   size_t chunk = 2 * wave;
   while ((F + chunk - 1) / chunk > (size_t)kMaxChunks) chunk += wave;
   const int n_chunks = (int)((F + chunk - 1) / chunk);
@@ -565,8 +585,7 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
     if (want_trace) { io.decision = h->t_dec.p + f0 * T * M; io.index = h->t_idx.p + f0 * T * M; io.mahal = h->t_mah.p + f0 * T * M; }
     if (want_pose) io.pose_trace = h->t_pose.p + f0 * T * 3;
     kernel_event_begin(h);
-    if (tile) EKF_CK(h, ekf_tile_run(sub, io, h->k, h->sm_count, h->stream));
-    else EKF_CK(h, ekf_batch_run(sub, io, h->k, h->grid_cap, h->stream));
+    EKF_CK(h, launch_batch_kernel(h, kern, sub, io));
     kernel_event_end(h);
     h->launches += 1;
     EKF_CK(h, cudaEventRecord(h->ev_k[c], h->stream));

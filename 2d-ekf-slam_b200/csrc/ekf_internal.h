@@ -57,6 +57,11 @@ int ekf_tile_max_landmarks();
 cudaError_t ekf_tile_phase_cycles(long long* out);   // profiling aid, see ekf_tile.cu
 cudaError_t ekf_tile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
 
+// Shared-memory tiled-triangle variant of the fused path (ekf_stile.cu): four filters per SM.
+int ekf_stile_max_landmarks();
+int ekf_stile_ctas_per_sm(int cap_lm);
+cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
+
 // ---- regime B: whole grid per filter, covariance streamed from HBM (ekf_large.cu) ---------------
 struct EkfLargeWork {      // device scratch owned by the handle
   double2* W;              // [cap_n + 2]  downdate vectors

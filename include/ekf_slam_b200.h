@@ -56,6 +56,7 @@ extern "C" {
 #define EKF_BATCH_KERNEL_AUTO 0   /* register tiles when max_landmarks <= 62, else shared memory */
 #define EKF_BATCH_KERNEL_SMEM 1   /* covariance resident in shared memory                         */
 #define EKF_BATCH_KERNEL_TILE 2   /* covariance's lower block triangle resident in registers      */
+#define EKF_BATCH_KERNEL_STILE 3  /* lower block triangle tiled in shared memory, 4 filters per SM */
 
 typedef struct ekf_handle_s* ekf_handle;
 

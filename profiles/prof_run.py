@@ -19,13 +19,13 @@ spec.loader.exec_module(ekf)
 def batch(F=592, T=1000, cap=50):
     syn = ekf.Synth(50, steps_per_lap=T)
     rec = syn.generate(F, T)
-    fb = ekf.FilterBatch(F, cap)
+    fb = ekf.FilterBatch(F, cap, batch_kernel=int(os.environ.get("EKF_KERNEL", "0")))
     fb.upload_records(rec, 1)
     if os.environ.get("EKF_BUILD_WITH_SMEM"):   # experiment builds of the tile kernel without the New path
         fb.set_batch_kernel(1)
     for lap in range(3):                   # lap 0 builds the maps, laps 1-2 are full size
         if lap == 1:
-            fb.set_batch_kernel(0)
+            fb.set_batch_kernel(int(os.environ.get("EKF_KERNEL", "0")))
         if lap == 2 and os.environ.get("EKF_PHASES"):
             fb.sync()
             ekf.debug_phase_cycles(read=False)
