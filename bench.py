@@ -29,7 +29,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "filter-steps/sec (batched EKF, N=50)"
 UNIT = "filter-steps/s"
 N_LM = 50
-CAP_LM = 50          # landmark capacity per filter: 13x13 register tiles, 2 CTAs (filters) per SM
+CAP_LM = 50          # landmark capacity per filter: 182 shared-memory tiles, 4 CTAs (filters) per SM
 T_LAP = 1000
 MAX_MEAS = 1
 
@@ -335,7 +335,7 @@ def main():
         prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json")))
     except Exception:
         pass
-    roofline = {"bound": "fp64", "kernel": "ekf_batch_tile_kernel<13>",
+    roofline = {"bound": "fp64", "kernel": "ekf_batch_stile_kernel<13>",
                 "achieved": achieved / 1e12 if achieved else None, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
                 "traffic": prof.get("batch_traffic_bytes_per_launch"),
