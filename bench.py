@@ -206,6 +206,13 @@ def workload_name(args, world):
             % (args.filters_per_gpu, N_LM, T_LAP, "" if world == 1 else ", %d GPUs, disjoint filter ranges" % world))
 
 
+def profile_facts():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json")))
+    except Exception:
+        return {}
+
+
 def large_map_leg(ekf, n_lm, steps, hbm_peak, device):
     """BASELINE configs[3]/[4]: one large map, covariance in HBM, Old-updates from an injected state."""
     from parity import injected_state
@@ -238,7 +245,8 @@ def large_map_leg(ekf, n_lm, steps, hbm_peak, device):
            "update_steps_per_s": steps / (ms * 1e-3), "gpu_launches": int(l1 - l0),
            "roofline": {"bound": "hbm", "kernel": "large_downdate<2>", "achieved": alg / (kms * 1e-3) / 1e9 if kn else None,
                         "peak": hbm_peak, "unit": "GB/s", "frac": (alg / (kms * 1e-3) / 1e9) / hbm_peak if kn else None,
-                        "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_kernel_ms": kms,
+                        "traffic": profile_facts().get("large_traffic_bytes_per_launch", {}).get(str(n_lm)),
+                        "algorithmic_bytes_per_launch": alg, "avg_kernel_ms": kms,
                         "launches_timed": kn},
            "step_gbs": alg * n_old / (ms * 1e-3) / 1e9}
     return res
@@ -330,11 +338,7 @@ def main():
     # ---- roofline of the dominant kernel (fused batch kernel, FP64 pipe) ------------------------------
     fp64_peak = ekf.measure_fp64_peak(local)
     achieved = flops_per_launch / (kms * 1e-3) if kn else None
-    prof = {}
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json")))
-    except Exception:
-        pass
+    prof = profile_facts()
     roofline = {"bound": "fp64", "kernel": "ekf_batch_stile_kernel<13>",
                 "achieved": achieved / 1e12 if achieved else None, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
