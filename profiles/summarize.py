@@ -51,7 +51,7 @@ def summarize_rep(rep, prefix):
     hi = next(i for i, r in enumerate(src) if len(r) > 4 and r[0] == "Address")
     h = src[hi]
     ix = {k: i for i, k in enumerate(h)}
-    data = [r for r in src[hi + 1:] if len(r) == len(h)]
+    data = [r for r in src[hi + 1:] if len(r) == len(h) and r[ix["# Samples"]].isdigit()]
     tot = sum(int(r[ix["# Samples"]] or 0) for r in data) or 1
     stall_cols = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
     with open(prefix + "_hot.txt", "w") as f:
