@@ -239,8 +239,11 @@ class FilterBatch:
     def reset(self):
         self._chk(self.L.ekf_reset(self.h))
 
-    def sync(self):
-        self._chk(self.L.ekf_sync(self.h))
+    def sync(self, allow_capacity=False):
+        rc = self.L.ekf_sync(self.h)
+        if not (allow_capacity and rc == ERR_CAPACITY):
+            self._chk(rc)
+        return rc
 
     def set_state(self, filt, x, P, symmetric=False):
         """x (n), P (n x n, numpy row-major). symmetric=True skips the transpose copy to column-major
@@ -347,10 +350,12 @@ class FilterBatch:
     def run_resident(self, trace=False, pose_trace=False):
         self._chk(self.L.ekf_run_resident(self.h, int(trace), int(pose_trace)))
 
-    def download_outputs(self, trace=True, pose_trace=False, outputs=None):
+    def download_outputs(self, trace=True, pose_trace=False, outputs=None, allow_capacity=False):
         T, M = self._rec_shape
         o = outputs if outputs is not None else self.alloc_outputs(T, M, trace, pose_trace)
-        self._chk(self.L.ekf_download_outputs(self.h, C.byref(o["_c"])))
+        rc = self.L.ekf_download_outputs(self.h, C.byref(o["_c"]))
+        if not (allow_capacity and rc == ERR_CAPACITY):
+            self._chk(rc)
         return o
 
     def timer_start(self):
