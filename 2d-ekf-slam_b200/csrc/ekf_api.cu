@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -65,6 +66,7 @@ struct ekf_handle_s {
   int rec_T = 0, rec_M = 0, rec_L = 0;
   bool have_trace = false, have_pose_trace = false;
   std::vector<uint8_t> flag_compass, flag_nz;   // host mirror [F][T] of record flags (regime B)
+  std::vector<unsigned char> tmaps;             // tensor maps of the TMA-staged downdate (regime B)
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // user timer
   cudaEvent_t kev0[kTimingPairs], kev1[kTimingPairs];
@@ -278,11 +280,26 @@ int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, co
       return bail(EKF_ERR_CUDA, std::string("ekf_batch_prepare: ") + cudaGetErrorString(e));
   } else {
     if ((e = ekf_large_prepare(sms, &h->wk.grid)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
-    if ((e = cudaMalloc(&h->wk.W, (size_t)(st.cap_n + 2) * sizeof(double2))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    const size_t w_count = (size_t)st.cap_n + 512;   // zero tail: boundary tiles of the TMA sweep read past n
+    if ((e = cudaMalloc(&h->wk.W, w_count * sizeof(double2))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaMalloc(&h->wk.cand_val, (size_t)h->wk.grid * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaMalloc(&h->wk.cand_idx, (size_t)h->wk.grid * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaMalloc(&h->wk.small, ekf_large_small_doubles() * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
-    cudaMemset(h->wk.W, 0, (size_t)(st.cap_n + 2) * sizeof(double2));
+    cudaMemset(h->wk.W, 0, w_count * sizeof(double2));
+    {
+      // TMA-staged downdate: on unless EKF_LARGE_TMA=0 (the plain double2 sweep stays available)
+      const char* env = getenv("EKF_LARGE_TMA");
+      h->wk.use_tma = env ? atoi(env) : 1;
+      if (h->wk.use_tma) {
+        const size_t mb = ekf_large_tma_map_bytes();
+        h->tmaps.resize((size_t)n_filters * mb);
+        bool ok = ekf_large_tma_prepare(sms, &h->wk.tma_grid) == cudaSuccess;
+        for (int f = 0; ok && f < n_filters; ++f)
+          ok = ekf_large_tma_encode(h->tmaps.data() + (size_t)f * mb, st.P + (size_t)f * st.slab, st.cap_n, st.ld) == cudaSuccess;
+        if (!ok) { h->wk.use_tma = 0; cudaGetLastError(); }
+        h->wk.tmaps = h->tmaps.data();
+      }
+    }
     h->ltm.ev0 = h->kev0;
     h->ltm.ev1 = h->kev1;
     h->ltm.cap = kTimingPairs;
@@ -333,6 +350,7 @@ int ekf_reset(ekf_handle h) {
   EKF_CK(h, cudaMemsetAsync(st.P, 0, (size_t)st.F * st.slab * sizeof(double), h->stream));
   EKF_CK(h, cudaMemsetAsync(st.nlm, 0, (size_t)st.F * sizeof(int), h->stream));
   EKF_CK(h, cudaMemsetAsync(st.status, 0, (size_t)st.F * sizeof(int), h->stream));
+  if (h->wk.W) EKF_CK(h, cudaMemsetAsync(h->wk.W, 0, ((size_t)st.cap_n + 512) * sizeof(double2), h->stream));
   return EKF_OK;
 }
 
@@ -362,6 +380,7 @@ int ekf_set_state(ekf_handle h, int filter, int n_landmarks, const double* x, co
   EKF_CK(h, cudaMemcpy2DAsync(st.P + (size_t)filter * st.slab, (size_t)st.ld * sizeof(double), P, (size_t)ld * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
   EKF_CK(h, cudaMemcpyAsync(st.nlm + filter, &n_landmarks, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (h->wk.W) EKF_CK(h, cudaMemsetAsync(h->wk.W, 0, ((size_t)st.cap_n + 512) * sizeof(double2), h->stream));
   EKF_CK(h, cudaStreamSynchronize(h->stream));
   return EKF_OK;
 }

@@ -69,7 +69,27 @@ struct EkfLargeWork {      // device scratch owned by the handle
   int* cand_idx;           // [grid]
   double* small;           // LargeSmall (setup, winner, decision), ekf_large_small_doubles() doubles
   int grid;                // CTAs of the downdate sweep (multiple of the SM count)
+  // TMA-staged downdate (ekf_large_tma.cu): one tensor map per filter (host copies), persistent grid
+  const unsigned char* tmaps;   // [F][ekf_large_tma_map_bytes()] or null
+  int tma_grid;
+  int use_tma;
 };
+
+// Device addresses the TMA downdate reads its control state from (fields of LargeSmall).
+struct EkfLargeTmaArgs {
+  const int* decision;     // null for the compass variant
+  const int* n_dim;
+  const double* m0;
+  const double* m1;
+  const double2* W;
+  int* nlm_out;
+  const int* n_lm;
+};
+size_t ekf_large_tma_map_bytes();
+cudaError_t ekf_large_tma_encode(void* map_out, double* P, int cap_n, int ld);
+cudaError_t ekf_large_tma_prepare(int sm_count, int* grid);
+cudaError_t ekf_large_tma_downdate(const EkfLargeTmaArgs& t, const void* map, int grid, bool compass, cudaStream_t s);
+
 // Optional CUDA-event sampling of the dominant (downdate) kernel: every `every`-th launch is
 // bracketed by ev0[k]/ev1[k] until `cap` pairs are used.
 struct EkfLargeTiming {

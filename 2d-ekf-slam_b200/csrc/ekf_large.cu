@@ -345,6 +345,7 @@ __global__ void large_compass_setup(const LargeArgs a, const double* z, const do
   sm->cS = S;
   sm->csq = sqrt(fabs(S));
   sm->cm0 = S < 0 ? 1.0 : -1.0;
+  sm->n = 3 + 2 * a.st.nlm[a.f];
 }
 
 __global__ void __launch_bounds__(kThreads) large_compass_gain(const LargeArgs a) {
@@ -400,14 +401,24 @@ void launch_update(LargeArgs a, const EkfState& st, const EkfLargeWork& wk, cons
   large_gain<<<row_grid(st, wk), kThreads, 0, s>>>(a);
   const bool sample = tm && tm->used < tm->cap && (tm->seen++ % tm->every) == 0;
   if (sample) cudaEventRecord(tm->ev0[tm->used], s);
-  large_downdate<2, false><<<wk.grid, kThreads, 0, s>>>(a);
+  if (wk.use_tma) {
+    EkfLargeTmaArgs t{&a.sm->decision, &a.sm->n, &a.sm->m0, &a.sm->m1, a.W, a.st.nlm + a.f, &a.sm->n_lm};
+    ekf_large_tma_downdate(t, wk.tmaps + (size_t)a.f * ekf_large_tma_map_bytes(), wk.tma_grid, false, s);
+  } else {
+    large_downdate<2, false><<<wk.grid, kThreads, 0, s>>>(a);
+  }
   if (sample) cudaEventRecord(tm->ev1[tm->used++], s);
 }
 void launch_compass(const LargeArgs& a, const EkfState& st, const EkfLargeWork& wk, const double* z, const double* R,
                     cudaStream_t s) {
   large_compass_setup<<<1, 32, 0, s>>>(a, z, R);
   large_compass_gain<<<row_grid(st, wk), kThreads, 0, s>>>(a);
-  large_downdate<1, true><<<wk.grid, kThreads, 0, s>>>(a);
+  if (wk.use_tma) {
+    EkfLargeTmaArgs t{nullptr, &a.sm->n, &a.sm->cm0, &a.sm->cm0, a.W, nullptr, nullptr};
+    ekf_large_tma_downdate(t, wk.tmaps + (size_t)a.f * ekf_large_tma_map_bytes(), wk.tma_grid, true, s);
+  } else {
+    large_downdate<1, true><<<wk.grid, kThreads, 0, s>>>(a);
+  }
 }
 
 }  // namespace
