@@ -94,15 +94,16 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// first tile of row block I: sum_{i<I} (i/2 + 1)
-__device__ __forceinline__ int tile_row_offset(int I) {
-  const int h = I >> 1;
-  return h * (h + 1) + (I & 1) * (h + 1);
-}
+// Tiles are numbered column block by column block: column block J holds row blocks I = 2J..2NB-1,
+// so tile (I, J) is number J*(2NB) - J*(J-1) + (I - 2J). Consecutive threads then share J (their
+// W_col loads are warp-uniform broadcasts) and the strip tiles (J = 0) are tiles 0..2NB-1 in row
+// order (the gating / gain accesses to P(r, 0..2) are conflict-free).
+template <int NB>
+__device__ __forceinline__ int tile_number(int I, int J) { return J * (2 * NB) - J * (J - 1) + (I - 2 * J); }
 // index of P(r, c), r >= c, in the plane-major tile storage
 template <int NB>
 __device__ __forceinline__ int pidx_lower(int r, int c) {
-  return ((r & 3) + 4 * (c & 7)) * STileCfg<NB>::NTILES + tile_row_offset(r >> 2) + (c >> 3);
+  return ((r & 3) + 4 * (c & 7)) * STileCfg<NB>::NTILES + tile_number<NB>(r >> 2, c >> 3);
 }
 template <int NB>
 __device__ __forceinline__ int pidx(int r, int c) { return r >= c ? pidx_lower<NB>(r, c) : pidx_lower<NB>(c, r); }
@@ -151,10 +152,10 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
   const bool sc_trig = helper_warp && lane == SP0 + 1;
   const bool post_lane = helper_warp && lane == SP0 + 9;
   int I = 0, J = 0;
-  if (is_tile) {
+  if (is_tile) {                                     // inverse of tile_number
     int t = tid;
-    while (t > (I >> 1)) { t -= (I >> 1) + 1; ++I; }
-    J = t;
+    while (t >= 2 * NB - 2 * J) { t -= 2 * NB - 2 * J; ++J; }
+    I = 2 * J + t;
   }
   double* Tt = T + tid;                              // this thread's tile: element (a,b) at Tt[(a+4b)*NT]
   const int rowbase = pidx_lower<NB>(tid < C::NI ? tid : 0, 0);   // P(tid, 0); P(tid, j) = + 4*j*NT
