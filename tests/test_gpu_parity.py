@@ -267,3 +267,24 @@ def test_headline_config_properties_and_sampled_parity(ekf, oracle):
         assert np.linalg.eigvalsh(P).min() > -1e-12
         assert_state_close(x, P, want["final_x"][s, :n], want["final_P"][s, :n, :n].T, "filter %d" % f)
     fb.close()
+
+
+def test_pipelined_run_equals_resident_run(ekf):
+    """ekf_run() streams chunks of filters (H2D / kernel / D2H on three streams); with enough filters
+    for several chunks it must return exactly what upload + run_resident + download returns."""
+    N, F, T, cap = 12, 2600, 60, 14
+    rec = ekf.Synth(N, steps_per_lap=T).generate(F, T)
+    fa = ekf.FilterBatch(F, cap)
+    a = fa.run(rec, 1, pose_trace=True)
+    fb = ekf.FilterBatch(F, cap)
+    fb.upload_records(rec, 1)
+    fb.run_resident(trace=True, pose_trace=True)
+    b = fb.download_outputs(trace=True, pose_trace=True)
+    for k in ("decision", "index", "mahal", "pose_trace", "final_pose", "final_nlm"):
+        assert np.array_equal(a[k], b[k]), k
+    for f in (0, 1183, 1184, 2367, 2368, 2599):
+        xa, Pa = fa.get_state(f)
+        xb, Pb = fb.get_state(f)
+        assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
+    fa.close()
+    fb.close()
