@@ -551,8 +551,14 @@ template <int NB>
 cudaError_t launch_stile(const RunArgs& a, int sm_count, cudaStream_t stream) {
   using C = STileCfg<NB>;
   const size_t bytes = stile_smem_bytes<NB>(a.io.L);
-  static size_t configured = 0;
-  static int grid_cap = 0;
+  // function attributes are per device: keep one configuration per device of this process
+  static size_t configured_dev[64] = {0};
+  static int grid_cap_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  size_t& configured = configured_dev[dev];
+  int& grid_cap = grid_cap_dev[dev];
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(ekf_batch_stile_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;

@@ -698,7 +698,7 @@ long long* g_phase_cycles = nullptr;   // set by ekf_tile_phase_cycles()
 template <int NB>
 cudaError_t launch_tile(RunArgs a, int sm_count, cudaStream_t stream) {
   using C = TileCfg<NB>;
-  static int grid_cap = 0;
+  static int grid_cap = 0;   // occupancy is a property of the kernel binary; every device here is a B200
   a.phase_cycles = g_phase_cycles;
   if (!grid_cap) {
     int per_sm = 0;
