@@ -130,7 +130,7 @@ int launch_run(ekf_handle h, bool want_trace, bool want_pose) {
   const size_t FT = (size_t)h->st.F * h->rec_T, FTM = FT * (h->rec_M > 0 ? h->rec_M : 1);
   EkfRunIO io{};
   io.records = h->records.p;
-  io.T = h->rec_T; io.M = h->rec_M; io.L = h->rec_L;
+  io.T = h->rec_T; io.M = h->rec_M > 0 ? h->rec_M : 1; io.L = h->rec_L;   // M >= 1: a slot with n_z = 0 is reported as NONE
   h->have_trace = want_trace;
   h->have_pose_trace = want_pose;
   if (want_trace) {
@@ -600,7 +600,7 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
     sub.status = st.status + f0;
     EkfRunIO io{};
     io.records = h->records.p + f0 * T * L;
-    io.T = T; io.M = max_meas; io.L = L;
+    io.T = T; io.M = M; io.L = L;
     if (want_trace) { io.decision = h->t_dec.p + f0 * T * M; io.index = h->t_idx.p + f0 * T * M; io.mahal = h->t_mah.p + f0 * T * M; }
     if (want_pose) io.pose_trace = h->t_pose.p + f0 * T * 3;
     kernel_event_begin(h);

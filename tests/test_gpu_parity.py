@@ -288,3 +288,20 @@ def test_pipelined_run_equals_resident_run(ekf):
         assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
     fa.close()
     fb.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["smem", "tile", "stile"])
+def test_propagate_only_run(ekf, oracle, kernel):
+    """Records without measurement slots (max_meas = 0): dead reckoning, every slot reported as NONE."""
+    F, T = 3, 80
+    rec = ekf.Synth(8, steps_per_lap=T, max_meas=0, compass_every=3).generate(F, T)
+    assert rec.shape[2] == 8
+    fb = ekf.FilterBatch(F, 4, batch_kernel=kernel)
+    got = fb.run(rec, 0, pose_trace=True)
+    want = oracle.run_batch(rec, 0, 4, pose_trace=True, trace=False)
+    assert (got["decision"] == ekf.DECISION_NONE).all()
+    assert (got["final_nlm"] == 0).all()
+    assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL
+    x, P = fb.get_state(1)
+    assert len(x) == 3 and np.array_equal(P, P.T) and np.linalg.eigvalsh(P).min() > 0
+    fb.close()
