@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 2) ekf_batch_run_kernel(const RunArg
         UpdateOut o;
         if (m < nz) {
           const double* zr = cur + 8 + 6 * m;
-          o = cta_update(Ps, ld, xs, n_lm, a.st.cap_lm, zr[0], zr[1], zr + 2, Ws, sc, a.k);
+          o = cta_update(Ps, ld, xs, n_lm, n_lm, a.st.cap_lm, zr[0], zr[1], zr + 2, Ws, sc, a.k);
           dropped |= (o.decision == EKF_DEC_DROPPED);
         } else {
           o.decision = EKF_DEC_NONE; o.index = -1; o.mahal = 0.0;
@@ -196,9 +196,10 @@ __global__ void __launch_bounds__(kThreads) ekf_percall_kernel(const PercallArgs
     if (!a.io.cvalid || a.io.cvalid[f]) cta_update_compass(P, ld, xs, 3 + 2 * n_lm, a.io.cz[f], a.io.cR[f], Ws, sc, a.k);
   } else {
     int dropped = 0;
+    const int n_gate = n_lm;   // Update.cpp:26: the gating bound is read once per doUpdate call
     for (int m = 0; m < a.io.n_z; ++m) {
       const double* zr = a.io.zr + ((size_t)f * a.io.n_z + m) * 6;
-      const UpdateOut o = cta_update(P, ld, xs, n_lm, a.st.cap_lm, zr[0], zr[1], zr + 2, Ws, sc, a.k);
+      const UpdateOut o = cta_update(P, ld, xs, n_lm, n_gate, a.st.cap_lm, zr[0], zr[1], zr + 2, Ws, sc, a.k);
       dropped |= (o.decision == EKF_DEC_DROPPED);
       if (tid == 0) {
         const size_t oi = (size_t)f * a.io.n_z + m;

@@ -181,9 +181,12 @@ struct UpdateOut {
 };
 
 // One measurement of KalmanFilter::Update (Update.cpp:80-195). n_lm is updated in place
-// (uniformly by every thread). Returns the same UpdateOut in every thread.
+// (uniformly by every thread). n_gate is the gating loop's bound: Update.cpp:26 reads n_lm ONCE per
+// call, so inside one doUpdate(z_chunk) with n_z > 1 a landmark added by measurement j is not a
+// candidate for j+1..n_z (n_gate = n_lm at call entry); separate calls pass n_gate = n_lm.
+// Returns the same UpdateOut in every thread.
 __device__ __forceinline__ UpdateOut cta_update(double* __restrict__ P, int ld, double* __restrict__ xs, int& n_lm,
-                                                int cap_lm, double z0, double z1, const double* Rm,
+                                                int n_gate, int cap_lm, double z0, double z1, const double* Rm,
                                                 double2* __restrict__ Ws, CtaScratch* sc, const EkfConst& k) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int n = 3 + 2 * n_lm;
@@ -201,7 +204,7 @@ __device__ __forceinline__ UpdateOut cta_update(double* __restrict__ P, int ld, 
   double best = INFINITY;
   int best_idx = INT_MAX;
   double b_res0 = 0, b_res1 = 0, b_S0 = 0, b_S1 = 0, b_S2 = 0, b_S3 = 0, b_h0 = 0, b_h1 = 0;
-  for (int lm = tid; lm < n_lm; lm += nt) {
+  for (int lm = tid; lm < n_gate; lm += nt) {
     const int Li = 3 + 2 * lm;
     double p[6], pll[4];
 #pragma unroll

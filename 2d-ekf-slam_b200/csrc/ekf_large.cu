@@ -29,6 +29,7 @@ struct LargeSmall {
   PropSetup prop;
   UpdateSetup upd;
   int decision, opt_i, n, n_lm;
+  int gate_nlm;   // gating bound frozen at doUpdate entry (Update.cpp:26), see large_gate
   double mahal;
   double res[2], S[4], Si[4], h3[2];
   double l, sq0, sq1, m0, m1;
@@ -102,12 +103,16 @@ __device__ __forceinline__ void load_gate_inputs(const double* P, int ld, int Li
   pll[3] = P[Li + 1 + (size_t)(Li + 1) * ld];
 }
 
-__global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const double* zr) {
+// chunk_pos: 0 = a doUpdate call of its own (gating bound = live landmark count); 1 = first
+// measurement of an n_z > 1 call (same bound, and block 0 records it); 2 = later measurement of that
+// call: Update.cpp:26 read n_lm once, so landmarks added since the call began are not candidates.
+__global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const double* zr, int chunk_pos) {
   __shared__ CtaScratch sc;
   const double* P = filt_P(a);
   const double* x = filt_x(a);
   const int ld = a.st.ld;
-  const int n_lm = a.st.nlm[a.f];
+  const int n_lm = chunk_pos == 2 ? a.sm->gate_nlm : a.st.nlm[a.f];
+  if (chunk_pos == 1 && blockIdx.x == 0 && threadIdx.x == 0) a.sm->gate_nlm = n_lm;
   if (threadIdx.x == 0) {
     double PRR[9];
     for (int j = 0; j < 3; ++j)
@@ -392,11 +397,11 @@ void launch_propagate(const LargeArgs& a, const EkfState& st, const EkfLargeWork
   large_prop_setup<<<1, 32, 0, s>>>(a, vel, rot, dt);
   large_prop_strip<<<row_grid(st, wk), kThreads, 0, s>>>(a);
 }
-void launch_update(LargeArgs a, const EkfState& st, const EkfLargeWork& wk, const double* zr, int* dec, int* idx,
-                   double* mah, EkfLargeTiming* tm, cudaStream_t s) {
+void launch_update(LargeArgs a, const EkfState& st, const EkfLargeWork& wk, const double* zr, int chunk_pos, int* dec,
+                   int* idx, double* mah, EkfLargeTiming* tm, cudaStream_t s) {
   const int gg = gate_grid(st, wk);
   a.n_cand = gg;
-  large_gate<<<gg, kThreads, 0, s>>>(a, zr);
+  large_gate<<<gg, kThreads, 0, s>>>(a, zr, chunk_pos);
   large_decide<<<1, kThreads, 0, s>>>(a, zr, dec, idx, mah);
   large_gain<<<row_grid(st, wk), kThreads, 0, s>>>(a);
   const bool sample = tm && tm->used < tm->cap && (tm->seen++ % tm->every) == 0;
@@ -447,7 +452,7 @@ cudaError_t ekf_large_percall(const EkfState& st, int filter, const EkfPercallIO
   } else {
     for (int m = 0; m < io.n_z; ++m) {
       const size_t oi = (size_t)filter * io.n_z + m;
-      launch_update(a, st, wk, io.zr + oi * 6, io.decision ? io.decision + oi : nullptr,
+      launch_update(a, st, wk, io.zr + oi * 6, io.n_z == 1 ? 0 : (m == 0 ? 1 : 2), io.decision ? io.decision + oi : nullptr,
                     io.index ? io.index + oi : nullptr, io.mahal ? io.mahal + oi : nullptr, tm, stream);
     }
   }
@@ -471,7 +476,7 @@ cudaError_t ekf_large_run(const EkfState& st, int filter, const EkfRunIO& io, co
     for (int m = 0; m < io.M; ++m) {
       const size_t oi = ((size_t)filter * io.T + t) * io.M + m;
       if (m < n_z[t]) {
-        launch_update(a, st, wk, rec + 8 + 6 * m, io.decision ? io.decision + oi : nullptr,
+        launch_update(a, st, wk, rec + 8 + 6 * m, 0, io.decision ? io.decision + oi : nullptr,
                       io.index ? io.index + oi : nullptr, io.mahal ? io.mahal + oi : nullptr, tm, stream);
         *launches += 4;
       }

@@ -261,7 +261,11 @@ def main():
     ap.add_argument("--filters-per-gpu", type=int, default=4096)
     ap.add_argument("--large-map", default="2000,10000", help="comma list of landmark counts for the regime-B leg ('' = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--meas", type=int, default=1,
+                    help="measurements (doUpdate calls) per step; the headline is 1, SURVEY 8d also asks for 4")
     args = ap.parse_args()
+    global MAX_MEAS
+    MAX_MEAS = args.meas
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -316,7 +320,10 @@ def main():
     n_dropped = int((dec == ekf.DECISION_DROPPED).sum())
     n_old = int((dec == 1).sum())
     n_steps_lap = F * T_LAP
-    flops_per_launch = n_old * fmin_flops(N_LM, 1) + (n_steps_lap - n_old) * fmin_flops(N_LM, 2)
+    n_meas = int((dec >= 0).sum())
+    n = 3 + 2 * N_LM
+    # F_min: one propagate per step, gating per measurement, downdate per Old update
+    flops_per_launch = n_steps_lap * (8 * N_LM + 170) + n_meas * 150 * N_LM + n_old * (2 * n * n + 42 * n)
     value = world * F * T_LAP * args.steps / (ms_max * 1e-3)
 
     # ---- end-to-end through the C ABI with host buffers ("e2e") ---------------------------------------
@@ -359,7 +366,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "filters_per_gpu": F, "landmarks": N_LM,
                        "landmark_capacity": CAP_LM, "steps_per_lap": T_LAP, "measurements_per_step": MAX_MEAS,
-                       "old_fraction": n_old / n_steps_lap, "dropped_new_associations_last_lap_rank0": n_dropped,
+                       "old_fraction": n_old / max(n_meas, 1), "updates_per_step": n_meas / n_steps_lap, "dropped_new_associations_last_lap_rank0": n_dropped,
                        "l2": "inputs larger than L2: %.0f MB of step records + %.0f MB of covariance per pass"
                              % (rec.nbytes / 1e6, F * (3 + 2 * CAP_LM) * (4 + 2 * CAP_LM) * 8 / 1e6)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -118,7 +118,10 @@ int ekf_get_pose(ekf_handle h, double* xyphi, int32_t* n_landmarks);
 int ekf_propagate(ekf_handle h, const double* vel_mm_s, const double* rotvel_deg_s, const double* dt,
                   int dt_stride);
 /* KalmanFilter::doUpdate (kalmanfilter.cpp:64-90 -> Update.cpp:22-204) with n_z measurements per
- * filter, processed sequentially as Update.cpp:80-195 does. z[n_filters][n_z][2],
+ * filter, processed sequentially as Update.cpp:80-195 does - including its quirk that the gating
+ * bound n_lm is read once at call entry (Update.cpp:26): a landmark added by measurement j is not a
+ * candidate for measurements j+1..n_z of the same call (slam.cpp:150-171 itself always calls with
+ * n_z = 1, which is what ekf_run's M slots per step are). z[n_filters][n_z][2],
  * R[n_filters][n_z][4]. Optional outputs [n_filters][n_z] (NULL to skip; non-NULL synchronises):
  * decision (EKF_DECISION_*), lm_index (state index Opt_i of the associated landmark, or of the
  * new landmark for New), mahal (Mahal_dist after the gating loop). */

@@ -150,12 +150,12 @@ void ekf_oracle_measurement_from_feature(double fx_mm, double fy_mm, double* z_o
   z_out[1] = fy;
 }
 
-/* Update.cpp:80-195 for ONE measurement (n_z>1 is this applied sequentially, which is what the
- * reference's j-loop does). x: capacity >= n+2, P: ld >= n+2, in place. R column-major 2x2.
+/* Update.cpp:80-195, the body of the j-loop for ONE measurement. n_lm is the gating loop's bound:
+ * Update.cpp:26 reads it once per call, so for j > 1 of an n_z > 1 call it is the landmark count at
+ * call entry, not (n-3)/2. x: capacity >= n+2, P: ld >= n+2, in place. R column-major 2x2.
  * Returns the new dimension (n or n+2), or -1 if a New would exceed cap_n (state untouched). */
-int ekf_oracle_update(int n, double* x, double* P, int ld, int cap_n, const double* z, const double* R,
+static int update_one(int n, int n_lm, double* x, double* P, int ld, int cap_n, const double* z, const double* R,
                       int gamma_max, int gamma_min, OracleTrace* trace) {
-  const int n_lm = (n - 3) / 2;
   const double phi = x[2];
   const double cphi = cos(phi), sphi = sin(phi);
   const double C[4] = {cphi, sphi, -sphi, cphi};   /* C << cos,-sin,sin,cos (row-major fill) */
@@ -321,6 +321,28 @@ int ekf_oracle_update(int n, double* x, double* P, int ld, int cap_n, const doub
     trace->margin_cond = m_cond;
   }
   return n_out;
+}
+
+/* One doUpdate call with a single measurement (what slam.cpp:150-171 issues per feature). */
+int ekf_oracle_update(int n, double* x, double* P, int ld, int cap_n, const double* z, const double* R,
+                      int gamma_max, int gamma_min, OracleTrace* trace) {
+  return update_one(n, (n - 3) / 2, x, P, ld, cap_n, z, R, gamma_max, gamma_min, trace);
+}
+
+/* One doUpdate call with n_z measurements (z_chunk 2 x n_z, R_chunk 2 x 2n_z, both column-major):
+ * sequential, but with the gating bound frozen at call entry (Update.cpp:26) - a landmark added by
+ * measurement j is not a candidate for measurements j+1..n_z of the same call. traces: n_z entries
+ * or NULL. Returns the new dimension, or -1 on capacity (state as left by the measurements before). */
+int ekf_oracle_update_chunk(int n, double* x, double* P, int ld, int cap_n, int n_z, const double* z_chunk,
+                            const double* R_chunk, int gamma_max, int gamma_min, OracleTrace* traces) {
+  const int n_lm = (n - 3) / 2;
+  for (int j = 0; j < n_z; ++j) {
+    const int n2 = update_one(n, n_lm, x, P, ld, cap_n, z_chunk + 2 * j, R_chunk + 4 * j, gamma_max, gamma_min,
+                              traces ? traces + j : NULL);
+    if (n2 < 0) return -1;
+    n = n2;
+  }
+  return n;
 }
 
 /* kalmanfilter.cpp:96-130 */

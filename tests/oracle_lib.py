@@ -57,6 +57,9 @@ class Oracle:
         L.ekf_oracle_update.argtypes = [C.c_int, c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int,
                                         C.POINTER(Trace)]
         L.ekf_oracle_update.restype = C.c_int
+        L.ekf_oracle_update_chunk.argtypes = [C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_int,
+                                              C.c_int, C.POINTER(Trace)]
+        L.ekf_oracle_update_chunk.restype = C.c_int
         L.ekf_oracle_update_compass.argtypes = [C.c_int, c_dp, c_dp, C.c_int, C.c_double, C.c_double]
         L.ekf_oracle_measurement_from_feature.argtypes = [C.c_double, C.c_double, c_dp, c_dp]
         L.ekf_oracle_run_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_dp,
@@ -145,6 +148,19 @@ class OracleFilter:
             raise OverflowError("oracle filter capacity exceeded")
         self.n = n2
         return tr
+
+    def update_chunk(self, zs, Rs, gamma_max=50, gamma_min=10):
+        """One doUpdate call with n_z measurements: zs [n_z][2], Rs [n_z][4] (column-major 2x2 each).
+        The gating bound is frozen at call entry (Update.cpp:26). Returns the list of traces."""
+        zs = np.ascontiguousarray(zs, np.float64).reshape(-1, 2)
+        Rs = np.ascontiguousarray(Rs, np.float64).reshape(-1, 4)
+        trs = (Trace * len(zs))()
+        n2 = self.o.lib.ekf_oracle_update_chunk(self.n, _dp(self.x), _dp(self.Pbuf), self.cap_n, self.cap_n, len(zs),
+                                                _dp(zs), _dp(Rs), gamma_max, gamma_min, trs)
+        if n2 < 0:
+            raise OverflowError("oracle filter capacity exceeded")
+        self.n = n2
+        return list(trs)
 
     def update_compass(self, z, R):
         self.o.lib.ekf_oracle_update_compass(self.n, _dp(self.x), _dp(self.Pbuf), self.cap_n, z, R)

@@ -96,12 +96,12 @@ def test_percall_surface_matches_oracle(ekf, oracle, regime):
             zr = r[:, 8:8 + 6 * nz].reshape(F, nz, 6)
             dec, idx, mah = fb.update(zr[:, :, :2], zr[:, :, 2:])
             for f in range(F):
-                for m in range(nz):
-                    n_before = filters[f].n
-                    tr = filters[f].update(zr[f, m, :2], zr[f, m, 2:])
+                n_run = filters[f].n
+                for m, tr in enumerate(filters[f].update_chunk(zr[f, :, :2], zr[f, :, 2:])):   # ONE doUpdate call
                     assert dec[f, m] == tr.decision
-                    assert idx[f, m] == (n_before if tr.decision == 0 else tr.opt_i)
+                    assert idx[f, m] == (n_run if tr.decision == 0 else tr.opt_i)
                     assert abs(mah[f, m] - tr.mahal) <= TOL * max(1.0, abs(tr.mahal))
+                    n_run += 2 * (tr.decision == 0)
         if t % 10 == 0 or t == T - 1:
             for f in range(F):
                 x, P = fb.get_state(f)
@@ -111,6 +111,32 @@ def test_percall_surface_matches_oracle(ekf, oracle, regime):
     for f in range(F):
         assert nlm[f] == filters[f].num_landmarks
         assert rel_state(pose[f], filters[f].pose()) <= TOL
+    fb.close()
+
+
+@pytest.mark.parametrize("regime", [1, 2])
+def test_update_chunk_gating_bound_frozen_at_call_entry(ekf, oracle, regime):
+    """Update.cpp:26 reads n_lm once per doUpdate call: the same corner twice in ONE ekf_update call adds
+    two landmarks, in two calls the second is an Old update (tests/test_oracle_vs_ref.py pins this
+    against the reference's private Update)."""
+    z, R = np.array([2.0, 1.0]), np.array([0.01, 0.0, 0.0, 0.02])
+    zs, Rs = np.stack([z, z, z + 0.01])[None], np.stack([R, R, R])[None]
+    fb = ekf.FilterBatch(1, 6, regime=regime)
+    dec, idx, mah = fb.update(zs, Rs)
+    of = oracle.new_filter(6)
+    trs = of.update_chunk(zs[0], Rs[0])
+    assert list(dec[0]) == [t.decision for t in trs] == [0, 0, 0]
+    assert list(idx[0]) == [3, 5, 7]
+    x, P = fb.get_state(0)
+    xr, Pr = of.get_state()
+    assert_state_close(x, P, xr, Pr, "one call")
+    dec2, idx2, _ = fb.update(zs, Rs)                      # second call: all three now match landmark 1..3
+    trs2 = of.update_chunk(zs[0], Rs[0])
+    assert list(dec2[0]) == [t.decision for t in trs2] and list(idx2[0]) == [t.opt_i for t in trs2]
+    assert set(dec2[0]) <= {1, 2}
+    x, P = fb.get_state(0)
+    xr, Pr = of.get_state()
+    assert_state_close(x, P, xr, Pr, "second call")
     fb.close()
 
 

@@ -52,27 +52,49 @@ def test_single_calls_bit_identical_with_trace(ekf, oracle, ref):
     assert min_margin > 1e-6, "no knife-edge threshold decisions in the synthetic world"
 
 
-def test_private_update_with_nz_gt_1_equals_sequential_calls(ekf, oracle, ref):
-    """Update.cpp:80-195 processes the measurements of one call sequentially; the C ABI relies on
-    that to accept n_z measurements per launch."""
-    N, T = 8, 60
+def _chunk(r):
+    nz = int(r[5])
+    zs = np.array([r[8 + 6 * m:10 + 6 * m] for m in range(nz)])                   # [n_z][2]
+    Rs = np.array([r[10 + 6 * m:14 + 6 * m] for m in range(nz)])                  # [n_z][4] column-major 2x2
+    return nz, zs, Rs
+
+
+def test_private_update_with_nz_gt_1(ekf, oracle, ref):
+    """One doUpdate(z_chunk) with n_z > 1 (Update.cpp:80-195): measurements are applied sequentially,
+    but the gating bound n_lm is read once at call entry (Update.cpp:26). The restatement's
+    update_chunk follows the reference's private Update bit for bit from an empty map onwards
+    (chunks that add several landmarks included)."""
+    N, T = 8, 40
     rec = _records(ekf, N, 1, T, 2, max_meas=3)[0]
     fo = oracle.new_filter(N + 8)
+    seen_new_in_chunk = 0
     for r in rec[:T]:
         fo.propagate(r[0], r[1], r[2])
-        for m in range(int(r[5])):
-            fo.update(r[8 + 6 * m:10 + 6 * m], r[10 + 6 * m:14 + 6 * m])
-    x0, P0 = fo.get_state()
-    r = rec[T + 5]
-    nz = int(r[5])
-    assert nz == 3
-    zs = np.array([r[8 + 6 * m:10 + 6 * m] for m in range(nz)]).T                 # 2 x n_z
-    Rs = np.concatenate([r[10 + 6 * m:14 + 6 * m].reshape(2, 2).T for m in range(nz)], axis=1)  # 2 x 2n_z
-    x1, P1 = ref.call_update(x0, P0, zs, Rs)
-    for m in range(nz):
-        fo.update(r[8 + 6 * m:10 + 6 * m], r[10 + 6 * m:14 + 6 * m])
-    x2, P2 = fo.get_state()
-    assert np.array_equal(x1, x2) and np.array_equal(P1, P2)
+        nz, zs, Rs = _chunk(r)
+        if nz == 0:
+            continue
+        x0, P0 = fo.get_state()
+        x1, P1 = ref.call_update(x0, P0, zs.T, np.concatenate([R.reshape(2, 2).T for R in Rs], axis=1))
+        trs = fo.update_chunk(zs, Rs)
+        seen_new_in_chunk += sum(t.decision == 0 for t in trs) > 1
+        x2, P2 = fo.get_state()
+        assert np.array_equal(x1, x2) and np.array_equal(P1, P2)
+    assert seen_new_in_chunk > 0 and fo.num_landmarks == N
+
+
+def test_chunk_gating_bound_is_frozen_at_call_entry(oracle, ref):
+    """The quirk itself: the same corner twice in ONE call adds two landmarks (the second copy is
+    gated against the map as it was at call entry); in two calls the second is an Old update."""
+    z, R = np.array([2.0, 1.0]), np.array([0.01, 0.0, 0.0, 0.02])
+    x0, P0 = np.zeros(3), np.zeros((3, 3))
+    x1, _ = ref.call_update(x0, P0, np.stack([z, z], axis=1), np.concatenate([R.reshape(2, 2)] * 2, axis=1))
+    assert len(x1) == 7
+    fo = oracle.new_filter(4)
+    assert [t.decision for t in fo.update_chunk([z, z], [R, R])] == [0, 0] and fo.num_landmarks == 2
+    x2, _ = fo.get_state()
+    assert np.array_equal(x1, x2)
+    fs = oracle.new_filter(4)
+    assert [fs.update(z, R).decision, fs.update(z, R).decision] == [0, 1] and fs.num_landmarks == 1
 
 
 def test_measurement_covariance_from_feature(ekf, oracle, ref):
