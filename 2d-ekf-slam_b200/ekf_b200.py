@@ -123,6 +123,25 @@ def core_lib():
                                       C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.ekf_measure_fp64_peak.argtypes = [C.c_int, c_dp]
         L.ekf_debug_phase_cycles.argtypes = [C.POINTER(C.c_longlong)]
+        L.ekf_sharded_create.argtypes = [C.POINTER(H), C.c_int, c_ip, C.c_int, C.POINTER(Config)]
+        L.ekf_sharded_destroy.argtypes = [H]
+        L.ekf_sharded_reset.argtypes = [H]
+        L.ekf_sharded_n_shards.argtypes = [H]
+        L.ekf_sharded_max_landmarks.argtypes = [H]
+        L.ekf_sharded_columns.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ekf_sharded_set_state.argtypes = [H, C.c_int, c_dp, c_dp, C.c_int]
+        L.ekf_sharded_get_state.argtypes = [H, C.POINTER(C.c_int), c_dp, c_dp, C.c_int]
+        L.ekf_sharded_get_pose.argtypes = [H, c_dp, c_ip]
+        L.ekf_sharded_get_replica.argtypes = [H, C.c_int, C.POINTER(C.c_int), c_dp, c_dp]
+        L.ekf_sharded_propagate.argtypes = [H, C.c_double, C.c_double, C.c_double]
+        L.ekf_sharded_update.argtypes = [H, C.c_int, c_dp, c_dp, c_ip, c_ip, c_dp]
+        L.ekf_sharded_update_compass.argtypes = [H, C.c_double, C.c_double]
+        L.ekf_sharded_run.argtypes = [H, C.c_int, C.c_int, c_dp, C.POINTER(RunOutputs)]
+        L.ekf_sharded_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ekf_sharded_kernel_launches.argtypes = [H]
+        L.ekf_sharded_kernel_launches.restype = C.c_longlong
+        L.ekf_sharded_last_error.argtypes = [H]
+        L.ekf_sharded_last_error.restype = C.c_char_p
         _core = L
     return _core
 
@@ -374,6 +393,139 @@ class FilterBatch:
         n = C.c_int()
         self._chk(self.L.ekf_kernel_time(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+class ShardedMap:
+    """ONE large map whose covariance is column-sharded over several GPUs (one ekf_sharded handle;
+    devices may repeat an ordinal to put several shards on one GPU)."""
+
+    def __init__(self, devices, max_landmarks, **cfg_overrides):
+        self.L = core_lib()
+        cfg = Config()
+        self.L.ekf_default_config(C.byref(cfg))
+        for k, v in cfg_overrides.items():
+            setattr(cfg, k, v)
+        dev = np.ascontiguousarray(devices, np.int32)
+        self.h = C.c_void_p()
+        rc = self.L.ekf_sharded_create(C.byref(self.h), len(dev), _ip(dev), max_landmarks, C.byref(cfg))
+        if rc:
+            msg = self.L.ekf_sharded_last_error(None)
+            self.h = None
+            raise EkfError(rc, msg.decode() if msg else "")
+        self.G = len(dev)
+        self.cap_lm = max_landmarks
+        self.cap_n = 3 + 2 * max_landmarks
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ekf_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            msg = self.L.ekf_sharded_last_error(self.h)
+            raise EkfError(rc, msg.decode() if msg else "")
+
+    def columns(self, shard):
+        c0, c1 = C.c_int(), C.c_int()
+        self._chk(self.L.ekf_sharded_columns(self.h, shard, C.byref(c0), C.byref(c1)))
+        return c0.value, c1.value
+
+    def reset(self):
+        self._chk(self.L.ekf_sharded_reset(self.h))
+
+    def set_state(self, x, P, symmetric=False):
+        x = np.ascontiguousarray(x, np.float64)
+        n = len(x)
+        Pa = np.asarray(P, np.float64)
+        Pc = np.ascontiguousarray(Pa if symmetric else Pa.T)
+        self._chk(self.L.ekf_sharded_set_state(self.h, (n - 3) // 2, _dp(x), _dp(Pc), n))
+
+    def get_state(self, want_P=True):
+        nl = C.c_int()
+        self._chk(self.L.ekf_sharded_get_pose(self.h, None, C.cast(C.byref(nl), c_ip)))
+        n = 3 + 2 * nl.value
+        x = np.zeros(n)
+        P = np.zeros((n, n)) if want_P else None
+        self._chk(self.L.ekf_sharded_get_state(self.h, C.byref(nl), _dp(x), _dp(P), n))
+        return x, (P.T.copy() if want_P else None)
+
+    def get_replica(self, shard):
+        nl = C.c_int()
+        x = np.zeros(self.cap_n)
+        prr = np.zeros(9)
+        self._chk(self.L.ekf_sharded_get_replica(self.h, shard, C.byref(nl), _dp(x), _dp(prr)))
+        return nl.value, x[:3 + 2 * nl.value].copy(), prr.reshape(3, 3).T.copy()
+
+    def get_pose(self):
+        pose = np.zeros(3)
+        nl = np.zeros(1, np.int32)
+        self._chk(self.L.ekf_sharded_get_pose(self.h, _dp(pose), _ip(nl)))
+        return pose, int(nl[0])
+
+    def propagate(self, vel_mm_s, rotvel_deg_s, dt):
+        self._chk(self.L.ekf_sharded_propagate(self.h, vel_mm_s, rotvel_deg_s, dt))
+
+    def update(self, z, R, allow_capacity=False):
+        """z [n_z][2], R [n_z][4] (column-major 2x2): ONE doUpdate call. Returns decision, index, mahal [n_z]."""
+        z = np.ascontiguousarray(z, np.float64).reshape(-1, 2)
+        R = np.ascontiguousarray(R, np.float64).reshape(-1, 4)
+        nz = len(z)
+        dec = np.zeros(nz, np.int32)
+        idx = np.zeros(nz, np.int32)
+        mah = np.zeros(nz)
+        rc = self.L.ekf_sharded_update(self.h, nz, _dp(z), _dp(R), _ip(dec), _ip(idx), _dp(mah))
+        if not (allow_capacity and rc == ERR_CAPACITY):
+            self._chk(rc)
+        return dec, idx, mah
+
+    def update_compass(self, z, R):
+        self._chk(self.L.ekf_sharded_update_compass(self.h, z, R))
+
+    def run(self, records, max_meas, trace=True, pose_trace=False, allow_capacity=False):
+        """records [T][L] (or [1][T][L]) of the one map. Returns the outputs dict of FilterBatch.run with F = 1."""
+        records = np.ascontiguousarray(records, np.float64)
+        if records.ndim == 3:
+            assert records.shape[0] == 1
+            records = records[0]
+        T, L = records.shape
+        assert L == record_len(max_meas)
+        M = max(max_meas, 1)
+        o = {
+            "decision": np.zeros((1, T, M), np.int32) if trace else None,
+            "index": np.zeros((1, T, M), np.int32) if trace else None,
+            "mahal": np.zeros((1, T, M)) if trace else None,
+            "pose_trace": np.zeros((1, T, 3)) if pose_trace else None,
+            "final_pose": np.zeros((1, 3)),
+            "final_nlm": np.zeros((1,), np.int32),
+        }
+        o["_c"] = RunOutputs(_ip(o["decision"]), _ip(o["index"]), _dp(o["mahal"]), _dp(o["pose_trace"]),
+                             _dp(o["final_pose"]), _ip(o["final_nlm"]))
+        rc = self.L.ekf_sharded_run(self.h, T, max_meas, _dp(records), C.byref(o["_c"]))
+        if not (allow_capacity and rc == ERR_CAPACITY):
+            self._chk(rc)
+        return o
+
+    def last_run_ms(self):
+        a, b = C.c_float(), C.c_float()
+        self._chk(self.L.ekf_sharded_last_run_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def kernel_launches(self):
+        return int(self.L.ekf_sharded_kernel_launches(self.h))
+
+
+def device_count():
+    n = 0
+    while core_lib().ekf_device_info(n, None, None, None, None, None) == 0:
+        n += 1
+    return n
 
 
 def device_info(device=0):

@@ -172,6 +172,45 @@ int ekf_measure_fp64_peak(int device, double* flops_per_s);
  * downdate, step epilogue, unused, then 24 finer probes along thread 0 (only in -DEKF_FINE_TIMING builds)}. */
 int ekf_debug_phase_cycles(long long* out32);
 
+/* ---- one large map sharded over several GPUs ---------------------------- */
+/* The covariance of ONE map is split by columns over n_shards devices (one process drives them;
+ * every pair needs CUDA peer access = NVLink on an NVSwitch node). Same reference calls as above,
+ * same bits as the single-GPU large regime for every shard count: the state vector, P_RR and the
+ * landmark count are replicated, the O(n^2) covariance downdate (Update.cpp:188,193-194) runs on
+ * each shard's own columns, and the gain kernel stores its rows of K / W / x straight into every
+ * peer's memory before the sweep (the one exchange step the path has). devices may repeat an
+ * ordinal (several shards on one GPU), which is how the logic is tested on a single-GPU box. */
+#define EKF_SHARDED_MAX_SHARDS 8
+typedef struct ekf_sharded_s* ekf_sharded;
+int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int max_landmarks, const ekf_config* cfg);
+int ekf_sharded_destroy(ekf_sharded m);
+/* kalmanfilter.cpp:7-11 */
+int ekf_sharded_reset(ekf_sharded m);
+int ekf_sharded_n_shards(ekf_sharded m);
+int ekf_sharded_max_landmarks(ekf_sharded m);
+/* Column range [c0, c1) of the covariance held by one shard. */
+int ekf_sharded_columns(ekf_sharded m, int shard, int* c0, int* c1);
+/* As ekf_set_state / ekf_get_state / ekf_get_pose for the one map (P column-major, bit-symmetric). */
+int ekf_sharded_set_state(ekf_sharded m, int n_landmarks, const double* x, const double* P, int ld);
+int ekf_sharded_get_state(ekf_sharded m, int* n_landmarks, double* x, double* P, int ld);
+int ekf_sharded_get_pose(ekf_sharded m, double* xyphi, int32_t* n_landmarks);
+/* Test hook: the replicas one shard holds (x[0:n], P_RR column-major, landmark count). */
+int ekf_sharded_get_replica(ekf_sharded m, int shard, int* n_landmarks, double* x, double* PRR9);
+/* KalmanFilter::doPropagation / doUpdate (n_z <= 16, gating bound frozen at call entry as
+ * Update.cpp:26) / doUpdateCompass for the sharded map; each call synchronises. */
+int ekf_sharded_propagate(ekf_sharded m, double vel_mm_s, double rotvel_deg_s, double dt);
+int ekf_sharded_update(ekf_sharded m, int n_z, const double* z, const double* R, int32_t* decision, int32_t* lm_index,
+                       double* mahal);
+int ekf_sharded_update_compass(ekf_sharded m, double z, double R);
+/* slam.cpp:127-182 for n_steps step records of the one map (layout above, F = 1): all kernels and
+ * exchange steps of all steps are enqueued without a host round trip. */
+int ekf_sharded_run(ekf_sharded m, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out);
+/* Device time of the last ekf_sharded_run (events on shard 0 bracketing cross-shard barriers) and
+ * of one covariance downdate sampled mid-run on shard 0 (0 if none ran). */
+int ekf_sharded_last_run_ms(ekf_sharded m, float* run_ms, float* downdate_ms);
+long long ekf_sharded_kernel_launches(ekf_sharded m);
+const char* ekf_sharded_last_error(ekf_sharded m);
+
 #ifdef __cplusplus
 }
 #endif
