@@ -31,10 +31,12 @@
 // independent of the shard count.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ekf_cta.cuh"
@@ -465,7 +467,8 @@ struct Shard {
   int device = 0, sms = 0, grid = 0;
   int c0 = 0, c1 = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev = nullptr;            // exchange steps of the per-call surface (single host thread)
+  cudaEvent_t evx[2] = {nullptr, nullptr};   // exchange steps of ekf_sharded_run (one host thread per shard)
   double* P = nullptr;
   double* x = nullptr;
   int* nlm = nullptr;
@@ -619,6 +622,110 @@ int check_capacity(ekf_sharded m) {
   return EKF_OK;
 }
 
+// ---- ekf_sharded_run: one host thread per shard ------------------------------------------------------
+// With G shards a step is ~6 G launches plus two exchange steps of G records and G (G-1) waits;
+// issued from one thread that is more host time than the GPUs need for the step at G = 8. Each
+// shard's stream is therefore fed by its own host thread. An exchange step needs every record
+// call to precede the waits on it (cudaStreamWaitEvent captures the event's state at call time):
+// record, host barrier, waits. Two alternating events per shard make one barrier per exchange
+// enough (an event is re-recorded only after the NEXT barrier, by which time every wait on its
+// previous record has been issued).
+struct SpinBarrier {
+  std::atomic<int> count{0};
+  std::atomic<int> gen{0};
+  int n = 1;
+  void wait() {
+    const int g = gen.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+      count.store(0, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (gen.load(std::memory_order_acquire) == g)
+        if (++spins > 4096) std::this_thread::yield();
+    }
+  }
+};
+
+struct RunCtx {
+  ekf_sharded m = nullptr;
+  int T = 0, L = 0, M = 1, max_meas = 0;
+  const double* hrec = nullptr;
+  bool want_trace = false, want_pose = false, timed = false;
+  SpinBarrier bar;
+  cudaError_t err[kMaxShards];
+};
+
+#define TH_CK(call)                                      \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess && c.err[s] == cudaSuccess) c.err[s] = e__;   \
+  } while (0)
+
+// Errors are recorded, never returned early: every thread must reach every barrier.
+void run_shard_thread(RunCtx& c, int s) {
+  ekf_sharded m = c.m;
+  Shard& sh = m->sh[s];
+  const int G = m->G;
+  int xk = 0;
+  auto xchg = [&]() {
+    if (G == 1) return;
+    TH_CK(cudaEventRecord(sh.evx[xk & 1], sh.stream));
+    c.bar.wait();
+    for (int t = 0; t < G; ++t)
+      if (t != s) TH_CK(cudaStreamWaitEvent(sh.stream, m->sh[t].evx[xk & 1], 0));
+    ++xk;
+  };
+  TH_CK(cudaSetDevice(sh.device));
+  xchg();                                   // uploads and resets of every shard precede the first peer store
+  if (s == 0) TH_CK(cudaEventRecord(m->t0, sh.stream));
+  const int g_strip = rows_grid(sh, s == 0 ? m->cap_n : sh.c1 - sh.c0);
+  const int g_rows = rows_grid(sh, sh.c1 - sh.c0);
+  const int g_gate = rows_grid(sh, (sh.c1 - sh.c0) / 2);
+  bool timed = false;
+  for (int t = 0; t < c.T; ++t) {
+    const double* hrec = c.hrec + (size_t)t * c.L;
+    const double* rec = sh.records + (size_t)t * c.L;
+    shard_prop_setup<<<1, 32, 0, sh.stream>>>(sh.args, rec);
+    shard_prop_strip<<<g_strip, kThreads, 0, sh.stream>>>(sh.args);
+    if (hrec[6] != 0.0) {
+      shard_compass_setup<<<1, 32, 0, sh.stream>>>(sh.args, rec + 3);
+      xchg();
+      shard_compass_gain<<<g_rows, kThreads, 0, sh.stream>>>(sh.args);
+      xchg();
+      shard_downdate<1, true><<<sh.grid, kThreads, 0, sh.stream>>>(sh.args);
+    }
+    int nz = (int)hrec[5];
+    nz = nz < 0 ? 0 : nz > c.max_meas ? c.max_meas : nz;
+    for (int q = 0; q < nz; ++q) {
+      const double* zr = rec + 8 + 6 * q;
+      const size_t oi = (size_t)t * c.M + q;
+      const bool out = s == 0 && c.want_trace;
+      shard_gate<<<g_gate, kThreads, 0, sh.stream>>>(sh.args, zr, 0);
+      xchg();
+      shard_decide<<<1, 32, 0, sh.stream>>>(sh.args, zr, out ? m->t_dec + oi : nullptr, out ? m->t_idx + oi : nullptr,
+                                          out ? m->t_mah + oi : nullptr);
+      shard_gain<<<g_rows, kThreads, 0, sh.stream>>>(sh.args);
+      xchg();
+      const bool time_this = s == 0 && !timed && t >= c.T / 2;   // one downdate sampled mid-run on shard 0
+      if (time_this) TH_CK(cudaEventRecord(m->d0, sh.stream));
+      shard_downdate<2, false><<<sh.grid, kThreads, 0, sh.stream>>>(sh.args);
+      if (time_this) TH_CK(cudaEventRecord(m->d1, sh.stream));
+      timed = timed || time_this;
+    }
+    if (s == 0 && c.want_pose)
+      TH_CK(cudaMemcpyAsync(m->t_pose + (size_t)t * 3, sh.x, 3 * sizeof(double), cudaMemcpyDeviceToDevice, sh.stream));
+  }
+  xchg();
+  if (s == 0) {
+    TH_CK(cudaEventRecord(m->t1, sh.stream));
+    c.timed = timed;
+  }
+  TH_CK(cudaGetLastError());
+  TH_CK(cudaStreamSynchronize(sh.stream));
+}
+#undef TH_CK
+
 // Copy the same small host block into every shard's staging buffer at offset off.
 int stage_all(ekf_sharded m, const double* host, size_t count, size_t off) {
   for (int s = 0; s < m->G; ++s) {
@@ -695,6 +802,8 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
     return bail(EKF_ERR_CUDA, std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaEventCreateWithFlags(&sh.ev, cudaEventDisableTiming)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&sh.evx[0], cudaEventDisableTiming)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&sh.evx[1], cudaEventDisableTiming)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
     SH_ALLOC(sh.P, slab * sizeof(double));
     SH_ALLOC(sh.x, (size_t)(m->cap_n + 1) * sizeof(double));
     SH_ALLOC(sh.nlm, sizeof(int));
@@ -756,6 +865,8 @@ int ekf_sharded_destroy(ekf_sharded m) {
       if (m->t0) { cudaEventDestroy(m->t0); cudaEventDestroy(m->t1); cudaEventDestroy(m->d0); cudaEventDestroy(m->d1); }
     }
     if (sh.ev) cudaEventDestroy(sh.ev);
+    if (sh.evx[0]) cudaEventDestroy(sh.evx[0]);
+    if (sh.evx[1]) cudaEventDestroy(sh.evx[1]);
     if (sh.stream) cudaStreamDestroy(sh.stream);
   }
   delete m;
@@ -961,46 +1072,37 @@ int ekf_sharded_run(ekf_sharded m, int n_steps, int max_meas, const double* reco
     SH_CK(m, cudaMalloc(&m->t_pose, (size_t)T * 3 * sizeof(double)));
     m->pose_cap = (size_t)T * 3;
   }
-  int rc = exchange(m);
-  if (rc != EKF_OK) return rc;
-  SH_CK(m, cudaSetDevice(s0.device));
-  SH_CK(m, cudaEventRecord(m->t0, s0.stream));
-  bool timed = false;
+  RunCtx c;
+  c.m = m;
+  c.T = T; c.L = L; c.M = M; c.max_meas = max_meas;
+  c.hrec = records;
+  c.want_trace = want_trace;
+  c.want_pose = want_pose;
+  c.bar.n = m->G;
+  for (int s = 0; s < kMaxShards; ++s) c.err[s] = cudaSuccess;
+  if (m->G == 1) {
+    run_shard_thread(c, 0);
+  } else {
+    std::vector<std::thread> th;
+    for (int s = 1; s < m->G; ++s) th.emplace_back(run_shard_thread, std::ref(c), s);
+    run_shard_thread(c, 0);
+    for (auto& t : th) t.join();
+  }
+  long long per_step = 0;
   for (int t = 0; t < T; ++t) {
     const double* hrec = records + (size_t)t * L;
-    const double* ptr[kMaxShards];
-    for (int s = 0; s < m->G; ++s) ptr[s] = m->sh[s].records + (size_t)t * L;
-    if ((rc = enqueue_propagate(m, ptr)) != EKF_OK) return rc;
-    if (hrec[6] != 0.0) {
-      const double* pc[kMaxShards];
-      for (int s = 0; s < m->G; ++s) pc[s] = ptr[s] + 3;
-      if ((rc = enqueue_compass(m, pc)) != EKF_OK) return rc;
-    }
     int nz = (int)hrec[5];
     nz = nz < 0 ? 0 : nz > max_meas ? max_meas : nz;
-    for (int q = 0; q < nz; ++q) {
-      const double* pz[kMaxShards];
-      for (int s = 0; s < m->G; ++s) pz[s] = ptr[s] + 8 + 6 * q;
-      const size_t oi = (size_t)t * M + q;
-      const bool time_this = !timed && t >= T / 2;     // one downdate sampled mid-run on shard 0
-      if ((rc = enqueue_update(m, pz, 0, want_trace ? m->t_dec + oi : nullptr, want_trace ? m->t_idx + oi : nullptr,
-                               want_trace ? m->t_mah + oi : nullptr, time_this)) != EKF_OK)
-        return rc;
-      timed = timed || time_this;
-    }
-    if (want_pose) {
-      SH_CK(m, cudaSetDevice(s0.device));
-      SH_CK(m, cudaMemcpyAsync(m->t_pose + (size_t)t * 3, s0.x, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s0.stream));
-    }
+    per_step += 2 + (hrec[6] != 0.0 ? 3 : 0) + 4 * nz;
   }
-  if ((rc = exchange(m)) != EKF_OK) return rc;
-  SH_CK(m, cudaSetDevice(s0.device));
-  SH_CK(m, cudaEventRecord(m->t1, s0.stream));
-  if ((rc = sync_all(m)) != EKF_OK) return rc;
+  m->launches += per_step * m->G;
+  for (int s = 0; s < m->G; ++s)
+    if (c.err[s] != cudaSuccess)
+      return sfail(m, EKF_ERR_CUDA, "ekf_sharded_run, shard " + std::to_string(s) + ": " + cudaGetErrorString(c.err[s]));
   SH_CK(m, cudaSetDevice(s0.device));
   SH_CK(m, cudaEventElapsedTime(&m->last_ms, m->t0, m->t1));
   m->last_downdate_ms = 0.f;
-  if (timed) SH_CK(m, cudaEventElapsedTime(&m->last_downdate_ms, m->d0, m->d1));
+  if (c.timed) SH_CK(m, cudaEventElapsedTime(&m->last_downdate_ms, m->d0, m->d1));
   if (out) {
     if (out->decision) SH_CK(m, cudaMemcpy(out->decision, m->t_dec, TM * sizeof(int), cudaMemcpyDeviceToHost));
     if (out->lm_index) SH_CK(m, cudaMemcpy(out->lm_index, m->t_idx, TM * sizeof(int), cudaMemcpyDeviceToHost));

@@ -252,6 +252,40 @@ def large_map_leg(ekf, n_lm, steps, hbm_peak, device):
     return res
 
 
+def sharded_map_leg(ekf, n_lm, steps, hbm_peak, devices):
+    """the same large-map workload with the covariance column-sharded over
+    several GPUs (one process, peer stores over NVLink for the one exchange the path has)."""
+    from parity import injected_state
+    syn = ekf.Synth(n_lm, steps_per_lap=10 ** 7, max_meas=1)
+    rec = syn.generate(1, steps)
+    x0, P0 = injected_state(syn.world(), seed=n_lm)
+    sm = ekf.ShardedMap(devices, n_lm + 2)
+    sm.set_state(x0, P0, symmetric=True)
+    sm.run(rec, 1, trace=True)                 # warm-up pass
+    sm.set_state(x0, P0, symmetric=True)
+    del P0
+    l0 = sm.kernel_launches()
+    out = sm.run(rec, 1, trace=True)
+    ms, dms = sm.last_run_ms()
+    l1 = sm.kernel_launches()
+    n_old = int((out["decision"] == 1).sum())
+    cols = [sm.columns(s) for s in range(len(devices))]
+    sm.close()
+    alg = large_bytes(n_lm)
+    n = 3 + 2 * n_lm
+    alg0 = 16.0 * n * (cols[0][1] - cols[0][0])      # shard 0's share of the downdate traffic
+    G = len(devices)
+    return {"workload": "1 map x %d landmarks (n=%d, P=%.2f GB) column-sharded over devices %s, %d update steps" %
+                        (n_lm, n, 8.0 * n * n / 1e9, list(devices), steps),
+            "shards": G, "old_updates": n_old, "steps": steps, "ms_per_step": ms / steps,
+            "update_steps_per_s": steps / (ms * 1e-3), "gpu_launches": int(l1 - l0),
+            "step_gbs_aggregate": alg * n_old / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "shard_downdate<2> (shard 0, one launch sampled mid-run)",
+                         "achieved": alg0 / (dms * 1e-3) / 1e9 if dms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (alg0 / (dms * 1e-3) / 1e9) / hbm_peak if dms > 0 else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg0, "avg_kernel_ms": dms, "launches_timed": 1 if dms > 0 else 0}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -260,6 +294,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--filters-per-gpu", type=int, default=4096)
     ap.add_argument("--large-map", default="2000,10000", help="comma list of landmark counts for the regime-B leg ('' = skip)")
+    ap.add_argument("--sharded-map", default="", help="landmark count for the multi-GPU sharded single-map leg ('' = skip)")
+    ap.add_argument("--shard-devices", default="", help="comma list of device ordinals for --sharded-map (default: all visible)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--meas", type=int, default=1,
                     help="measurements (doUpdate calls) per step; the headline is 1, SURVEY 8d also asks for 4")
@@ -381,6 +417,10 @@ def main():
             legs.append(large_map_leg(ekf, n_lm, steps, hbm_peak, local))
         line["large_map"] = legs
         line["roofline_hbm"] = dict(legs[-1]["roofline"], peak_source=hbm_src)
+    if world == 1 and args.sharded_map:
+        devs = [int(t) for t in args.shard_devices.split(",") if t.strip()] or list(range(ekf.device_count()))
+        steps = 400 if int(args.sharded_map) <= 4000 else 60
+        line["sharded_map"] = [sharded_map_leg(ekf, int(args.sharded_map), steps, hbm_peak, devs)]
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(rec)
         line["cpu_baseline"] = cb
