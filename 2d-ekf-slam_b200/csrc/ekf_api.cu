@@ -697,6 +697,11 @@ int ekf_debug_phase_cycles(long long* out8) {
   return ekf_tile_phase_cycles(out8) == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
 }
 
+int ekf_debug_stile_timestamps(long long* out128) {
+  if (!out128) return EKF_ERR_BAD_ARG;
+  return ekf_stile_timestamps(out128) == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
+}
+
 int ekf_measure_fp64_peak(int device, double* flops_per_s) {
   if (!flops_per_s) return EKF_ERR_BAD_ARG;
   int n = 0;

@@ -60,6 +60,7 @@ cudaError_t ekf_tile_run(const EkfState& st, const EkfRunIO& io, const EkfConst&
 // Shared-memory tiled-triangle variant of the fused path (ekf_stile.cu): four filters per SM.
 int ekf_stile_max_landmarks();
 int ekf_stile_ctas_per_sm(int cap_lm);
+cudaError_t ekf_stile_timestamps(long long* out128);
 cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
 
 // ---- regime B: whole grid per filter, covariance streamed from HBM (ekf_large.cu) ---------------

@@ -34,19 +34,39 @@
 
 namespace {
 
+#ifdef EKF_STILE_TIMING
+// Profiling builds only: lane 0 of every warp of CTA 0 stamps its ARRIVAL at each barrier of one
+// step (first filter, step 500), so the phase critical paths can be read as max-over-warps deltas.
+__device__ long long g_stile_ts[8][16];
+#define STILE_TS(kk)                                                                              \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && f == 0 && t == 500 && (threadIdx.x & 31) == 0) g_stile_ts[threadIdx.x >> 5][kk] = clock64(); \
+  } while (0)
+#else
+#define STILE_TS(kk) do { } while (0)
+#endif
+
 template <int NB>
 struct STileCfg {
   static constexpr int NI = 8 * NB;                    // padded internal dimension
   static constexpr int NTILES = NB * (NB + 1);         // tiles (I,J), I = r/4, J = c/8, J <= I/2
-  static constexpr int THREADS = (NTILES + 31) / 32 * 32;
+  // Plane stride of the tile storage T[a + 4b][PS] in doubles: the smallest value >= NTILES that is
+  // 4 or 12 (mod 16). One tile per lane is conflict-free for any stride; the row-wise accesses of
+  // the O(n) phases (lane = row r: plane r&3, tile r>>2; lane = landmark: planes {0,2} / {1,3})
+  // are conflict-free only when 4 consecutive planes land 4 double-banks apart.
+  static constexpr int PS = NTILES + ((4 - NTILES % 8) % 8 + 8) % 8;
+  // One warp more than the tiles need: the helper warp (scalar chains, robot block, S^-1) owns no
+  // tile, so its sincos chain runs beside the other warps' downdate instead of in front of its own
+  // (measured +4 %; 72 registers per thread at four CTAs per SM).
+  static constexpr int THREADS = (NTILES + 31) / 32 * 32 + 32;
   static constexpr int NW = THREADS / 32;
   static constexpr int MAX_LM = (NI - 4) / 2;
   static constexpr int GA = (MAX_LM + 31) / 32;        // warps per gating group
   static constexpr int LMP = GA * 32;
-  static constexpr int SP0 = NTILES - (NW - 1) * 32;   // first spare lane of the last warp
+  static constexpr int SP0 = 0;                        // first helper lane of the last warp
   static constexpr int MINB = NB == 13 ? 4 : (NB == 14 ? 3 : 2);
   static_assert(2 * GA <= NW - 1, "gating groups must not use the helper warp");
-  static_assert(THREADS - NTILES >= 10 && SP0 + 9 <= 32, "need ten spare lanes in the last warp");
+  static_assert(NTILES <= (NW - 1) * 32 && SP0 + 9 <= 32, "the helper warp owns no tile");
   static_assert(NI <= THREADS, "one state row per thread");
 };
 
@@ -103,7 +123,7 @@ __device__ __forceinline__ int tile_number(int I, int J) { return J * (2 * NB) -
 // index of P(r, c), r >= c, in the plane-major tile storage
 template <int NB>
 __device__ __forceinline__ int pidx_lower(int r, int c) {
-  return ((r & 3) + 4 * (c & 7)) * STileCfg<NB>::NTILES + tile_number<NB>(r >> 2, c >> 3);
+  return ((r & 3) + 4 * (c & 7)) * STileCfg<NB>::PS + tile_number<NB>(r >> 2, c >> 3);
 }
 template <int NB>
 __device__ __forceinline__ int pidx(int r, int c) { return r >= c ? pidx_lower<NB>(r, c) : pidx_lower<NB>(c, r); }
@@ -113,7 +133,7 @@ __device__ __forceinline__ int widx(int r) { return (r & 7) * NB + (r >> 3); }  
 template <int NB, int RANK>
 __device__ __forceinline__ void tile_downdate(double* __restrict__ Tt, const double2* __restrict__ W, int I, int J,
                                               double m0, double m1) {
-  constexpr int NT = STileCfg<NB>::NTILES;
+  constexpr int NT = STileCfg<NB>::PS;   // plane stride
   double2 wi[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) wi[a] = W[(4 * (I & 1) + a) * NB + (I >> 1)];
@@ -139,14 +159,14 @@ __device__ __forceinline__ void tile_downdate(double* __restrict__ Tt, const dou
 template <int NB>
 __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf_batch_stile_kernel(const RunArgs a) {
   using C = STileCfg<NB>;
-  constexpr int NT = C::NTILES, SP0 = C::SP0;
+  constexpr int NT = C::PS, SP0 = C::SP0;   // NT: plane stride of the tile storage
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* T = reinterpret_cast<double*>(smem_raw);                               // [32][NT]
   STileSmem<NB>& sm = *reinterpret_cast<STileSmem<NB>*>(smem_raw + (size_t)32 * NT * sizeof(double));
   double* recbuf = reinterpret_cast<double*>(smem_raw + (size_t)32 * NT * sizeof(double) +
                                              ((sizeof(STileSmem<NB>) + 15) & ~(size_t)15));   // [2][Lp]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool is_tile = tid < NT;
+  const bool is_tile = tid < C::NTILES;
   const bool helper_warp = warp == C::NW - 1;
   const bool sc_prop = helper_warp && lane == SP0;
   const bool sc_trig = helper_warp && lane == SP0 + 1;
@@ -227,6 +247,8 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
         for (int i = tid; i < L; i += C::THREADS) cp_async8(nxt + i, g + i);
       }
       const int nz = (int)cur[5];
+      bool rec_ready = false;
+      STILE_TS(0);
       // ---- doPropagation (slam.cpp:136) ------------------------------------------------------------
       if (!scalar_done) {
         scalar_chains(cur);
@@ -263,6 +285,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
         ekf_prop_col(sm.prop, a0, a1, a2);
         T[rowbase] = a0; T[rowbase + 4 * NT] = a1; T[rowbase + 8 * NT] = a2;
       }
+      STILE_TS(1);
       __syncthreads();
 
       bool setup_valid = true;
@@ -330,6 +353,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
 #pragma unroll
               for (int q = 0; q < 4; ++q) { sm.t34[q][lm] = t3[q]; sm.t34[4 + q][lm] = t4[q]; }
             }
+            STILE_TS(2);
             named_barrier(1, 2 * C::GA * 32);
             if (groupA) {
               double val = INFINITY;
@@ -365,6 +389,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
               }
             }
           }
+          STILE_TS(3);
           __syncthreads();
           // ---- decision (Update.cpp:152,181,191), uniform over the CTA -----------------------------
           int wsel = 0;
@@ -384,6 +409,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
             index = opt_i ? opt_i - 1 : 0;   // external state index
           }
           const Candidate& cd = sm.cand[wsel];
+          STILE_TS(9);
 
           if (decision == EKF_DEC_OLD) {
             const int Li = cd.idx;
@@ -420,7 +446,10 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
               M0 = A0 + B0;
               M1 = A1 + B1;
             }
+            STILE_TS(10);
             cp_async_wait_all();   // next step's record (prefetched at step start) is visible after the barrier
+            rec_ready = true;
+            STILE_TS(4);
             __syncthreads();
             // ---- gain, state correction, downdate vectors (Update.cpp:186-187) --------------------
             if (tid < C::NI) {
@@ -434,6 +463,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
               }
               sm.W[widx<NB>(tid)] = w;
             }
+            STILE_TS(5);
             __syncthreads();
             // x is final for this step if this was its last measurement: run the next step's scalar
             // chains now, on two spare lanes, while every warp does its covariance downdate.
@@ -443,6 +473,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
             }
             // ---- covariance downdate (Update.cpp:188,193-194) -----------------------------------------
             if (is_tile && 4 * I < n_int) tile_downdate<NB, 2>(Tt, sm.W, I, J, sm.post.m0, sm.post.m1);
+            STILE_TS(6);
             __syncthreads();
           } else if (decision == EKF_DEC_NEW) {
             // ---- state augmentation (Update.cpp:152-178) -----------------------------------------
@@ -511,9 +542,19 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
           if (a.io.mahal) a.io.mahal[oi] = mahal;
         }
       }
-      if (a.io.pose_trace && tid < 3) a.io.pose_trace[((size_t)f * T_steps + t) * 3 + tid] = sm.xs[tid];   // slam.cpp:181
-      cp_async_wait_all();
-      __syncthreads();
+      if (a.io.pose_trace && sc_prop) {   // slam.cpp:181; by the lane that overwrites the pose at the next step start
+        double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
+        pt[0] = sm.xs[0]; pt[1] = sm.xs[1]; pt[2] = sm.xs[2];
+      }
+      // The next step's record (prefetched at step start) must be visible to every thread. An Old
+      // update already waited for it in front of one of its barriers and ended on a barrier (the
+      // decision is CTA-uniform), so only the other paths pay for this one.
+      if (!rec_ready) {
+        cp_async_wait_all();
+        STILE_TS(7);
+        __syncthreads();
+      }
+      STILE_TS(8);
     }
 
     // ---- write back to HBM (external layout, both triangles) -------------------------------------
@@ -543,7 +584,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
 
 template <int NB>
 size_t stile_smem_bytes(int L) {
-  return (size_t)32 * STileCfg<NB>::NTILES * sizeof(double) + ((sizeof(STileSmem<NB>) + 15) & ~(size_t)15) +
+  return (size_t)32 * STileCfg<NB>::PS * sizeof(double) + ((sizeof(STileSmem<NB>) + 15) & ~(size_t)15) +
          (size_t)2 * ((L + 1) & ~1) * sizeof(double);
 }
 
@@ -577,6 +618,16 @@ cudaError_t launch_stile(const RunArgs& a, int sm_count, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// Profiling builds (-DEKF_STILE_TIMING): the barrier-arrival stamps of one step, [warp][barrier].
+cudaError_t ekf_stile_timestamps(long long* out128) {
+#ifdef EKF_STILE_TIMING
+  return cudaMemcpyFromSymbol(out128, g_stile_ts, sizeof(long long) * 128);
+#else
+  for (int i = 0; i < 128; ++i) out128[i] = 0;
+  return cudaSuccess;
+#endif
+}
 
 int ekf_stile_max_landmarks() { return STileCfg<16>::MAX_LM; }
 

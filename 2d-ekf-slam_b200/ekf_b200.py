@@ -123,6 +123,7 @@ def core_lib():
                                       C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.ekf_measure_fp64_peak.argtypes = [C.c_int, c_dp]
         L.ekf_debug_phase_cycles.argtypes = [C.POINTER(C.c_longlong)]
+        L.ekf_debug_stile_timestamps.argtypes = [C.POINTER(C.c_longlong)]
         L.ekf_sharded_create.argtypes = [C.POINTER(H), C.c_int, c_ip, C.c_int, C.POINTER(Config)]
         L.ekf_sharded_destroy.argtypes = [H]
         L.ekf_sharded_reset.argtypes = [H]
@@ -546,6 +547,12 @@ def debug_phase_cycles(read=True):
     buf = (C.c_longlong * 32)()
     core_lib().ekf_debug_phase_cycles(buf)
     return list(buf)
+
+
+def debug_stile_timestamps():
+    out = (C.c_longlong * 128)()
+    core_lib().ekf_debug_stile_timestamps(out)
+    return np.array(out[:], np.int64).reshape(8, 16)
 
 
 def measure_fp64_peak(device=0):

@@ -171,6 +171,10 @@ int ekf_measure_fp64_peak(int device, double* flops_per_s);
  * 32 counters {scalar chains, covariance propagate, gating, column publish, gain rows,
  * downdate, step epilogue, unused, then 24 finer probes along thread 0 (only in -DEKF_FINE_TIMING builds)}. */
 int ekf_debug_phase_cycles(long long* out32);
+/* Profiling aid for the shared-memory tiled fused kernel (-DEKF_STILE_TIMING builds, zeros
+ * otherwise): clock64 at which lane 0 of each warp of CTA 0 arrived at each barrier of one step
+ * (first filter, step 500), out128 = [8 warps][16 barriers]. */
+int ekf_debug_stile_timestamps(long long* out128);
 
 /* ---- one large map sharded over several GPUs ---------------------------- */
 /* The covariance of ONE map is split by columns over n_shards devices (one process drives them;

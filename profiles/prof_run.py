@@ -48,6 +48,20 @@ def batch(F=592, T=1000, cap=50):
                     "propagate (own)", "barrier (robot block/strip)", "-", "-"]
             for n, c in zip(fine, cyc[8:]):
                 print("    %-24s %8.0f" % (n, c / (per * T)))
+    if os.environ.get("EKF_STILE_TS"):      # -DEKF_STILE_TIMING builds: barrier arrivals of one step
+        ts = ekf.debug_stile_timestamps()
+        names = ["step start", "B1 propagate done", "B2 gating terms (named)", "B3 gating done", "B4 P*H^T rows / S^-1",
+                 "B5 gain, x, W", "B6 downdate", "B7 end of step", "after B7", "  (decision known)", "  (rows / S^-1 done)"]
+        t0 = ts[:, 0][ts[:, 0] > 0].min()
+        print("barrier arrivals of CTA 0, first filter, step 500 (cycles since the first warp entered the step):")
+        print("  %-26s %s   phase (max-to-max)" % ("", " ".join("   w%d" % w for w in range(8))))
+        prev = None
+        for kk, nm in enumerate(names):
+            row = ts[:, kk]
+            cells = " ".join("%5d" % (v - t0) if v > 0 else "    -" for v in row)
+            mx = row[row > 0].max() - t0 if (row > 0).any() else 0
+            print("  %-26s %s   %s" % (nm, cells, "" if prev is None else "%5d" % (mx - prev)))
+            prev = mx
     assert (out["final_nlm"] == 50).mean() > 0.99
     ms, n = fb.kernel_time()
     print("batch: F=%d T=%d avg kernel %.3f ms over %d launches -> %.3e filter-steps/s"
