@@ -20,6 +20,7 @@
 // in ekf_cta.cuh.
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
+#include "ekf_pdl.cuh"
 
 namespace {
 
@@ -53,6 +54,7 @@ __device__ __forceinline__ double* filt_x(const LargeArgs& a) { return a.st.x + 
 
 // ---- propagate ---------------------------------------------------------------------------------
 __global__ void large_prop_setup(const LargeArgs a, const double* vel, const double* rot, const double* dt) {
+  ekf_pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double* P = filt_P(a);
   double* x = filt_x(a);
@@ -74,6 +76,7 @@ __global__ void large_prop_setup(const LargeArgs a, const double* vel, const dou
 
 __global__ void __launch_bounds__(kThreads) large_prop_strip(const LargeArgs a) {
   __shared__ PropSetup ps;
+  ekf_pdl_entry();
   if (threadIdx.x == 0) ps = a.sm->prop;
   __syncthreads();
   double* P = filt_P(a);
@@ -108,6 +111,7 @@ __device__ __forceinline__ void load_gate_inputs(const double* P, int ld, int Li
 // call: Update.cpp:26 read n_lm once, so landmarks added since the call began are not candidates.
 __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const double* zr, int chunk_pos) {
   __shared__ CtaScratch sc;
+  ekf_pdl_entry();
   const double* P = filt_P(a);
   const double* x = filt_x(a);
   const int ld = a.st.ld;
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const 
 __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, const double* zr, int* out_decision,
                                                         int* out_index, double* out_mahal) {
   __shared__ CtaScratch sc;
+  ekf_pdl_entry();
   double val = INFINITY;
   int idx = INT_MAX;
   for (int c = threadIdx.x; c < a.n_cand; c += kThreads) {
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
 
 // ---- update: gain / augmentation (O(n)) ----------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) large_gain(const LargeArgs a) {
+  ekf_pdl_entry();
   const LargeSmall* sm = a.sm;
   const int decision = sm->decision;
   if (decision != EKF_DEC_OLD && decision != EKF_DEC_NEW) return;
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(kThreads) large_gain(const LargeArgs a) {
 constexpr int kCB = 8;
 template <int RANK, bool COMPASS>
 __global__ void __launch_bounds__(kThreads) large_downdate(const LargeArgs a) {
+  ekf_pdl_entry();
   const LargeSmall* sm = a.sm;
   if (!COMPASS) {
     if (sm->decision != EKF_DEC_OLD) {
@@ -341,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) large_downdate(const LargeArgs a) {
 
 // ---- compass ---------------------------------------------------------------------------------------
 __global__ void large_compass_setup(const LargeArgs a, const double* z, const double* R) {
+  ekf_pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double* P = filt_P(a);
   const double* x = filt_x(a);
@@ -354,6 +362,7 @@ __global__ void large_compass_setup(const LargeArgs a, const double* z, const do
 }
 
 __global__ void __launch_bounds__(kThreads) large_compass_gain(const LargeArgs a) {
+  ekf_pdl_entry();
   const LargeSmall* sm = a.sm;
   const double* P = filt_P(a);
   double* x = filt_x(a);
@@ -394,35 +403,35 @@ int row_grid(const EkfState& st, const EkfLargeWork& wk) {
 
 void launch_propagate(const LargeArgs& a, const EkfState& st, const EkfLargeWork& wk, const double* vel,
                       const double* rot, const double* dt, cudaStream_t s) {
-  large_prop_setup<<<1, 32, 0, s>>>(a, vel, rot, dt);
-  large_prop_strip<<<row_grid(st, wk), kThreads, 0, s>>>(a);
+  ekf_launch_pdl(large_prop_setup, 1, 32, 0, s, a, vel, rot, dt);
+  ekf_launch_pdl(large_prop_strip, row_grid(st, wk), kThreads, 0, s, a);
 }
 void launch_update(LargeArgs a, const EkfState& st, const EkfLargeWork& wk, const double* zr, int chunk_pos, int* dec,
                    int* idx, double* mah, EkfLargeTiming* tm, cudaStream_t s) {
   const int gg = gate_grid(st, wk);
   a.n_cand = gg;
-  large_gate<<<gg, kThreads, 0, s>>>(a, zr, chunk_pos);
-  large_decide<<<1, kThreads, 0, s>>>(a, zr, dec, idx, mah);
-  large_gain<<<row_grid(st, wk), kThreads, 0, s>>>(a);
+  ekf_launch_pdl(large_gate, gg, kThreads, 0, s, a, zr, chunk_pos);
+  ekf_launch_pdl(large_decide, 1, kThreads, 0, s, a, zr, dec, idx, mah);
+  ekf_launch_pdl(large_gain, row_grid(st, wk), kThreads, 0, s, a);
   const bool sample = tm && tm->used < tm->cap && (tm->seen++ % tm->every) == 0;
   if (sample) cudaEventRecord(tm->ev0[tm->used], s);
   if (wk.use_tma) {
     EkfLargeTmaArgs t{&a.sm->decision, &a.sm->n, &a.sm->m0, &a.sm->m1, a.W, a.st.nlm + a.f, &a.sm->n_lm};
     ekf_large_tma_downdate(t, wk.tmaps + (size_t)a.f * ekf_large_tma_map_bytes(), wk.tma_grid, false, s);
   } else {
-    large_downdate<2, false><<<wk.grid, kThreads, 0, s>>>(a);
+    ekf_launch_pdl(large_downdate<2, false>, wk.grid, kThreads, 0, s, a);
   }
   if (sample) cudaEventRecord(tm->ev1[tm->used++], s);
 }
 void launch_compass(const LargeArgs& a, const EkfState& st, const EkfLargeWork& wk, const double* z, const double* R,
                     cudaStream_t s) {
-  large_compass_setup<<<1, 32, 0, s>>>(a, z, R);
-  large_compass_gain<<<row_grid(st, wk), kThreads, 0, s>>>(a);
+  ekf_launch_pdl(large_compass_setup, 1, 32, 0, s, a, z, R);
+  ekf_launch_pdl(large_compass_gain, row_grid(st, wk), kThreads, 0, s, a);
   if (wk.use_tma) {
     EkfLargeTmaArgs t{nullptr, &a.sm->n, &a.sm->cm0, &a.sm->cm0, a.W, nullptr, nullptr};
     ekf_large_tma_downdate(t, wk.tmaps + (size_t)a.f * ekf_large_tma_map_bytes(), wk.tma_grid, true, s);
   } else {
-    large_downdate<1, true><<<wk.grid, kThreads, 0, s>>>(a);
+    ekf_launch_pdl(large_downdate<1, true>, wk.grid, kThreads, 0, s, a);
   }
 }
 

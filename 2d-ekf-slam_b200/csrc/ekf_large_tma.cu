@@ -14,6 +14,7 @@
 
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
+#include "ekf_pdl.cuh"
 
 namespace {
 
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
   double* tiles = reinterpret_cast<double*>(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * kTileBytes);
   uint64_t* done = full + STAGES;
+  ekf_pdl_entry();
   if (!COMPASS) {
     const int dec = *q.decision;
     if (dec != EKF_DEC_OLD) {
@@ -210,7 +212,6 @@ cudaError_t ekf_large_tma_downdate(const EkfLargeTmaArgs& t, const void* map, in
   q.decision = t.decision; q.n_dim = t.n_dim; q.m0 = t.m0; q.m1 = t.m1; q.W = t.W; q.nlm_out = t.nlm_out; q.n_lm = t.n_lm;
   const size_t bytes = (size_t)STAGES * kTileBytes + 2 * STAGES * sizeof(uint64_t);
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(map);
-  if (compass) large_downdate_tma<1, true><<<grid, kThreadsTma, bytes, s>>>(q, *m);
-  else large_downdate_tma<2, false><<<grid, kThreadsTma, bytes, s>>>(q, *m);
-  return cudaGetLastError();
+  if (compass) return ekf_launch_pdl(large_downdate_tma<1, true>, grid, kThreadsTma, bytes, s, q, *m);
+  return ekf_launch_pdl(large_downdate_tma<2, false>, grid, kThreadsTma, bytes, s, q, *m);
 }

@@ -41,6 +41,7 @@
 
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
+#include "ekf_pdl.cuh"
 #include "ekf_slam_b200.h"
 
 namespace {
@@ -95,6 +96,7 @@ __device__ __forceinline__ double* scol(const ShardArgs& a, int j) { return a.P 
 
 // ---- propagate ---------------------------------------------------------------------------------
 __global__ void shard_prop_setup(const ShardArgs a, const double* in3) {
+  ekf_pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double* x = a.x;
   PropSetup p;
@@ -114,6 +116,7 @@ __global__ void shard_prop_setup(const ShardArgs a, const double* in3) {
 }
 
 __global__ void __launch_bounds__(kThreads) shard_prop_strip(const ShardArgs a) {
+  ekf_pdl_entry();
   __shared__ PropSetup ps;
   if (threadIdx.x == 0) ps = a.sm->prop;
   __syncthreads();
@@ -159,6 +162,7 @@ __device__ __forceinline__ void shard_gate_inputs(const ShardArgs& a, int Li, do
 // chunk_pos as in ekf_large.cu: 0 separate doUpdate call, 1 first / 2 later measurement of an
 // n_z > 1 call (gating bound frozen at call entry, Update.cpp:26).
 __global__ void __launch_bounds__(kThreads) shard_gate(const ShardArgs a, const double* zr, int chunk_pos) {
+  ekf_pdl_entry();
   __shared__ CtaScratch sc;
   __shared__ bool last;
   const double* x = a.x;
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(kThreads) shard_gate(const ShardArgs a, const 
 
 // ---- update: decision (every shard, identically) -------------------------------------------------
 __global__ void shard_decide(const ShardArgs a, const double* zr, int* out_decision, int* out_index, double* out_mahal) {
+  ekf_pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ShardSmall* sm = a.sm;
   double val = INFINITY;
@@ -295,6 +300,7 @@ __global__ void shard_decide(const ShardArgs a, const double* zr, int* out_decis
 
 // ---- update: gain / augmentation of the own rows + exchange 2 ------------------------------------
 __global__ void __launch_bounds__(kThreads) shard_gain(const ShardArgs a) {
+  ekf_pdl_entry();
   const ShardSmall* sm = a.sm;
   const int decision = sm->decision;
   if (decision != EKF_DEC_OLD && decision != EKF_DEC_NEW) return;
@@ -355,6 +361,7 @@ __global__ void __launch_bounds__(kThreads) shard_gain(const ShardArgs a) {
 // ---- the HBM-bound kernel over the own columns ---------------------------------------------------
 template <int RANK, bool COMPASS>
 __global__ void __launch_bounds__(kThreads) shard_downdate(const ShardArgs a) {
+  ekf_pdl_entry();
   ShardSmall* sm = a.sm;
   const int n = sm->n;
   if (!COMPASS && sm->decision != EKF_DEC_OLD) {
@@ -434,6 +441,7 @@ __global__ void __launch_bounds__(kThreads) shard_downdate(const ShardArgs a) {
 
 // ---- compass ---------------------------------------------------------------------------------------
 __global__ void shard_compass_setup(const ShardArgs a, const double* zR) {
+  ekf_pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ShardSmall* sm = a.sm;
   sm->cres = ekf_compass_residual(a.x[2], zR[0], a.k);
@@ -445,6 +453,7 @@ __global__ void shard_compass_setup(const ShardArgs a, const double* zR) {
 }
 
 __global__ void __launch_bounds__(kThreads) shard_compass_gain(const ShardArgs a) {
+  ekf_pdl_entry();
   const ShardSmall* sm = a.sm;
   const int n = sm->n;
   const double res = sm->cres, invS = 1 / sm->cS, sq = sm->csq;
@@ -548,8 +557,8 @@ int enqueue_propagate(ekf_sharded m, const double* const* in3) {
   for (int s = 0; s < m->G; ++s) {
     Shard& sh = m->sh[s];
     SH_CK(m, cudaSetDevice(sh.device));
-    shard_prop_setup<<<1, 32, 0, sh.stream>>>(sh.args, in3[s]);
-    shard_prop_strip<<<rows_grid(sh, s == 0 ? m->cap_n : sh.c1 - sh.c0), kThreads, 0, sh.stream>>>(sh.args);
+    ekf_launch_pdl(shard_prop_setup, 1, 32, 0, sh.stream, sh.args, in3[s]);
+    ekf_launch_pdl(shard_prop_strip, rows_grid(sh, s == 0 ? m->cap_n : sh.c1 - sh.c0), kThreads, 0, sh.stream, sh.args);
   }
   m->launches += 2 * m->G;
   return EKF_OK;
@@ -559,15 +568,15 @@ int enqueue_update(ekf_sharded m, const double* const* zr, int chunk_pos, int* d
   for (int s = 0; s < m->G; ++s) {
     Shard& sh = m->sh[s];
     SH_CK(m, cudaSetDevice(sh.device));
-    shard_gate<<<rows_grid(sh, (sh.c1 - sh.c0) / 2), kThreads, 0, sh.stream>>>(sh.args, zr[s], chunk_pos);
+    ekf_launch_pdl(shard_gate, rows_grid(sh, (sh.c1 - sh.c0) / 2), kThreads, 0, sh.stream, sh.args, zr[s], chunk_pos);
   }
   int rc = exchange(m);
   if (rc != EKF_OK) return rc;
   for (int s = 0; s < m->G; ++s) {
     Shard& sh = m->sh[s];
     SH_CK(m, cudaSetDevice(sh.device));
-    shard_decide<<<1, 32, 0, sh.stream>>>(sh.args, zr[s], s == 0 ? dec : nullptr, s == 0 ? idx : nullptr, s == 0 ? mah : nullptr);
-    shard_gain<<<rows_grid(sh, sh.c1 - sh.c0), kThreads, 0, sh.stream>>>(sh.args);
+    ekf_launch_pdl(shard_decide, 1, 32, 0, sh.stream, sh.args, zr[s], s == 0 ? dec : nullptr, s == 0 ? idx : nullptr, s == 0 ? mah : nullptr);
+    ekf_launch_pdl(shard_gain, rows_grid(sh, sh.c1 - sh.c0), kThreads, 0, sh.stream, sh.args);
   }
   rc = exchange(m);
   if (rc != EKF_OK) return rc;
@@ -575,7 +584,7 @@ int enqueue_update(ekf_sharded m, const double* const* zr, int chunk_pos, int* d
     Shard& sh = m->sh[s];
     SH_CK(m, cudaSetDevice(sh.device));
     if (s == 0 && time_downdate) SH_CK(m, cudaEventRecord(m->d0, sh.stream));
-    shard_downdate<2, false><<<sh.grid, kThreads, 0, sh.stream>>>(sh.args);
+    ekf_launch_pdl(shard_downdate<2, false>, sh.grid, kThreads, 0, sh.stream, sh.args);
     if (s == 0 && time_downdate) SH_CK(m, cudaEventRecord(m->d1, sh.stream));
   }
   m->launches += 4 * m->G;
@@ -586,21 +595,21 @@ int enqueue_compass(ekf_sharded m, const double* const* zR) {
   for (int s = 0; s < m->G; ++s) {
     Shard& sh = m->sh[s];
     SH_CK(m, cudaSetDevice(sh.device));
-    shard_compass_setup<<<1, 32, 0, sh.stream>>>(sh.args, zR[s]);
+    ekf_launch_pdl(shard_compass_setup, 1, 32, 0, sh.stream, sh.args, zR[s]);
   }
   int rc = exchange(m);
   if (rc != EKF_OK) return rc;
   for (int s = 0; s < m->G; ++s) {
     Shard& sh = m->sh[s];
     SH_CK(m, cudaSetDevice(sh.device));
-    shard_compass_gain<<<rows_grid(sh, sh.c1 - sh.c0), kThreads, 0, sh.stream>>>(sh.args);
+    ekf_launch_pdl(shard_compass_gain, rows_grid(sh, sh.c1 - sh.c0), kThreads, 0, sh.stream, sh.args);
   }
   rc = exchange(m);
   if (rc != EKF_OK) return rc;
   for (int s = 0; s < m->G; ++s) {
     Shard& sh = m->sh[s];
     SH_CK(m, cudaSetDevice(sh.device));
-    shard_downdate<1, true><<<sh.grid, kThreads, 0, sh.stream>>>(sh.args);
+    ekf_launch_pdl(shard_downdate<1, true>, sh.grid, kThreads, 0, sh.stream, sh.args);
   }
   m->launches += 3 * m->G;
   return EKF_OK;
@@ -686,14 +695,14 @@ void run_shard_thread(RunCtx& c, int s) {
   for (int t = 0; t < c.T; ++t) {
     const double* hrec = c.hrec + (size_t)t * c.L;
     const double* rec = sh.records + (size_t)t * c.L;
-    shard_prop_setup<<<1, 32, 0, sh.stream>>>(sh.args, rec);
-    shard_prop_strip<<<g_strip, kThreads, 0, sh.stream>>>(sh.args);
+    ekf_launch_pdl(shard_prop_setup, 1, 32, 0, sh.stream, sh.args, rec);
+    ekf_launch_pdl(shard_prop_strip, g_strip, kThreads, 0, sh.stream, sh.args);
     if (hrec[6] != 0.0) {
-      shard_compass_setup<<<1, 32, 0, sh.stream>>>(sh.args, rec + 3);
+      ekf_launch_pdl(shard_compass_setup, 1, 32, 0, sh.stream, sh.args, rec + 3);
       xchg();
-      shard_compass_gain<<<g_rows, kThreads, 0, sh.stream>>>(sh.args);
+      ekf_launch_pdl(shard_compass_gain, g_rows, kThreads, 0, sh.stream, sh.args);
       xchg();
-      shard_downdate<1, true><<<sh.grid, kThreads, 0, sh.stream>>>(sh.args);
+      ekf_launch_pdl(shard_downdate<1, true>, sh.grid, kThreads, 0, sh.stream, sh.args);
     }
     int nz = (int)hrec[5];
     nz = nz < 0 ? 0 : nz > c.max_meas ? c.max_meas : nz;
@@ -701,15 +710,15 @@ void run_shard_thread(RunCtx& c, int s) {
       const double* zr = rec + 8 + 6 * q;
       const size_t oi = (size_t)t * c.M + q;
       const bool out = s == 0 && c.want_trace;
-      shard_gate<<<g_gate, kThreads, 0, sh.stream>>>(sh.args, zr, 0);
+      ekf_launch_pdl(shard_gate, g_gate, kThreads, 0, sh.stream, sh.args, zr, 0);
       xchg();
-      shard_decide<<<1, 32, 0, sh.stream>>>(sh.args, zr, out ? m->t_dec + oi : nullptr, out ? m->t_idx + oi : nullptr,
+      ekf_launch_pdl(shard_decide, 1, 32, 0, sh.stream, sh.args, zr, out ? m->t_dec + oi : nullptr, out ? m->t_idx + oi : nullptr,
                                           out ? m->t_mah + oi : nullptr);
-      shard_gain<<<g_rows, kThreads, 0, sh.stream>>>(sh.args);
+      ekf_launch_pdl(shard_gain, g_rows, kThreads, 0, sh.stream, sh.args);
       xchg();
       const bool time_this = s == 0 && !timed && t >= c.T / 2;   // one downdate sampled mid-run on shard 0
       if (time_this) TH_CK(cudaEventRecord(m->d0, sh.stream));
-      shard_downdate<2, false><<<sh.grid, kThreads, 0, sh.stream>>>(sh.args);
+      ekf_launch_pdl(shard_downdate<2, false>, sh.grid, kThreads, 0, sh.stream, sh.args);
       if (time_this) TH_CK(cudaEventRecord(m->d1, sh.stream));
       timed = timed || time_this;
     }
