@@ -8,13 +8,18 @@
 // stand-ins under oracle/shim are used because real Eigen / ARIA are not installed):
 //   g++ -std=c++11 -O2 -Ioracle/shim -I2d-ekf-slam_b200/host -Iinclude examples/slam_synthetic.cpp \
 //       -L2d-ekf-slam_b200/lib -lekf_slam_b200 -lekf_synth -o slam_synthetic
-// Usage: slam_synthetic [n_landmarks] [n_steps] [max_landmarks]  -> one line per step on stdout:
-//   "Update: <tokens><Num_Landmarks>" lines as slam.cpp:169-171 prints, then "odom X Y Phi".
+// Usage: slam_synthetic [n_landmarks] [n_steps] [max_landmarks] [log_dir]  -> one line per step on
+//   stdout: "Update: <tokens><Num_Landmarks>" lines as slam.cpp:169-171 prints, then "odom X Y Phi".
+//   With log_dir the reference's log files are written there in its own text formats
+//   (odomRun.txt slam.cpp:181, featuresRun.txt slam.cpp:172-177, covRun.txt and knownfeaturesRun.txt
+//   kalmanfilter.cpp:51-61), so plot.py / RealTimePlotting.m read a synthetic run unchanged;
+//   scanRun.txt needs laser readings and is not produced.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "ekf_synth.h"
@@ -35,7 +40,14 @@ int main(int argc, char** argv) {
   ekf_synth_generate(&cfg, 0, 1, 0, n_steps, rec.data(), nullptr, 1);
 
   ArRobot robot;
-  std::ofstream covFile, knownfeaturesFile;   // left closed, as in the parity harness
+  std::ofstream odomFile, featuresFile, covFile, knownfeaturesFile;   // closed unless log_dir is given
+  if (argc > 4) {
+    const std::string dir(argv[4]);
+    odomFile.open((dir + "/odomRun.txt").c_str());
+    featuresFile.open((dir + "/featuresRun.txt").c_str());
+    covFile.open((dir + "/covRun.txt").c_str());
+    knownfeaturesFile.open((dir + "/knownfeaturesRun.txt").c_str());
+  }
   std::cout.precision(17);
 
   // Initialize the kalman filter (slam.cpp:127)
@@ -61,7 +73,14 @@ int main(int argc, char** argv) {
       std::cout << "Update: ";
       ekf->doUpdate(z_chunk, R_chunk);
       std::cout << ekf->Num_Landmarks << std::endl;
+      if (featuresFile.is_open()) {                                  // slam.cpp:172-177
+        const double fx = zr[0], fy = zr[1];
+        const double newX = fx * cos(ekf->Phi) - fy * sin(ekf->Phi);
+        const double newY = fx * sin(ekf->Phi) + fy * cos(ekf->Phi);
+        featuresFile << newX + ekf->X << " " << newY + ekf->Y << std::endl;
+      }
     }
+    if (odomFile.is_open()) odomFile << ekf->X << " " << ekf->Y << std::endl;          // slam.cpp:181
     std::cout << "odom " << ekf->X << " " << ekf->Y << " " << ekf->Phi << std::endl;   // slam.cpp:181
   }
   delete ekf;

@@ -272,6 +272,50 @@ void ref_measurement_from_feature(double fx_mm, double fy_mm, double* z_out, dou
   for (int k = 0; k < 4; ++k) R_out[k] = R_chunk(k);
 }
 
+// The reference's log files for one filter driven by n_steps step records (layout below), written
+// with the reference's own statements where they live in the compiled TUs (covRun / knownfeaturesRun:
+// kalmanfilter.cpp:51-61, with OPEN streams this time) and with slam.cpp's expressions restated here
+// for the two files main() writes (featuresRun: slam.cpp:172-177, odomRun: slam.cpp:181). scanRun
+// needs laser readings and is not produced. Returns 0, or -1 if a file cannot be opened.
+int ref_run_logged(int n_steps, int max_meas, const double* inputs, const char* dir) {
+  const int L = 8 + 6 * max_meas;
+  const std::string d(dir);
+  std::ofstream odomFile((d + "/odomRun.txt").c_str()), featuresFile((d + "/featuresRun.txt").c_str());
+  std::ofstream covFile((d + "/covRun.txt").c_str()), knownfeaturesFile((d + "/knownfeaturesRun.txt").c_str());
+  if (!odomFile.is_open() || !featuresFile.is_open() || !covFile.is_open() || !knownfeaturesFile.is_open()) return -1;
+  install_cout_capture();    // "New / Old / Ignore" go nowhere (tls_tokens stays null)
+  ArRobot robot;
+  KalmanFilter* ekf = new KalmanFilter(&robot);
+  for (int t = 0; t < n_steps; ++t) {
+    const double* rec = inputs + static_cast<size_t>(t) * L;
+    robot.vel_mm_s = rec[0];
+    robot.rotvel_deg_s = rec[1];
+    ekf->doPropagation(rec[2], covFile, knownfeaturesFile);
+    if (rec[6] != 0.0) ekf->doUpdateCompass(rec[3], rec[4]);
+    const int nz = static_cast<int>(rec[5]);
+    for (int m = 0; m < nz && m < max_meas; ++m) {
+      const double* zr = rec + 8 + 6 * m;
+      Eigen::MatrixXd z_chunk(2, 1), R_chunk(2, 2);
+      z_chunk(0, 0) = zr[0];
+      z_chunk(1, 0) = zr[1];
+      R_chunk(0, 0) = zr[2];
+      R_chunk(1, 0) = zr[3];
+      R_chunk(0, 1) = zr[4];
+      R_chunk(1, 1) = zr[5];
+      ekf->doUpdate(z_chunk, R_chunk);
+      const double fx = zr[0], fy = zr[1];
+      const double newX = fx * cos(ekf->Phi) - fy * sin(ekf->Phi);
+      const double newY = fx * sin(ekf->Phi) + fy * cos(ekf->Phi);
+      featuresFile << newX + ekf->X << " " << newY + ekf->Y << std::endl;
+    }
+    odomFile << ekf->X << " " << ekf->Y << std::endl;
+  }
+  delete ekf->state;         // the reference has no destructor (kalmanfilter.h:21-43)
+  delete ekf->covariance;
+  delete ekf;
+  return 0;
+}
+
 // ---- batch runner (CPU baseline and bulk golden generation) ---------------------------------
 // Step record layout (doubles), identical to include/ekf_slam_b200.h:
 //   [0] vel_mm_s [1] rotvel_deg_s [2] dt [3] compass_z [4] compass_R [5] n_z [6] has_compass [7] 0

@@ -213,6 +213,15 @@ class Ref:
         self.lib.ref_measurement_from_feature(fx_mm, fy_mm, _dp(z), _dp(R))
         return z, R
 
+    def run_logged(self, records, max_meas, directory):
+        """The reference's odomRun / featuresRun / covRun / knownfeaturesRun text files for one filter."""
+        records = np.ascontiguousarray(records, np.float64)
+        T, L = records.shape
+        assert L == record_len(max_meas)
+        self.lib.ref_run_logged.argtypes = [C.c_int, C.c_int, c_dp, C.c_char_p]
+        rc = self.lib.ref_run_logged(T, max_meas, _dp(records), str(directory).encode())
+        assert rc == 0
+
     def call_update(self, x, P, z_chunk, R_chunk, gamma_max=50, gamma_min=10):
         """Pure-function call of the private KalmanFilter::Update (n_z >= 1). z_chunk 2 x n_z,
         R_chunk 2 x 2n_z (numpy, any layout). Returns (x', P')."""

@@ -42,3 +42,36 @@ def test_slam_loop_through_the_dropin_class(ekf, oracle, tmp_path):
         assert odom.shape == (T, 3)
         err = np.abs(odom - want["pose_trace"][0]).max() / np.abs(want["pose_trace"][0]).max()
         assert err <= 1e-9, err
+
+
+def test_log_files_match_the_reference_formats(ekf, ref, tmp_path):
+    """odomRun / featuresRun / covRun / knownfeaturesRun written through the
+    drop-in class are the reference's text, line for line (default ostream formatting, the
+    reference's own knownfeatures index stride), so plot.py / RealTimePlotting.m work unchanged."""
+    exe = str(tmp_path / "slam_synthetic")
+    lib = os.path.join(ROOT, "2d-ekf-slam_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "oracle", "shim"),
+                    "-I" + os.path.join(ROOT, "2d-ekf-slam_b200", "host"), "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "slam_synthetic.cpp"), "-L" + lib, "-lekf_slam_b200",
+                    "-lekf_synth", "-Wl,-rpath," + lib, "-o", exe], check=True)
+    N, T = 12, 240
+    ours, theirs = tmp_path / "ours", tmp_path / "ref"
+    ours.mkdir()
+    theirs.mkdir()
+    subprocess.run([exe, str(N), str(T), "16", str(ours)], stdout=subprocess.DEVNULL, check=True)
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=2, compass_every=10)
+    ref.run_logged(syn.generate(1, T)[0], 2, theirs)
+    for name, min_lines in (("odomRun.txt", T), ("featuresRun.txt", T), ("covRun.txt", T), ("knownfeaturesRun.txt", T)):
+        a = (ours / name).read_text().split("\n")
+        b = (theirs / name).read_text().split("\n")
+        assert len(a) == len(b) and len(b) > min_lines, name
+        diff = 0
+        for la, lb in zip(a, b):
+            if la == lb:
+                continue
+            fa, fb = la.split(), lb.split()
+            assert len(fa) == len(fb), name
+            for va, vb in zip(fa, fb):      # 6 significant digits: a 1e-12 difference may flip the last one
+                assert abs(float(va) - float(vb)) <= 2e-6 * max(abs(float(vb)), 1e-30), (name, la, lb)
+            diff += 1
+        assert diff <= len(b) // 100, "%s: %d of %d lines differ in the last printed digit" % (name, diff, len(b))
