@@ -15,4 +15,19 @@ class ArRobot {
   double getRotVel() const { return rotvel_deg_s; }
 };
 
+// The Hough front-end (features/houghtransform.cpp:240-250) reads three things of a laser return:
+// its range [mm] and its position in the robot frame [mm].
+class ArSensorReading {
+ public:
+  ArSensorReading() {}
+  ArSensorReading(double x_mm, double y_mm, unsigned int range_mm) : x_(x_mm), y_(y_mm), range_(range_mm) {}
+  unsigned int getRange() const { return range_; }
+  double getLocalX() const { return x_; }
+  double getLocalY() const { return y_; }
+
+ private:
+  double x_ = 0.0, y_ = 0.0;
+  unsigned int range_ = 0;
+};
+
 #endif  // EKF_SHIM_ARIA_H
