@@ -1,0 +1,531 @@
+// ekf_hough.cu — batched Hough line extraction for LMS-200 scans (sm_100a), the measurement
+// front-end of the reference (features/houghtransform.cpp), C ABI in include/ekf_hough_b200.h.
+//
+// One CTA per scan, the accumulator on chip. The reference's accumulator is 180 x 1601 bytes
+// (288 KB), more than an SM's shared memory, so a scan is processed in two halves of 90 angles
+// (144 KB each); nothing of the accumulator ever goes to HBM unless the caller asks for it.
+//   vote      houghtransform.cpp:240-256: one (reading, angle) pair per thread,
+//             radius = (int)round(x*cos + y*sin) / 10 + 800 in the reference's arithmetic
+//             (double products of the float tables, no fma), a byte-wide increment done as a
+//             32-bit shared-memory atomic on the containing word (counts stay below 256)
+//   compact   the non-zero cells of the half, in cell order, packed as (cell << 8 | count): two
+//             passes over a contiguous chunk per thread around a block-wide exclusive scan
+//   select    houghtransform.cpp:260-280 is a STREAMING top-200 selection whose result (which
+//             cells, and in which slots) depends on the visiting order; the grouping stage that
+//             follows is greedy in slot order, so the slots must come out exactly as the
+//             reference leaves them. Zero cells can never replace a slot, so the stream is the
+//             compacted list. One warp walks it 32 candidates at a time: a ballot finds the
+//             candidates above the current minimum, each is placed into the minimum slot and the
+//             new minimum slot is found with one REDUX over (count << 8 | slot) keys - the
+//             reference's rescan ("first slot holding a strictly smaller count, else stay").
+//             The 200 slots live in the registers of that warp (7 per lane).
+// While warp 0 runs the selection of half h, the other seven warps already zero the accumulator
+// and cast the votes of half h+1.
+// Peak grouping, merging and the conversion to (radius, theta, weight) lines
+// (houghtransform.cpp:58-236) is integer work on <= 200 items per scan and runs on the host.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ekf_hough_b200.h"
+#include "ekf_slam_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int TH = EKF_HOUGH_THETA_SIZE, RS = EKF_HOUGH_RADIUS_SIZE, ADD = RS / 2, PK = EKF_HOUGH_NUM_PEAKS;
+constexpr int PARTS = 2, TPP = TH / PARTS;                 // angles per half
+constexpr int ACC_BYTES = TPP * RS;                        // 144,090
+constexpr int ACC_WORDS = (ACC_BYTES + 3) / 4;
+constexpr int ACC_WORDS_PAD = (ACC_WORDS + 31) / 32 * 32;
+constexpr int MAXP = EKF_HOUGH_MAX_POINTS;
+constexpr int CAND_CAP = MAXP * TPP;                       // a half cannot hold more non-zero cells than votes
+constexpr int SLOTS_PER_LANE = (PK + 31) / 32;             // 7
+
+struct HoughSmem {
+  unsigned int acc[ACC_WORDS_PAD];
+  unsigned int cand[CAND_CAP];
+  double px[MAXP], py[MAXP];
+  float cs[TH], sn[TH];
+  unsigned char valid[(MAXP + 15) / 16 * 16];
+  int warp_sum[kThreads / 32];
+  int n_cand;
+  int grid0;
+};
+
+struct HoughArgs {
+  const double* x;
+  const double* y;
+  const unsigned int* range;
+  const float* cos_tab;
+  const float* sin_tab;
+  int n_scans, n_points;
+  int* peaks;            // [n_scans][PK]
+  int* values;           // [n_scans][PK]
+  unsigned char* grid;   // [n_scans][TH*RS] or null
+};
+
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void zero_acc(HoughSmem& sm, int t0, int nt) {
+  for (int w = t0; w < ACC_WORDS_PAD; w += nt) sm.acc[w] = 0u;
+}
+
+// houghtransform.cpp:240-256 for the angles of one half
+__device__ __forceinline__ void vote(HoughSmem& sm, int part, int n_points, int t0, int nt) {
+  const int total = n_points * TPP;
+  for (int q = t0; q < total; q += nt) {
+    const int p = q / TPP, tl = q - p * TPP;
+    if (!sm.valid[p]) continue;
+    const int t = part * TPP + tl;
+    const double rho = sm.px[p] * (double)sm.cs[t] + sm.py[p] * (double)sm.sn[t];
+    int r = (int)round(rho);
+    r /= EKF_HOUGH_DISTANCE;
+    r += ADD;
+    if ((unsigned)r < (unsigned)RS) {
+      const int b = tl * RS + r;
+      atomicAdd(&sm.acc[b >> 2], 1u << ((b & 3) * 8));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) hough_scan_kernel(const HoughArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HoughSmem& sm = *reinterpret_cast<HoughSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_points = a.n_points;
+  for (int i = tid; i < TH; i += kThreads) { sm.cs[i] = a.cos_tab[i]; sm.sn[i] = a.sin_tab[i]; }
+
+  for (int scan = blockIdx.x; scan < a.n_scans; scan += gridDim.x) {
+    const size_t pbase = (size_t)scan * n_points;
+    for (int i = tid; i < n_points; i += kThreads) {
+      sm.px[i] = a.x[pbase + i];
+      sm.py[i] = a.y[pbase + i];
+      sm.valid[i] = a.range[pbase + i] <= (unsigned int)EKF_HOUGH_MAX_DIST;   // houghtransform.cpp:245
+    }
+    zero_acc(sm, tid, kThreads);
+    __syncthreads();
+    vote(sm, 0, n_points, tid, kThreads);
+    __syncthreads();
+
+    // the 200 slots of houghtransform.cpp:46 (warp 0 only): slot s = k*32 + lane
+    int pv[SLOTS_PER_LANE], pi[SLOTS_PER_LANE];
+    int mindex = 0, minval = 0;
+
+    for (int part = 0; part < PARTS; ++part) {
+      // ---- compact the non-zero cells of this half, in cell order --------------------------------
+      constexpr int WPT = (ACC_WORDS + kThreads - 1) / kThreads;
+      const int w0 = tid * WPT, w1 = (w0 + WPT < ACC_WORDS) ? w0 + WPT : ACC_WORDS;
+      int cnt = 0;
+      for (int w = w0; w < w1; ++w) {
+        const unsigned int v = sm.acc[w];
+        cnt += ((v & 0xFFu) != 0) + ((v & 0xFF00u) != 0) + ((v & 0xFF0000u) != 0) + ((v & 0xFF000000u) != 0);
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) sm.warp_sum[warp] = incl;
+      if (part == 0 && tid == 0) sm.grid0 = (int)(sm.acc[0] & 0xFFu);
+      __syncthreads();
+      int off = incl - cnt;
+      for (int w = 0; w < warp; ++w) off += sm.warp_sum[w];
+      if (tid == kThreads - 1) sm.n_cand = off + cnt;
+      const unsigned int cell0 = (unsigned int)(part * ACC_BYTES);
+      for (int w = w0; w < w1; ++w) {
+        const unsigned int v = sm.acc[w];
+        if (v == 0u) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned int byte = (v >> (8 * k)) & 0xFFu;
+          if (byte) sm.cand[off++] = ((cell0 + 4u * w + k) << 8) | byte;
+        }
+      }
+      if (a.grid) {   // debug / parity: the accumulator itself
+        unsigned char* g = a.grid + (size_t)scan * TH * RS + (size_t)part * ACC_BYTES;
+        for (int w = w0; w < w1; ++w) {
+          const unsigned int v = sm.acc[w];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (4 * w + k < ACC_BYTES) g[4 * w + k] = (unsigned char)(v >> (8 * k));
+        }
+      }
+      __syncthreads();
+
+      if (warp == 0) {
+        // ---- houghtransform.cpp:260-280 over the compacted stream ----------------------------------
+        if (part == 0) {
+          const int g0 = sm.grid0;       // every slot starts at cell 0 (houghtransform.cpp:46)
+#pragma unroll
+          for (int k = 0; k < SLOTS_PER_LANE; ++k) { pv[k] = g0; pi[k] = 0; }
+          mindex = 0;
+          minval = g0;
+        }
+        const int n_cand = sm.n_cand;
+        for (int base = 0; base < n_cand; base += 32) {
+          const unsigned int c = base + lane < n_cand ? sm.cand[base + lane] : 0u;
+          const int v = (int)(c & 0xFFu), cell = (int)(c >> 8);
+          unsigned int pend = __ballot_sync(0xffffffffu, v > minval);
+          while (pend) {
+            const int src = __ffs(pend) - 1;
+            const int v_s = __shfl_sync(0xffffffffu, v, src);
+            const int cell_s = __shfl_sync(0xffffffffu, cell, src);
+            const int owner = mindex & 31, kk = mindex >> 5;
+            unsigned int lkey = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < SLOTS_PER_LANE; ++k) {
+              if (lane == owner && k == kk) { pv[k] = v_s; pi[k] = cell_s; }
+              const int slot = k * 32 + lane;
+              if (slot < PK) {
+                const unsigned int key = ((unsigned int)pv[k] << 8) | (unsigned int)slot;
+                lkey = key < lkey ? key : lkey;
+              }
+            }
+            const unsigned int gkey = __reduce_min_sync(0xffffffffu, lkey);
+            const int gmin = (int)(gkey >> 8);
+            if (gmin < v_s) { mindex = (int)(gkey & 0xFFu); minval = gmin; }   // first slot with a strictly smaller count
+            else minval = v_s;                                                 // none: the slot just written stays the minimum
+            pend = __ballot_sync(0xffffffffu, v > minval) & ~((2u << src) - 1u);
+          }
+        }
+      } else if (part + 1 < PARTS) {
+        // ---- meanwhile: next half's votes ------------------------------------------------------------
+        zero_acc(sm, tid - 32, kThreads - 32);
+        named_barrier(1, kThreads - 32);
+        vote(sm, part + 1, n_points, tid - 32, kThreads - 32);
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < SLOTS_PER_LANE; ++k) {
+        const int slot = k * 32 + lane;
+        if (slot < PK) {
+          a.peaks[(size_t)scan * PK + slot] = pi[k];
+          a.values[(size_t)scan * PK + slot] = pv[k];
+        }
+      }
+    }
+  }
+}
+
+// ---- host: houghtransform.cpp:58-236 -------------------------------------------------------------
+struct Group {
+  int hi_r, lo_r, hi_t, lo_t;
+  int sum_r, sum_t, weight, count;
+};
+
+inline bool close_to(int hi, int lo, int v, int tol) {
+  return std::abs(hi - v) < tol || std::abs(lo - v) < tol || (v < hi && v > lo);
+}
+
+int lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line* lines, int max_lines) {
+  Group g[PK];
+  int ng = 0;
+  for (int p = 0; p < PK; ++p) {                       // greedy clustering in slot order (:66-112)
+    const int r = peaks[p] % RS, t = peaks[p] / RS, w = values[p];
+    if (r <= 0) continue;
+    int j = 0;
+    for (; j < ng; ++j)
+      if (close_to(g[j].hi_t, g[j].lo_t, t, 30) && close_to(g[j].hi_r, g[j].lo_r, r, 5)) break;
+    if (j == ng) {
+      g[ng++] = Group{r, r, t, t, r * w, t * w, w, 1};
+    } else {
+      Group& q = g[j];
+      if (r > q.hi_r) q.hi_r = r;
+      if (r < q.lo_r) q.lo_r = r;
+      if (t > q.hi_t) q.hi_t = t;
+      if (t < q.lo_t) q.lo_t = t;
+      q.sum_r += r * w;
+      q.sum_t += t * w;
+      q.weight += w;
+      q.count += 1;
+    }
+  }
+  for (int i = 0; i < ng; ++i) {                       // negative radii -> the opposite normal (:118-129)
+    Group& q = g[i];
+    if (q.sum_r < ADD * q.weight) {
+      q.sum_r = 2 * ADD * q.weight - q.sum_r;
+      q.hi_r = 2 * ADD - q.hi_r;
+      q.lo_r = 2 * ADD - q.lo_r;
+      q.sum_t -= TH * q.weight;
+      q.hi_t -= TH;
+      q.lo_t -= TH;
+    }
+  }
+  int root_of[PK];                                     // :158-190 (the last matching earlier group wins)
+  for (int j = 0; j < ng; ++j) {
+    root_of[j] = -1;
+    for (int i = 0; i < j; ++i) {
+      const Group &u = g[i], &v = g[j];
+      const bool t_ok = std::abs(v.hi_t - u.lo_t) < 30 || std::abs(v.lo_t - u.hi_t) < 30 || (u.hi_t > v.lo_t && u.lo_t < v.hi_t);
+      const bool r_ok = std::abs(v.hi_r - u.lo_r) < 5 || std::abs(v.lo_r - u.hi_r) < 5 || (u.hi_r > v.lo_r && u.lo_r < v.hi_r);
+      if (t_ok && r_ok) root_of[j] = i;
+    }
+  }
+  for (int i = 0; i < ng; ++i) {                       // :194-211
+    if (root_of[i] < 0) continue;
+    int j = i;
+    while (root_of[j] >= 0) j = root_of[j];
+    Group& d = g[j];
+    const Group& s = g[i];
+    if (s.hi_r > d.hi_r) d.hi_r = s.hi_r;
+    if (s.lo_r < d.lo_r) d.lo_r = s.lo_r;
+    if (s.hi_t > d.hi_t) d.hi_t = s.hi_t;
+    if (s.lo_t < d.lo_t) d.lo_t = s.lo_t;
+    d.sum_r += s.sum_r;
+    d.sum_t += s.sum_t;
+    d.weight += s.weight;
+    d.count += s.count;
+  }
+  int n = 0;
+  for (int i = 0; i < ng; ++i) {                       // :215-233
+    if (root_of[i] >= 0) continue;
+    if (n < max_lines) {
+      ekf_hough_line& L = lines[n];
+      L.theta = g[i].sum_t / (double)g[i].weight;
+      L.theta *= 3.141592654 / TH;
+      L.radius = g[i].sum_r / (double)g[i].weight;
+      L.radius -= ADD;
+      L.radius *= EKF_HOUGH_DISTANCE;
+      L.weight = g[i].weight / (double)g[i].count;
+    }
+    ++n;
+  }
+  return n;
+}
+
+std::string g_hough_create_error;
+
+}  // namespace
+
+struct ekf_hough_s {
+  int device = 0, sm_count = 0, max_scans = 0;
+  cudaStream_t stream = nullptr;
+  double* d_x = nullptr;
+  double* d_y = nullptr;
+  unsigned int* d_range = nullptr;
+  float* d_cos = nullptr;
+  float* d_sin = nullptr;
+  int* d_peaks = nullptr;
+  int* d_values = nullptr;
+  unsigned char* d_grid = nullptr;
+  size_t grid_cap = 0;
+  int n_scans = 0, n_points = 0;
+  std::vector<int32_t> h_peaks, h_values;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float kernel_ms = 0.f;
+  int kernel_launches = 0;
+  bool pending_event = false;
+  std::string err;
+};
+
+namespace {
+
+int hfail(ekf_hough h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_hough_create_error = msg;
+  return code;
+}
+
+#define HG_CK(h, call)                                                                           \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return hfail(h, EKF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+
+int collect_kernel_time(ekf_hough h) {
+  if (h->pending_event) {
+    float ms = 0.f;
+    HG_CK(h, cudaEventSynchronize(h->ev1));
+    HG_CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->kernel_ms += ms;
+    h->kernel_launches += 1;
+    h->pending_event = false;
+  }
+  return EKF_OK;
+}
+
+int launch(ekf_hough h, bool want_grid) {
+  if (h->n_scans < 1) return hfail(h, EKF_ERR_BAD_ARG, "no scans uploaded");
+  int rc = collect_kernel_time(h);
+  if (rc != EKF_OK) return rc;
+  HoughArgs a;
+  a.x = h->d_x; a.y = h->d_y; a.range = h->d_range; a.cos_tab = h->d_cos; a.sin_tab = h->d_sin;
+  a.n_scans = h->n_scans; a.n_points = h->n_points;
+  a.peaks = h->d_peaks; a.values = h->d_values;
+  a.grid = nullptr;
+  if (want_grid) {
+    const size_t need = (size_t)h->n_scans * TH * RS;
+    if (need > h->grid_cap) {
+      cudaFree(h->d_grid);
+      h->d_grid = nullptr;
+      h->grid_cap = 0;
+      HG_CK(h, cudaMalloc(&h->d_grid, need));
+      h->grid_cap = need;
+    }
+    a.grid = h->d_grid;
+  }
+  const int grid = h->n_scans < h->sm_count ? h->n_scans : h->sm_count;   // one CTA per SM (214 KB of shared memory)
+  HG_CK(h, cudaEventRecord(h->ev0, h->stream));
+  hough_scan_kernel<<<grid, kThreads, sizeof(HoughSmem), h->stream>>>(a);
+  HG_CK(h, cudaGetLastError());
+  HG_CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->pending_event = true;
+  return EKF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ekf_hough_tables(float* cos_out, float* sin_out) {
+  // houghtransform.cpp:5-18: the angle accumulates in float; cos / sin are the double functions
+  const float step = (float)(3.141592654 / TH);
+  float theta = 0.0f;
+  for (int i = 0; i < TH; ++i) {
+    cos_out[i] = (float)std::cos((double)theta);
+    sin_out[i] = (float)std::sin((double)theta);
+    theta += step;
+  }
+}
+
+int ekf_hough_lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line* lines, int max_lines) {
+  if (!peaks || !values || (!lines && max_lines > 0)) return 0;
+  return lines_from_peaks(peaks, values, lines, max_lines);
+}
+
+int ekf_hough_create(ekf_hough* out, int device, int max_scans) {
+  if (!out) return hfail(nullptr, EKF_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  if (max_scans < 1) return hfail(nullptr, EKF_ERR_BAD_ARG, "max_scans must be >= 1");
+  int sms = 0, maj = 0, mnr = 0;
+  size_t smem_optin = 0;
+  if (ekf_device_info(device, &sms, &maj, &mnr, &smem_optin, nullptr) != EKF_OK)
+    return hfail(nullptr, EKF_ERR_NO_DEVICE, "no usable CUDA device " + std::to_string(device) + " (this library has no CPU fallback)");
+  if (maj != 10) return hfail(nullptr, EKF_ERR_NO_DEVICE, "device is sm_" + std::to_string(maj * 10 + mnr) + "; this library is built for sm_100a (B200) only");
+  if (smem_optin < sizeof(HoughSmem)) return hfail(nullptr, EKF_ERR_UNSUPPORTED, "not enough shared memory per block");
+  ekf_hough h = new ekf_hough_s();
+  h->device = device;
+  h->sm_count = sms;
+  h->max_scans = max_scans;
+  auto bail = [&](int code, const std::string& msg) {
+    g_hough_create_error = msg;
+    ekf_hough_destroy(h);
+    return code;
+  };
+  cudaError_t e;
+  if (cudaSetDevice(device) != cudaSuccess) return bail(EKF_ERR_CUDA, "cudaSetDevice failed");
+  if ((e = cudaFuncSetAttribute(hough_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HoughSmem))) != cudaSuccess)
+    return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  const size_t np = (size_t)max_scans * MAXP;
+  if ((e = cudaMalloc(&h->d_x, np * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&h->d_y, np * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&h->d_range, np * sizeof(unsigned int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&h->d_peaks, (size_t)max_scans * PK * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&h->d_values, (size_t)max_scans * PK * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&h->d_cos, TH * sizeof(float))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&h->d_sin, TH * sizeof(float))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  float c[TH], s[TH];
+  ekf_hough_tables(c, s);
+  cudaMemcpy(h->d_cos, c, sizeof(c), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_sin, s, sizeof(s), cudaMemcpyHostToDevice);
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  h->h_peaks.resize((size_t)max_scans * PK);
+  h->h_values.resize((size_t)max_scans * PK);
+  *out = h;
+  return EKF_OK;
+}
+
+int ekf_hough_destroy(ekf_hough h) {
+  if (!h) return EKF_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_range); cudaFree(h->d_peaks); cudaFree(h->d_values);
+  cudaFree(h->d_cos); cudaFree(h->d_sin); cudaFree(h->d_grid);
+  if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return EKF_OK;
+}
+
+int ekf_hough_upload(ekf_hough h, int n_scans, int n_points, const double* x, const double* y, const uint32_t* range) {
+  if (!h || !x || !y || !range || n_scans < 1 || n_scans > h->max_scans || n_points < 1 || n_points > MAXP)
+    return hfail(h, EKF_ERR_BAD_ARG, "ekf_hough_upload: 1 <= n_scans <= max_scans and 1 <= n_points <= " + std::to_string(MAXP) + " required");
+  cudaSetDevice(h->device);
+  const size_t np = (size_t)n_scans * n_points;
+  HG_CK(h, cudaMemcpyAsync(h->d_x, x, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  HG_CK(h, cudaMemcpyAsync(h->d_y, y, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  HG_CK(h, cudaMemcpyAsync(h->d_range, range, np * sizeof(unsigned int), cudaMemcpyHostToDevice, h->stream));
+  h->n_scans = n_scans;
+  h->n_points = n_points;
+  return EKF_OK;
+}
+
+int ekf_hough_run_resident(ekf_hough h) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return launch(h, false);
+}
+
+int ekf_hough_download(ekf_hough h, ekf_hough_line* lines, int max_lines, int32_t* n_lines, int32_t* peaks, int32_t* values) {
+  if (!h || max_lines < 0 || (max_lines > 0 && !lines)) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t cnt = (size_t)h->n_scans * PK;
+  HG_CK(h, cudaMemcpyAsync(h->h_peaks.data(), h->d_peaks, cnt * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  HG_CK(h, cudaMemcpyAsync(h->h_values.data(), h->d_values, cnt * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  HG_CK(h, cudaStreamSynchronize(h->stream));
+  if (peaks) std::memcpy(peaks, h->h_peaks.data(), cnt * sizeof(int));
+  if (values) std::memcpy(values, h->h_values.data(), cnt * sizeof(int));
+  for (int s = 0; s < h->n_scans; ++s) {
+    const int n = lines_from_peaks(h->h_peaks.data() + (size_t)s * PK, h->h_values.data() + (size_t)s * PK,
+                                   lines ? lines + (size_t)s * max_lines : nullptr, max_lines);
+    if (n_lines) n_lines[s] = n;
+  }
+  return EKF_OK;
+}
+
+int ekf_hough_get_lines(ekf_hough h, int n_scans, int n_points, const double* x, const double* y, const uint32_t* range,
+                        ekf_hough_line* lines, int max_lines, int32_t* n_lines, int32_t* peaks, int32_t* values,
+                        uint8_t* grid) {
+  int rc = ekf_hough_upload(h, n_scans, n_points, x, y, range);
+  if (rc != EKF_OK) return rc;
+  rc = launch(h, grid != nullptr);
+  if (rc != EKF_OK) return rc;
+  if (grid) HG_CK(h, cudaMemcpyAsync(grid, h->d_grid, (size_t)n_scans * TH * RS, cudaMemcpyDeviceToHost, h->stream));
+  return ekf_hough_download(h, lines, max_lines, n_lines, peaks, values);
+}
+
+int ekf_hough_kernel_time(ekf_hough h, float* total_ms, int* n_launches) {
+  if (!h || !total_ms || !n_launches) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  int rc = collect_kernel_time(h);
+  if (rc != EKF_OK) return rc;
+  *total_ms = h->kernel_ms;
+  *n_launches = h->kernel_launches;
+  h->kernel_ms = 0.f;
+  h->kernel_launches = 0;
+  return EKF_OK;
+}
+
+int ekf_hough_sync(ekf_hough h) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  HG_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
+const char* ekf_hough_last_error(ekf_hough h) { return h ? h->err.c_str() : g_hough_create_error.c_str(); }
+
+}  // extern "C"

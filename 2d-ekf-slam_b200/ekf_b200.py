@@ -124,6 +124,21 @@ def core_lib():
         L.ekf_measure_fp64_peak.argtypes = [C.c_int, c_dp]
         L.ekf_debug_phase_cycles.argtypes = [C.POINTER(C.c_longlong)]
         L.ekf_debug_stile_timestamps.argtypes = [C.POINTER(C.c_longlong)]
+        c_u32p = C.POINTER(C.c_uint32)
+        c_u8p = C.POINTER(C.c_uint8)
+        L.ekf_hough_create.argtypes = [C.POINTER(H), C.c_int, C.c_int]
+        L.ekf_hough_destroy.argtypes = [H]
+        L.ekf_hough_tables.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ekf_hough_tables.restype = None
+        L.ekf_hough_get_lines.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, c_u32p, c_dp, C.c_int, c_ip, c_ip, c_ip, c_u8p]
+        L.ekf_hough_upload.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, c_u32p]
+        L.ekf_hough_run_resident.argtypes = [H]
+        L.ekf_hough_download.argtypes = [H, c_dp, C.c_int, c_ip, c_ip, c_ip]
+        L.ekf_hough_kernel_time.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.ekf_hough_sync.argtypes = [H]
+        L.ekf_hough_lines_from_peaks.argtypes = [c_ip, c_ip, c_dp, C.c_int]
+        L.ekf_hough_last_error.argtypes = [H]
+        L.ekf_hough_last_error.restype = C.c_char_p
         L.ekf_sharded_create.argtypes = [C.POINTER(H), C.c_int, c_ip, C.c_int, C.POINTER(Config)]
         L.ekf_sharded_destroy.argtypes = [H]
         L.ekf_sharded_reset.argtypes = [H]
@@ -520,6 +535,102 @@ class ShardedMap:
 
     def kernel_launches(self):
         return int(self.L.ekf_sharded_kernel_launches(self.h))
+
+
+HOUGH_THETA, HOUGH_RADIUS, HOUGH_PEAKS = 180, 1601, 200
+
+
+def hough_tables():
+    """COS_ARRAY / SIN_ARRAY of the reference constructor (host only)."""
+    c = np.zeros(HOUGH_THETA, np.float32)
+    s = np.zeros(HOUGH_THETA, np.float32)
+    core_lib().ekf_hough_tables(c.ctypes.data_as(C.POINTER(C.c_float)), s.ctypes.data_as(C.POINTER(C.c_float)))
+    return c, s
+
+
+def hough_lines_from_peaks(peaks, values, max_lines=HOUGH_PEAKS):
+    peaks = np.ascontiguousarray(peaks, np.int32)
+    values = np.ascontiguousarray(values, np.int32)
+    lines = np.zeros((max_lines, 3))
+    n = core_lib().ekf_hough_lines_from_peaks(_ip(peaks), _ip(values), _dp(lines), max_lines)
+    return lines[:n].copy()
+
+
+class HoughBatch:
+    """HoughTransform::getLines for batches of laser scans (one ekf_hough handle)."""
+
+    def __init__(self, max_scans, device=0):
+        self.L = core_lib()
+        self.h = C.c_void_p()
+        rc = self.L.ekf_hough_create(C.byref(self.h), device, max_scans)
+        if rc:
+            msg = self.L.ekf_hough_last_error(None)
+            self.h = None
+            raise EkfError(rc, msg.decode() if msg else "")
+        self.max_scans = max_scans
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ekf_hough_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            msg = self.L.ekf_hough_last_error(self.h)
+            raise EkfError(rc, msg.decode() if msg else "")
+
+    @staticmethod
+    def _inputs(X, Y, R):
+        X = np.ascontiguousarray(X, np.float64)
+        Y = np.ascontiguousarray(Y, np.float64)
+        R = np.ascontiguousarray(R, np.uint32)
+        assert X.ndim == 2 and X.shape == Y.shape == R.shape
+        return X, Y, R
+
+    def get_lines(self, X, Y, R, max_lines=64, want_grid=False):
+        """X, Y, R [n_scans][n_points]. -> dict(lines=[per-scan (n,3) arrays], n_lines, peaks, values, grid)"""
+        X, Y, R = self._inputs(X, Y, R)
+        S, P = X.shape
+        lines = np.zeros((S, max_lines, 3))
+        n_lines = np.zeros(S, np.int32)
+        peaks = np.zeros((S, HOUGH_PEAKS), np.int32)
+        values = np.zeros((S, HOUGH_PEAKS), np.int32)
+        grid = np.zeros((S, HOUGH_THETA * HOUGH_RADIUS), np.uint8) if want_grid else None
+        self._chk(self.L.ekf_hough_get_lines(self.h, S, P, _dp(X), _dp(Y), R.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             _dp(lines), max_lines, _ip(n_lines), _ip(peaks), _ip(values),
+                                             grid.ctypes.data_as(C.POINTER(C.c_uint8)) if want_grid else None))
+        return {"lines": [lines[s, :min(n_lines[s], max_lines)].copy() for s in range(S)], "n_lines": n_lines,
+                "peaks": peaks, "values": values, "grid": grid}
+
+    def upload(self, X, Y, R):
+        X, Y, R = self._inputs(X, Y, R)
+        self._shape = X.shape
+        self._chk(self.L.ekf_hough_upload(self.h, X.shape[0], X.shape[1], _dp(X), _dp(Y),
+                                          R.ctypes.data_as(C.POINTER(C.c_uint32))))
+
+    def run_resident(self):
+        self._chk(self.L.ekf_hough_run_resident(self.h))
+
+    def download(self, max_lines=64):
+        S = self._shape[0]
+        lines = np.zeros((S, max_lines, 3))
+        n_lines = np.zeros(S, np.int32)
+        self._chk(self.L.ekf_hough_download(self.h, _dp(lines), max_lines, _ip(n_lines), None, None))
+        return lines, n_lines
+
+    def sync(self):
+        self._chk(self.L.ekf_hough_sync(self.h))
+
+    def kernel_time(self):
+        ms, n = C.c_float(), C.c_int()
+        self._chk(self.L.ekf_hough_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
 
 def device_count():

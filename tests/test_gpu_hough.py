@@ -1,0 +1,80 @@
+"""GPU parity tests of the batched Hough line extractor (`ekf_hough_*`) against
+the C restatement of HoughTransform::getLines (oracle/hough_oracle.c, itself pinned to the
+reference's translation unit by tests/test_hough_oracle.py). Everything is integer or
+integer-derived, so the bar is bit-exact: accumulator bytes, the order-dependent peak array, the
+counts at the peaks, and the doubles of the lines."""
+import numpy as np
+import pytest
+
+import scan_synth
+from hough_lib import HoughOracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ho(built):
+    return HoughOracle()
+
+
+def _check(ekf, ho, X, Y, R, want_grid):
+    hb = ekf.HoughBatch(len(X))
+    got = hb.get_lines(X, Y, R, max_lines=200, want_grid=want_grid)
+    hb.close()
+    for k in range(len(X)):
+        lines, peaks, grid = ho.get_lines(X[k], Y[k], R[k], want_grid=True)
+        if want_grid:
+            assert np.array_equal(got["grid"][k], grid), "accumulator, scan %d" % k
+        assert np.array_equal(got["peaks"][k], peaks), "peak array, scan %d" % k
+        assert np.array_equal(got["values"][k], grid[peaks].astype(np.int32)), "counts at the peaks, scan %d" % k
+        assert got["n_lines"][k] == len(lines), "line count, scan %d" % k
+        assert np.array_equal(got["lines"][k], lines), "lines, scan %d" % k
+    return got
+
+
+def test_scans_match_the_oracle_bit_for_bit(ekf, ho):
+    X, Y, R = scan_synth.make_scans(64, seed=11)
+    got = _check(ekf, ho, X, Y, R, want_grid=True)
+    assert got["n_lines"].min() >= 1 and got["n_lines"].max() >= 4
+
+
+def test_more_scans_than_sms(ekf, ho):
+    """A persistent grid: 400 scans over 148 CTAs; every scan must still come out exact."""
+    X, Y, R = scan_synth.make_scans(400, seed=5, n_boxes=5)
+    _check(ekf, ho, X, Y, R, want_grid=False)
+
+
+def test_edge_cases(ekf, ho):
+    ang = np.deg2rad(np.arange(181) - 90.0)
+    rows = []
+    r = np.full(181, 8191, np.uint32)
+    rows.append((r * np.cos(ang), r * np.sin(ang), r))                             # nothing in range
+    r = np.full(181, 8191, np.uint32); r[90] = 2500
+    rows.append((r * np.cos(ang), r * np.sin(ang), r))                             # one return
+    d = 3000.0 / np.maximum(np.cos(ang), 1e-3)
+    r = np.where(d < 8000, np.rint(d), 8191).astype(np.uint32)
+    rows.append((r * np.cos(ang), r * np.sin(ang), r))                             # one wall
+    r = np.full(181, 4000, np.uint32)
+    rows.append((np.full(181, 4000.0), np.zeros(181), r))                          # 181 votes in one cell
+    r = np.full(181, 8000, np.uint32)
+    rows.append((r * np.cos(ang), r * np.sin(ang), r))                             # exactly MAX_DIST
+    X = np.stack([a for a, _, _ in rows]); Y = np.stack([b for _, b, _ in rows]); R = np.stack([c for _, _, c in rows])
+    got = _check(ekf, ho, X, Y, R, want_grid=True)
+    assert got["n_lines"][0] == 0 and got["grid"][3].max() == 181
+    # fewer readings per scan than an LMS-200 delivers, and the largest accepted count
+    for P in (1, 37, 200):
+        Xs, Ys, Rs = scan_synth.make_scans(3, seed=P)
+        idx = np.arange(P) % 181
+        _check(ekf, ho, Xs[:, idx], Ys[:, idx], Rs[:, idx], want_grid=True)
+
+
+def test_argument_validation(ekf):
+    hb = ekf.HoughBatch(4)
+    X, Y, R = scan_synth.make_scans(5, seed=1)
+    with pytest.raises(ekf.EkfError) as e:
+        hb.get_lines(X, Y, R)                      # more scans than the handle was created for
+    assert e.value.code == ekf.ERR_BAD_ARG
+    idx = np.arange(201) % 181
+    with pytest.raises(ekf.EkfError):
+        hb.get_lines(X[:2, idx], Y[:2, idx], R[:2, idx])
+    hb.close()
