@@ -2,27 +2,31 @@
 // front-end of the reference (features/houghtransform.cpp), C ABI in include/ekf_hough_b200.h.
 //
 // One CTA per scan, the accumulator on chip. The reference's accumulator is 180 x 1601 bytes
-// (288 KB), more than an SM's shared memory, so a scan is processed in two halves of 90 angles
-// (144 KB each); nothing of the accumulator ever goes to HBM unless the caller asks for it.
+// (288 KB), more than an SM's shared memory, and the selection stage below is serial per scan, so
+// a scan is processed in PARTS slices of 180/PARTS angles, small enough that several CTAs (= several
+// serial selection streams) share an SM; nothing of the accumulator ever goes to HBM unless the
+// caller asks for it.
 //   vote      houghtransform.cpp:240-256: one (reading, angle) pair per thread,
 //             radius = (int)round(x*cos + y*sin) / 10 + 800 in the reference's arithmetic
 //             (double products of the float tables, no fma), a byte-wide increment done as a
 //             32-bit shared-memory atomic on the containing word (counts stay below 256)
-//   compact   the non-zero cells of the half, in cell order, packed as (cell << 8 | count): two
-//             passes over a contiguous chunk per thread around a block-wide exclusive scan
+//   compact   the cells of the slice that can still enter the peak array - count above the current
+//             minimum slot, which never decreases, so everything else (all zero cells included) is
+//             dropped exactly - in cell order, packed as (cell << 8 | count): two passes over a
+//             contiguous chunk per thread around a block-wide exclusive scan
 //   select    houghtransform.cpp:260-280 is a STREAMING top-200 selection whose result (which
 //             cells, and in which slots) depends on the visiting order; the grouping stage that
 //             follows is greedy in slot order, so the slots must come out exactly as the
-//             reference leaves them. Zero cells can never replace a slot, so the stream is the
-//             compacted list. One warp walks it 32 candidates at a time: a ballot finds the
+//             reference leaves them. One warp walks the compacted list 32 candidates at a time: a ballot finds the
 //             candidates above the current minimum, each is placed into the minimum slot and the
 //             new minimum slot is found with one REDUX over (count << 8 | slot) keys - the
 //             reference's rescan ("first slot holding a strictly smaller count, else stay").
 //             The 200 slots live in the registers of that warp (7 per lane).
-// While warp 0 runs the selection of half h, the other seven warps already zero the accumulator
-// and cast the votes of half h+1.
+// While warp 0 runs the selection of slice s, the other warps already zero the accumulator and cast
+// the votes of slice s+1.
 // Peak grouping, merging and the conversion to (radius, theta, weight) lines
-// (houghtransform.cpp:58-236) is integer work on <= 200 items per scan and runs on the host.
+// (houghtransform.cpp:58-236) is sequential integer work on <= 200 items per scan: a second kernel
+// runs it with one thread per scan (the same function is exported for host use).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -36,10 +40,17 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef EKF_HOUGH_PARTS
+#define EKF_HOUGH_PARTS 12
+#endif
+#ifndef EKF_HOUGH_THREADS
+#define EKF_HOUGH_THREADS 128
+#endif
+constexpr int kThreads = EKF_HOUGH_THREADS;
 constexpr int TH = EKF_HOUGH_THETA_SIZE, RS = EKF_HOUGH_RADIUS_SIZE, ADD = RS / 2, PK = EKF_HOUGH_NUM_PEAKS;
-constexpr int PARTS = 2, TPP = TH / PARTS;                 // angles per half
-constexpr int ACC_BYTES = TPP * RS;                        // 144,090
+constexpr int PARTS = EKF_HOUGH_PARTS, TPP = TH / PARTS;   // angles per slice
+static_assert(TH % PARTS == 0, "slices of equal size");
+constexpr int ACC_BYTES = TPP * RS;
 constexpr int ACC_WORDS = (ACC_BYTES + 3) / 4;
 constexpr int ACC_WORDS_PAD = (ACC_WORDS + 31) / 32 * 32;
 constexpr int MAXP = EKF_HOUGH_MAX_POINTS;
@@ -55,6 +66,7 @@ struct HoughSmem {
   int warp_sum[kThreads / 32];
   int n_cand;
   int grid0;
+  int minval;   // count in the current minimum slot after the last selection pass
 };
 
 struct HoughArgs {
@@ -95,7 +107,7 @@ __device__ __forceinline__ void vote(HoughSmem& sm, int part, int n_points, int 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) hough_scan_kernel(const HoughArgs a) {
+__global__ void __launch_bounds__(kThreads) hough_scan_kernel(const HoughArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HoughSmem& sm = *reinterpret_cast<HoughSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,10 +134,12 @@ __global__ void __launch_bounds__(kThreads, 1) hough_scan_kernel(const HoughArgs
       // ---- compact the non-zero cells of this half, in cell order --------------------------------
       constexpr int WPT = (ACC_WORDS + kThreads - 1) / kThreads;
       const int w0 = tid * WPT, w1 = (w0 + WPT < ACC_WORDS) ? w0 + WPT : ACC_WORDS;
+      // a cell can only ever enter the peak array if its count exceeds the current minimum slot
+      const unsigned int thr = part == 0 ? (sm.acc[0] & 0xFFu) : (unsigned int)sm.minval;
       int cnt = 0;
       for (int w = w0; w < w1; ++w) {
         const unsigned int v = sm.acc[w];
-        cnt += ((v & 0xFFu) != 0) + ((v & 0xFF00u) != 0) + ((v & 0xFF0000u) != 0) + ((v & 0xFF000000u) != 0);
+        cnt += ((v & 0xFFu) > thr) + (((v >> 8) & 0xFFu) > thr) + (((v >> 16) & 0xFFu) > thr) + ((v >> 24) > thr);
       }
       int incl = cnt;
 #pragma unroll
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) hough_scan_kernel(const HoughArgs
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const unsigned int byte = (v >> (8 * k)) & 0xFFu;
-          if (byte) sm.cand[off++] = ((cell0 + 4u * w + k) << 8) | byte;
+          if (byte > thr) sm.cand[off++] = ((cell0 + 4u * w + k) << 8) | byte;
         }
       }
       if (a.grid) {   // debug / parity: the accumulator itself
@@ -196,6 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) hough_scan_kernel(const HoughArgs
             pend = __ballot_sync(0xffffffffu, v > minval) & ~((2u << src) - 1u);
           }
         }
+        if (lane == 0) sm.minval = minval;
       } else if (part + 1 < PARTS) {
         // ---- meanwhile: next half's votes ------------------------------------------------------------
         zero_acc(sm, tid - 32, kThreads - 32);
@@ -217,17 +232,18 @@ __global__ void __launch_bounds__(kThreads, 1) hough_scan_kernel(const HoughArgs
   }
 }
 
-// ---- host: houghtransform.cpp:58-236 -------------------------------------------------------------
+// ---- houghtransform.cpp:58-236, one scan (host and device) ---------------------------------------
 struct Group {
   int hi_r, lo_r, hi_t, lo_t;
   int sum_r, sum_t, weight, count;
 };
 
-inline bool close_to(int hi, int lo, int v, int tol) {
-  return std::abs(hi - v) < tol || std::abs(lo - v) < tol || (v < hi && v > lo);
+__host__ __device__ inline int iabs(int v) { return v < 0 ? -v : v; }
+__host__ __device__ inline bool close_to(int hi, int lo, int v, int tol) {
+  return iabs(hi - v) < tol || iabs(lo - v) < tol || (v < hi && v > lo);
 }
 
-int lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line* lines, int max_lines) {
+__host__ __device__ int lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line* lines, int max_lines) {
   Group g[PK];
   int ng = 0;
   for (int p = 0; p < PK; ++p) {                       // greedy clustering in slot order (:66-112)
@@ -237,7 +253,13 @@ int lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line
     for (; j < ng; ++j)
       if (close_to(g[j].hi_t, g[j].lo_t, t, 30) && close_to(g[j].hi_r, g[j].lo_r, r, 5)) break;
     if (j == ng) {
-      g[ng++] = Group{r, r, t, t, r * w, t * w, w, 1};
+      Group& q = g[ng++];
+      q.hi_r = q.lo_r = r;
+      q.hi_t = q.lo_t = t;
+      q.sum_r = r * w;
+      q.sum_t = t * w;
+      q.weight = w;
+      q.count = 1;
     } else {
       Group& q = g[j];
       if (r > q.hi_r) q.hi_r = r;
@@ -266,8 +288,8 @@ int lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line
     root_of[j] = -1;
     for (int i = 0; i < j; ++i) {
       const Group &u = g[i], &v = g[j];
-      const bool t_ok = std::abs(v.hi_t - u.lo_t) < 30 || std::abs(v.lo_t - u.hi_t) < 30 || (u.hi_t > v.lo_t && u.lo_t < v.hi_t);
-      const bool r_ok = std::abs(v.hi_r - u.lo_r) < 5 || std::abs(v.lo_r - u.hi_r) < 5 || (u.hi_r > v.lo_r && u.lo_r < v.hi_r);
+      const bool t_ok = iabs(v.hi_t - u.lo_t) < 30 || iabs(v.lo_t - u.hi_t) < 30 || (u.hi_t > v.lo_t && u.lo_t < v.hi_t);
+      const bool r_ok = iabs(v.hi_r - u.lo_r) < 5 || iabs(v.lo_r - u.hi_r) < 5 || (u.hi_r > v.lo_r && u.lo_r < v.hi_r);
       if (t_ok && r_ok) root_of[j] = i;
     }
   }
@@ -303,12 +325,20 @@ int lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line
   return n;
 }
 
+__global__ void __launch_bounds__(64) hough_lines_kernel(const int* __restrict__ peaks, const int* __restrict__ values,
+                                                         ekf_hough_line* __restrict__ lines, int* __restrict__ n_lines,
+                                                         int max_lines, int n_scans) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  n_lines[s] = lines_from_peaks(peaks + (size_t)s * PK, values + (size_t)s * PK, lines + (size_t)s * max_lines, max_lines);
+}
+
 std::string g_hough_create_error;
 
 }  // namespace
 
 struct ekf_hough_s {
-  int device = 0, sm_count = 0, max_scans = 0;
+  int device = 0, sm_count = 0, max_scans = 0, ctas_per_sm = 1;
   cudaStream_t stream = nullptr;
   double* d_x = nullptr;
   double* d_y = nullptr;
@@ -319,8 +349,11 @@ struct ekf_hough_s {
   int* d_values = nullptr;
   unsigned char* d_grid = nullptr;
   size_t grid_cap = 0;
+  ekf_hough_line* d_lines = nullptr;
+  int* d_nlines = nullptr;
+  int lines_cap = 0;          // lines per scan the device buffer holds
+  int run_max_lines = 0;      // of the last run
   int n_scans = 0, n_points = 0;
-  std::vector<int32_t> h_peaks, h_values;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float kernel_ms = 0.f;
   int kernel_launches = 0;
@@ -355,8 +388,18 @@ int collect_kernel_time(ekf_hough h) {
   return EKF_OK;
 }
 
-int launch(ekf_hough h, bool want_grid) {
+int launch(ekf_hough h, bool want_grid, int max_lines) {
   if (h->n_scans < 1) return hfail(h, EKF_ERR_BAD_ARG, "no scans uploaded");
+  if (max_lines < 1) max_lines = 1;
+  if (max_lines > PK) max_lines = PK;
+  if (max_lines > h->lines_cap) {
+    cudaFree(h->d_lines);
+    h->d_lines = nullptr;
+    h->lines_cap = 0;
+    HG_CK(h, cudaMalloc(&h->d_lines, (size_t)h->max_scans * max_lines * sizeof(ekf_hough_line)));
+    h->lines_cap = max_lines;
+  }
+  h->run_max_lines = max_lines;
   int rc = collect_kernel_time(h);
   if (rc != EKF_OK) return rc;
   HoughArgs a;
@@ -375,9 +418,12 @@ int launch(ekf_hough h, bool want_grid) {
     }
     a.grid = h->d_grid;
   }
-  const int grid = h->n_scans < h->sm_count ? h->n_scans : h->sm_count;   // one CTA per SM (214 KB of shared memory)
+  const int cap = h->ctas_per_sm * h->sm_count;                            // persistent grid: all CTAs co-resident
+  const int grid = h->n_scans < cap ? h->n_scans : cap;
   HG_CK(h, cudaEventRecord(h->ev0, h->stream));
   hough_scan_kernel<<<grid, kThreads, sizeof(HoughSmem), h->stream>>>(a);
+  hough_lines_kernel<<<(h->n_scans + 63) / 64, 64, 0, h->stream>>>(h->d_peaks, h->d_values, h->d_lines, h->d_nlines, max_lines,
+                                                                h->n_scans);
   HG_CK(h, cudaGetLastError());
   HG_CK(h, cudaEventRecord(h->ev1, h->stream));
   h->pending_event = true;
@@ -427,6 +473,10 @@ int ekf_hough_create(ekf_hough* out, int device, int max_scans) {
   if (cudaSetDevice(device) != cudaSuccess) return bail(EKF_ERR_CUDA, "cudaSetDevice failed");
   if ((e = cudaFuncSetAttribute(hough_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HoughSmem))) != cudaSuccess)
     return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  cudaFuncSetAttribute(hough_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm, hough_scan_kernel, kThreads, sizeof(HoughSmem))) != cudaSuccess)
+    return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if (h->ctas_per_sm < 1) h->ctas_per_sm = 1;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
   const size_t np = (size_t)max_scans * MAXP;
   if ((e = cudaMalloc(&h->d_x, np * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
@@ -434,6 +484,7 @@ int ekf_hough_create(ekf_hough* out, int device, int max_scans) {
   if ((e = cudaMalloc(&h->d_range, np * sizeof(unsigned int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMalloc(&h->d_peaks, (size_t)max_scans * PK * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMalloc(&h->d_values, (size_t)max_scans * PK * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&h->d_nlines, (size_t)max_scans * sizeof(int))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMalloc(&h->d_cos, TH * sizeof(float))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMalloc(&h->d_sin, TH * sizeof(float))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
   float c[TH], s[TH];
@@ -442,8 +493,6 @@ int ekf_hough_create(ekf_hough* out, int device, int max_scans) {
   cudaMemcpy(h->d_sin, s, sizeof(s), cudaMemcpyHostToDevice);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
-  h->h_peaks.resize((size_t)max_scans * PK);
-  h->h_values.resize((size_t)max_scans * PK);
   *out = h;
   return EKF_OK;
 }
@@ -453,7 +502,7 @@ int ekf_hough_destroy(ekf_hough h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_range); cudaFree(h->d_peaks); cudaFree(h->d_values);
-  cudaFree(h->d_cos); cudaFree(h->d_sin); cudaFree(h->d_grid);
+  cudaFree(h->d_cos); cudaFree(h->d_sin); cudaFree(h->d_grid); cudaFree(h->d_lines); cudaFree(h->d_nlines);
   if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -473,26 +522,25 @@ int ekf_hough_upload(ekf_hough h, int n_scans, int n_points, const double* x, co
   return EKF_OK;
 }
 
-int ekf_hough_run_resident(ekf_hough h) {
+int ekf_hough_run_resident(ekf_hough h, int max_lines) {
   if (!h) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
-  return launch(h, false);
+  return launch(h, false, max_lines);
 }
 
 int ekf_hough_download(ekf_hough h, ekf_hough_line* lines, int max_lines, int32_t* n_lines, int32_t* peaks, int32_t* values) {
   if (!h || max_lines < 0 || (max_lines > 0 && !lines)) return EKF_ERR_BAD_ARG;
+  if (h->run_max_lines < 1) return hfail(h, EKF_ERR_BAD_ARG, "ekf_hough_download: nothing has been run");
   cudaSetDevice(h->device);
-  const size_t cnt = (size_t)h->n_scans * PK;
-  HG_CK(h, cudaMemcpyAsync(h->h_peaks.data(), h->d_peaks, cnt * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  HG_CK(h, cudaMemcpyAsync(h->h_values.data(), h->d_values, cnt * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  const size_t S = (size_t)h->n_scans, cnt = S * PK;
+  const int dev_lines = h->run_max_lines, take = max_lines < dev_lines ? max_lines : dev_lines;
+  if (lines && take > 0)
+    HG_CK(h, cudaMemcpy2DAsync(lines, (size_t)max_lines * sizeof(ekf_hough_line), h->d_lines, (size_t)dev_lines * sizeof(ekf_hough_line),
+                               (size_t)take * sizeof(ekf_hough_line), S, cudaMemcpyDeviceToHost, h->stream));
+  if (n_lines) HG_CK(h, cudaMemcpyAsync(n_lines, h->d_nlines, S * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (peaks) HG_CK(h, cudaMemcpyAsync(peaks, h->d_peaks, cnt * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (values) HG_CK(h, cudaMemcpyAsync(values, h->d_values, cnt * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   HG_CK(h, cudaStreamSynchronize(h->stream));
-  if (peaks) std::memcpy(peaks, h->h_peaks.data(), cnt * sizeof(int));
-  if (values) std::memcpy(values, h->h_values.data(), cnt * sizeof(int));
-  for (int s = 0; s < h->n_scans; ++s) {
-    const int n = lines_from_peaks(h->h_peaks.data() + (size_t)s * PK, h->h_values.data() + (size_t)s * PK,
-                                   lines ? lines + (size_t)s * max_lines : nullptr, max_lines);
-    if (n_lines) n_lines[s] = n;
-  }
   return EKF_OK;
 }
 
@@ -501,7 +549,7 @@ int ekf_hough_get_lines(ekf_hough h, int n_scans, int n_points, const double* x,
                         uint8_t* grid) {
   int rc = ekf_hough_upload(h, n_scans, n_points, x, y, range);
   if (rc != EKF_OK) return rc;
-  rc = launch(h, grid != nullptr);
+  rc = launch(h, grid != nullptr, max_lines);
   if (rc != EKF_OK) return rc;
   if (grid) HG_CK(h, cudaMemcpyAsync(grid, h->d_grid, (size_t)n_scans * TH * RS, cudaMemcpyDeviceToHost, h->stream));
   return ekf_hough_download(h, lines, max_lines, n_lines, peaks, values);

@@ -132,7 +132,7 @@ def core_lib():
         L.ekf_hough_tables.restype = None
         L.ekf_hough_get_lines.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, c_u32p, c_dp, C.c_int, c_ip, c_ip, c_ip, c_u8p]
         L.ekf_hough_upload.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, c_u32p]
-        L.ekf_hough_run_resident.argtypes = [H]
+        L.ekf_hough_run_resident.argtypes = [H, C.c_int]
         L.ekf_hough_download.argtypes = [H, c_dp, C.c_int, c_ip, c_ip, c_ip]
         L.ekf_hough_kernel_time.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.ekf_hough_sync.argtypes = [H]
@@ -593,20 +593,21 @@ class HoughBatch:
         assert X.ndim == 2 and X.shape == Y.shape == R.shape
         return X, Y, R
 
-    def get_lines(self, X, Y, R, max_lines=64, want_grid=False):
-        """X, Y, R [n_scans][n_points]. -> dict(lines=[per-scan (n,3) arrays], n_lines, peaks, values, grid)"""
+    def get_lines(self, X, Y, R, max_lines=64, want_grid=False, want_peaks=True, split=True):
+        """X, Y, R [n_scans][n_points]. -> dict(lines, n_lines, peaks, values, grid); lines is a list of
+        per-scan (n, 3) arrays, or the raw [n_scans][max_lines][3] buffer when split=False."""
         X, Y, R = self._inputs(X, Y, R)
         S, P = X.shape
-        lines = np.zeros((S, max_lines, 3))
-        n_lines = np.zeros(S, np.int32)
-        peaks = np.zeros((S, HOUGH_PEAKS), np.int32)
-        values = np.zeros((S, HOUGH_PEAKS), np.int32)
+        lines = np.empty((S, max_lines, 3))
+        n_lines = np.empty(S, np.int32)
+        peaks = np.zeros((S, HOUGH_PEAKS), np.int32) if want_peaks else None
+        values = np.zeros((S, HOUGH_PEAKS), np.int32) if want_peaks else None
         grid = np.zeros((S, HOUGH_THETA * HOUGH_RADIUS), np.uint8) if want_grid else None
         self._chk(self.L.ekf_hough_get_lines(self.h, S, P, _dp(X), _dp(Y), R.ctypes.data_as(C.POINTER(C.c_uint32)),
                                              _dp(lines), max_lines, _ip(n_lines), _ip(peaks), _ip(values),
                                              grid.ctypes.data_as(C.POINTER(C.c_uint8)) if want_grid else None))
-        return {"lines": [lines[s, :min(n_lines[s], max_lines)].copy() for s in range(S)], "n_lines": n_lines,
-                "peaks": peaks, "values": values, "grid": grid}
+        return {"lines": [lines[s, :min(n_lines[s], max_lines)].copy() for s in range(S)] if split else lines,
+                "n_lines": n_lines, "peaks": peaks, "values": values, "grid": grid}
 
     def upload(self, X, Y, R):
         X, Y, R = self._inputs(X, Y, R)
@@ -614,8 +615,8 @@ class HoughBatch:
         self._chk(self.L.ekf_hough_upload(self.h, X.shape[0], X.shape[1], _dp(X), _dp(Y),
                                           R.ctypes.data_as(C.POINTER(C.c_uint32))))
 
-    def run_resident(self):
-        self._chk(self.L.ekf_hough_run_resident(self.h))
+    def run_resident(self, max_lines=64):
+        self._chk(self.L.ekf_hough_run_resident(self.h, max_lines))
 
     def download(self, max_lines=64):
         S = self._shape[0]

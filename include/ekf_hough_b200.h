@@ -6,9 +6,9 @@
  *         (features/houghtransform.h:32, features/houghtransform.cpp:40-236; called from
  *          FeatureDetector::getFeatures, features/featuredetector.cpp:39-41)
  *
- * for a BATCH of laser scans: accumulate (houghtransform.cpp:240-256), the streaming 200-peak
- * selection (:260-280, order-dependent and reproduced exactly) on the GPU, and the integer peak
- * grouping / merging / line conversion (:58-236) on the host. Results are bit-identical to the
+ * for a BATCH of laser scans, all on the GPU: accumulate (houghtransform.cpp:240-256), the
+ * streaming 200-peak selection (:260-280, order-dependent and reproduced exactly), and the integer
+ * peak grouping / merging / line conversion (:58-236). Results are bit-identical to the
  * reference's: same accumulator bytes, same peak array, same doubles in the lines.
  * Implemented in the same shared library as ekf_slam_b200.h; sm_100a only, no CPU fallback. */
 #ifndef EKF_HOUGH_B200_H
@@ -58,19 +58,19 @@ int ekf_hough_get_lines(ekf_hough h, int n_scans, int n_points, const double* x,
                         const uint32_t* range, ekf_hough_line* lines, int max_lines, int32_t* n_lines,
                         int32_t* peaks, int32_t* values, uint8_t* grid);
 
-/* The same in three steps, for timing with the inputs resident in HBM: upload, run (kernel only,
- * asynchronous), download (synchronises, then groups the peaks into lines on the host). */
+/* The same in three steps, for timing with the inputs resident in HBM: upload, run (kernels only,
+ * asynchronous; at most max_lines lines per scan are kept), download (synchronises). */
 int ekf_hough_upload(ekf_hough h, int n_scans, int n_points, const double* x, const double* y,
                      const uint32_t* range);
-int ekf_hough_run_resident(ekf_hough h);
+int ekf_hough_run_resident(ekf_hough h, int max_lines);
 int ekf_hough_download(ekf_hough h, ekf_hough_line* lines, int max_lines, int32_t* n_lines, int32_t* peaks,
                        int32_t* values);
 /* Device time of the kernel launches since the last call (CUDA events on the handle's stream). */
 int ekf_hough_kernel_time(ekf_hough h, float* total_ms, int* n_launches);
 int ekf_hough_sync(ekf_hough h);
 
-/* Host only: peaks + values -> lines (houghtransform.cpp:58-236), what ekf_hough_download applies
- * per scan. Returns the number of lines. */
+/* Host only: peaks + values -> lines (houghtransform.cpp:58-236), the function the second kernel
+ * runs per scan. Returns the number of lines. */
 int ekf_hough_lines_from_peaks(const int32_t* peaks, const int32_t* values, ekf_hough_line* lines, int max_lines);
 
 const char* ekf_hough_last_error(ekf_hough h);
