@@ -131,15 +131,22 @@ __global__ void __launch_bounds__(kThreads) hough_scan_kernel(const HoughArgs a)
     int mindex = 0, minval = 0;
 
     for (int part = 0; part < PARTS; ++part) {
-      // ---- compact the non-zero cells of this half, in cell order --------------------------------
-      constexpr int WPT = (ACC_WORDS + kThreads - 1) / kThreads;
-      const int w0 = tid * WPT, w1 = (w0 + WPT < ACC_WORDS) ? w0 + WPT : ACC_WORDS;
+      // ---- compact the cells of this slice that can still enter the peak array, in cell order -----
+      // Each thread owns a contiguous run of 16-byte groups; most groups are all zero and cost one
+      // 128-bit load and a test. Counts are compared four at a time (per-byte SIMD compare).
+      constexpr int GROUPS = ACC_WORDS_PAD / 4;
+      constexpr int GPT = (GROUPS + kThreads - 1) / kThreads;
+      const int g0 = tid * GPT, g1 = (g0 + GPT < GROUPS) ? g0 + GPT : GROUPS;
       // a cell can only ever enter the peak array if its count exceeds the current minimum slot
       const unsigned int thr = part == 0 ? (sm.acc[0] & 0xFFu) : (unsigned int)sm.minval;
+      const unsigned int thr4 = thr * 0x01010101u;
+      const uint4* acc4 = reinterpret_cast<const uint4*>(sm.acc);
       int cnt = 0;
-      for (int w = w0; w < w1; ++w) {
-        const unsigned int v = sm.acc[w];
-        cnt += ((v & 0xFFu) > thr) + (((v >> 8) & 0xFFu) > thr) + (((v >> 16) & 0xFFu) > thr) + ((v >> 24) > thr);
+      for (int g = g0; g < g1; ++g) {
+        const uint4 v = acc4[g];
+        if ((v.x | v.y | v.z | v.w) == 0u) continue;
+        cnt += (__popc(__vcmpgtu4(v.x, thr4)) + __popc(__vcmpgtu4(v.y, thr4)) + __popc(__vcmpgtu4(v.z, thr4)) +
+                __popc(__vcmpgtu4(v.w, thr4))) >> 3;
       }
       int incl = cnt;
 #pragma unroll
@@ -154,15 +161,26 @@ __global__ void __launch_bounds__(kThreads) hough_scan_kernel(const HoughArgs a)
       for (int w = 0; w < warp; ++w) off += sm.warp_sum[w];
       if (tid == kThreads - 1) sm.n_cand = off + cnt;
       const unsigned int cell0 = (unsigned int)(part * ACC_BYTES);
-      for (int w = w0; w < w1; ++w) {
-        const unsigned int v = sm.acc[w];
-        if (v == 0u) continue;
+      if (cnt) {
+        for (int g = g0; g < g1; ++g) {
+          const uint4 v = acc4[g];
+          if ((v.x | v.y | v.z | v.w) == 0u) continue;
+          const unsigned int vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned int byte = (v >> (8 * k)) & 0xFFu;
-          if (byte > thr) sm.cand[off++] = ((cell0 + 4u * w + k) << 8) | byte;
+          for (int j = 0; j < 4; ++j) {
+            unsigned int m = __vcmpgtu4(vv[j], thr4) & 0x01010101u;   // bit 8k set: byte k passes
+            while (m) {
+              const int k = (__ffs(m) - 1) >> 3;
+              m &= m - 1u;
+              sm.cand[off++] = ((cell0 + 16u * g + 4u * j + k) << 8) | ((vv[j] >> (8 * k)) & 0xFFu);
+            }
+          }
         }
       }
+      // the per-word bounds the debug dump below uses
+      constexpr int WPT = GPT * 4;
+      const int w0 = g0 * 4, w1 = (g1 * 4 < ACC_WORDS) ? g1 * 4 : ACC_WORDS;
+      (void)WPT;
       if (a.grid) {   // debug / parity: the accumulator itself
         unsigned char* g = a.grid + (size_t)scan * TH * RS + (size_t)part * ACC_BYTES;
         for (int w = w0; w < w1; ++w) {
@@ -177,11 +195,11 @@ __global__ void __launch_bounds__(kThreads) hough_scan_kernel(const HoughArgs a)
       if (warp == 0) {
         // ---- houghtransform.cpp:260-280 over the compacted stream ----------------------------------
         if (part == 0) {
-          const int g0 = sm.grid0;       // every slot starts at cell 0 (houghtransform.cpp:46)
+          const int first = sm.grid0;    // every slot starts at cell 0 (houghtransform.cpp:46)
 #pragma unroll
-          for (int k = 0; k < SLOTS_PER_LANE; ++k) { pv[k] = g0; pi[k] = 0; }
+          for (int k = 0; k < SLOTS_PER_LANE; ++k) { pv[k] = first; pi[k] = 0; }
           mindex = 0;
-          minval = g0;
+          minval = first;
         }
         const int n_cand = sm.n_cand;
         for (int base = 0; base < n_cand; base += 32) {
