@@ -24,6 +24,14 @@ def test_core_exports_every_declared_symbol(ekf):
         assert hasattr(lib, n), "libekf_slam_b200.so does not export " + n
 
 
+def test_core_exports_the_hough_front_end(ekf):
+    lib = ekf.core_lib()
+    names = declared("ekf_hough_b200.h")
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), "libekf_slam_b200.so does not export " + n
+
+
 def test_synth_exports_every_declared_symbol(ekf):
     lib = ekf.synth_lib()
     for n in declared("ekf_synth.h"):
@@ -56,6 +64,12 @@ def test_no_gpu_means_loud_failure(ekf):
         ekf.FilterBatch(2, 10)
     assert ei.value.code == ekf.ERR_NO_DEVICE
     assert "no CPU fallback" in str(ei.value)
+    with pytest.raises(ekf.EkfError) as ei:
+        ekf.HoughBatch(4)
+    assert ei.value.code == ekf.ERR_NO_DEVICE
+    with pytest.raises(ekf.EkfError) as ei:
+        ekf.ShardedMap([0, 0], 10)
+    assert ei.value.code == ekf.ERR_NO_DEVICE
 
 
 def test_product_never_touches_the_oracle():
