@@ -25,8 +25,8 @@
 // While warp 0 runs the selection of slice s, the other warps already zero the accumulator and cast
 // the votes of slice s+1.
 // Peak grouping, merging and the conversion to (radius, theta, weight) lines
-// (houghtransform.cpp:58-236) is sequential integer work on <= 200 items per scan: a second kernel
-// runs it with one thread per scan (the same function is exported for host use).
+// (houghtransform.cpp:58-236) is integer work on <= 200 items per scan: a second kernel runs it
+// with one warp per scan (a sequential version of the same logic is exported for host use).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -343,12 +343,126 @@ __host__ __device__ int lines_from_peaks(const int32_t* peaks, const int32_t* va
   return n;
 }
 
-__global__ void __launch_bounds__(64) hough_lines_kernel(const int* __restrict__ peaks, const int* __restrict__ values,
-                                                         ekf_hough_line* __restrict__ lines, int* __restrict__ n_lines,
-                                                         int max_lines, int n_scans) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// houghtransform.cpp:58-236 with one WARP per scan: the peaks are visited in slot order (the
+// clustering is greedy, so that loop stays sequential), but every peak is tested against all
+// existing groups at once (one group per lane, a ballot picks the first match, which is where the
+// reference's inner loop breaks), and the group-against-group pass and the line conversion run one
+// group per lane. Same integer arithmetic as lines_from_peaks above, which stays the host version.
+constexpr int kLinesWarps = 4;
+struct LinesSmem {
+  int hi_r[PK], lo_r[PK], hi_t[PK], lo_t[PK], sum_r[PK], sum_t[PK], weight[PK], count[PK];
+  int root_of[PK];
+  int pr[PK], pt[PK], pw[PK];
+};
+
+__global__ void __launch_bounds__(kLinesWarps * 32) hough_lines_kernel(const int* __restrict__ peaks, const int* __restrict__ values,
+                                                                      ekf_hough_line* __restrict__ lines, int* __restrict__ n_lines,
+                                                                      int max_lines, int n_scans) {
+  __shared__ LinesSmem smem[kLinesWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int s = blockIdx.x * kLinesWarps + wib;
   if (s >= n_scans) return;
-  n_lines[s] = lines_from_peaks(peaks + (size_t)s * PK, values + (size_t)s * PK, lines + (size_t)s * max_lines, max_lines);
+  LinesSmem& g = smem[wib];
+  for (int p = lane; p < PK; p += 32) {
+    const int cell = peaks[(size_t)s * PK + p];
+    g.pr[p] = cell % RS;
+    g.pt[p] = cell / RS;
+    g.pw[p] = values[(size_t)s * PK + p];
+  }
+  __syncwarp();
+  int ng = 0;
+  for (int p = 0; p < PK; ++p) {                       // :66-112
+    const int r = g.pr[p], t = g.pt[p], w = g.pw[p];
+    if (r <= 0) continue;
+    int found = -1;
+    for (int base = 0; base < ng && found < 0; base += 32) {
+      const int j = base + lane;
+      bool m = false;
+      if (j < ng) m = close_to(g.hi_t[j], g.lo_t[j], t, 30) && close_to(g.hi_r[j], g.lo_r[j], r, 5);
+      const unsigned int hit = __ballot_sync(0xffffffffu, m);
+      if (hit) found = base + __ffs(hit) - 1;
+    }
+    if (lane == 0) {
+      if (found < 0) {
+        g.hi_r[ng] = g.lo_r[ng] = r;
+        g.hi_t[ng] = g.lo_t[ng] = t;
+        g.sum_r[ng] = r * w;
+        g.sum_t[ng] = t * w;
+        g.weight[ng] = w;
+        g.count[ng] = 1;
+      } else {
+        if (r > g.hi_r[found]) g.hi_r[found] = r;
+        if (r < g.lo_r[found]) g.lo_r[found] = r;
+        if (t > g.hi_t[found]) g.hi_t[found] = t;
+        if (t < g.lo_t[found]) g.lo_t[found] = t;
+        g.sum_r[found] += r * w;
+        g.sum_t[found] += t * w;
+        g.weight[found] += w;
+        g.count[found] += 1;
+      }
+    }
+    if (found < 0) ++ng;
+    __syncwarp();
+  }
+  for (int i = lane; i < ng; i += 32) {                // :118-129
+    if (g.sum_r[i] < ADD * g.weight[i]) {
+      g.sum_r[i] = 2 * ADD * g.weight[i] - g.sum_r[i];
+      g.hi_r[i] = 2 * ADD - g.hi_r[i];
+      g.lo_r[i] = 2 * ADD - g.lo_r[i];
+      g.sum_t[i] -= TH * g.weight[i];
+      g.hi_t[i] -= TH;
+      g.lo_t[i] -= TH;
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < ng; j += 32) {                // :158-190, the last matching earlier group wins
+    int root = -1;
+    const int vhi_t = g.hi_t[j], vlo_t = g.lo_t[j], vhi_r = g.hi_r[j], vlo_r = g.lo_r[j];
+    for (int i = 0; i < j; ++i) {
+      const int uhi_t = g.hi_t[i], ulo_t = g.lo_t[i], uhi_r = g.hi_r[i], ulo_r = g.lo_r[i];
+      const bool t_ok = iabs(vhi_t - ulo_t) < 30 || iabs(vlo_t - uhi_t) < 30 || (uhi_t > vlo_t && ulo_t < vhi_t);
+      const bool r_ok = iabs(vhi_r - ulo_r) < 5 || iabs(vlo_r - uhi_r) < 5 || (uhi_r > vlo_r && ulo_r < vhi_r);
+      if (t_ok && r_ok) root = i;
+    }
+    g.root_of[j] = root;
+  }
+  __syncwarp();
+  if (lane == 0) {                                     // :194-211
+    for (int i = 0; i < ng; ++i) {
+      if (g.root_of[i] < 0) continue;
+      int j = i;
+      while (g.root_of[j] >= 0) j = g.root_of[j];
+      if (g.hi_r[i] > g.hi_r[j]) g.hi_r[j] = g.hi_r[i];
+      if (g.lo_r[i] < g.lo_r[j]) g.lo_r[j] = g.lo_r[i];
+      if (g.hi_t[i] > g.hi_t[j]) g.hi_t[j] = g.hi_t[i];
+      if (g.lo_t[i] < g.lo_t[j]) g.lo_t[j] = g.lo_t[i];
+      g.sum_r[j] += g.sum_r[i];
+      g.sum_t[j] += g.sum_t[i];
+      g.weight[j] += g.weight[i];
+      g.count[j] += g.count[i];
+    }
+  }
+  __syncwarp();
+  int n = 0;
+  ekf_hough_line* out = lines + (size_t)s * max_lines;
+  for (int base = 0; base < ng; base += 32) {          // :215-233, roots in group order
+    const int i = base + lane;
+    const bool is_root = i < ng && g.root_of[i] < 0;
+    const unsigned int roots = __ballot_sync(0xffffffffu, is_root);
+    const int pos = n + __popc(roots & ((1u << lane) - 1u));
+    if (is_root && pos < max_lines) {
+      ekf_hough_line L;
+      L.theta = g.sum_t[i] / (double)g.weight[i];
+      L.theta *= 3.141592654 / TH;
+      L.radius = g.sum_r[i] / (double)g.weight[i];
+      L.radius -= ADD;
+      L.radius *= EKF_HOUGH_DISTANCE;
+      L.weight = g.weight[i] / (double)g.count[i];
+      out[pos] = L;
+    }
+    n += __popc(roots);
+  }
+  if (lane == 0) n_lines[s] = n;
 }
 
 std::string g_hough_create_error;
@@ -440,8 +554,8 @@ int launch(ekf_hough h, bool want_grid, int max_lines) {
   const int grid = h->n_scans < cap ? h->n_scans : cap;
   HG_CK(h, cudaEventRecord(h->ev0, h->stream));
   hough_scan_kernel<<<grid, kThreads, sizeof(HoughSmem), h->stream>>>(a);
-  hough_lines_kernel<<<(h->n_scans + 63) / 64, 64, 0, h->stream>>>(h->d_peaks, h->d_values, h->d_lines, h->d_nlines, max_lines,
-                                                                h->n_scans);
+  hough_lines_kernel<<<(h->n_scans + kLinesWarps - 1) / kLinesWarps, kLinesWarps * 32, 0, h->stream>>>(
+      h->d_peaks, h->d_values, h->d_lines, h->d_nlines, max_lines, h->n_scans);
   HG_CK(h, cudaGetLastError());
   HG_CK(h, cudaEventRecord(h->ev1, h->stream));
   h->pending_event = true;
