@@ -466,12 +466,15 @@ __global__ void __launch_bounds__(kLinesWarps * 32) hough_lines_kernel(const int
 }
 
 std::string g_hough_create_error;
+constexpr int kHoughChunks = 16;
 
 }  // namespace
 
 struct ekf_hough_s {
   int device = 0, sm_count = 0, max_scans = 0, ctas_per_sm = 1;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the pipelined end-to-end path
+  cudaEvent_t ev_in[kHoughChunks], ev_k[kHoughChunks], ev_done = nullptr;
   double* d_x = nullptr;
   double* d_y = nullptr;
   unsigned int* d_range = nullptr;
@@ -625,6 +628,13 @@ int ekf_hough_create(ekf_hough* out, int device, int max_scans) {
   cudaMemcpy(h->d_sin, s, sizeof(s), cudaMemcpyHostToDevice);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+  for (int i = 0; i < kHoughChunks; ++i) {
+    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
+  }
   *out = h;
   return EKF_OK;
 }
@@ -636,6 +646,12 @@ int ekf_hough_destroy(ekf_hough h) {
   cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_range); cudaFree(h->d_peaks); cudaFree(h->d_values);
   cudaFree(h->d_cos); cudaFree(h->d_sin); cudaFree(h->d_grid); cudaFree(h->d_lines); cudaFree(h->d_nlines);
   if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
+  if (h->ev_done) {
+    cudaEventDestroy(h->ev_done);
+    for (int i = 0; i < kHoughChunks; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+    cudaStreamDestroy(h->s_in);
+    cudaStreamDestroy(h->s_out);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return EKF_OK;
@@ -676,9 +692,75 @@ int ekf_hough_download(ekf_hough h, ekf_hough_line* lines, int max_lines, int32_
   return EKF_OK;
 }
 
+// End-to-end path without the accumulator dump: chunks of scans go through copy-in, the two
+// kernels and copy-out on three streams, so the transfers of neighbouring chunks overlap the
+// kernels (scans are independent; a chunk is a multiple of the co-resident CTA count). With
+// pageable host buffers the copies serialise in the driver; ekf_host_alloc() gives pinned ones.
+static int get_lines_pipelined(ekf_hough h, int n_scans, int n_points, const double* x, const double* y,
+                               const uint32_t* range, ekf_hough_line* lines, int max_lines, int32_t* n_lines,
+                               int32_t* peaks, int32_t* values) {
+  if (!x || !y || !range || n_scans < 1 || n_scans > h->max_scans || n_points < 1 || n_points > MAXP)
+    return hfail(h, EKF_ERR_BAD_ARG, "ekf_hough_get_lines: 1 <= n_scans <= max_scans and 1 <= n_points <= " + std::to_string(MAXP) + " required");
+  if (max_lines < 0 || (max_lines > 0 && !lines)) return EKF_ERR_BAD_ARG;
+  int dev_lines = max_lines < 1 ? 1 : (max_lines > PK ? PK : max_lines);
+  if (dev_lines > h->lines_cap) {
+    cudaFree(h->d_lines);
+    h->d_lines = nullptr;
+    h->lines_cap = 0;
+    HG_CK(h, cudaMalloc(&h->d_lines, (size_t)h->max_scans * dev_lines * sizeof(ekf_hough_line)));
+    h->lines_cap = dev_lines;
+  }
+  h->run_max_lines = dev_lines;
+  h->n_scans = n_scans;
+  h->n_points = n_points;
+  const int wave = h->ctas_per_sm * h->sm_count;
+  int chunk = 2 * wave;
+  while ((n_scans + chunk - 1) / chunk > kHoughChunks) chunk += wave;
+  const int n_chunks = (n_scans + chunk - 1) / chunk;
+  const int take = max_lines < dev_lines ? max_lines : dev_lines;
+  HG_CK(h, cudaEventRecord(h->ev_done, h->stream));
+  HG_CK(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
+  HG_CK(h, cudaStreamWaitEvent(h->s_out, h->ev_done, 0));
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t s0 = (size_t)c * chunk;
+    const int ns = (int)((s0 + chunk <= (size_t)n_scans) ? chunk : n_scans - s0);
+    const size_t p0 = s0 * n_points, np = (size_t)ns * n_points;
+    HG_CK(h, cudaMemcpyAsync(h->d_x + p0, x + p0, np * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    HG_CK(h, cudaMemcpyAsync(h->d_y + p0, y + p0, np * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    HG_CK(h, cudaMemcpyAsync(h->d_range + p0, range + p0, np * sizeof(unsigned int), cudaMemcpyHostToDevice, h->s_in));
+    HG_CK(h, cudaEventRecord(h->ev_in[c], h->s_in));
+    HG_CK(h, cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+    HoughArgs a;
+    a.x = h->d_x + p0; a.y = h->d_y + p0; a.range = h->d_range + p0; a.cos_tab = h->d_cos; a.sin_tab = h->d_sin;
+    a.n_scans = ns; a.n_points = n_points;
+    a.peaks = h->d_peaks + s0 * PK; a.values = h->d_values + s0 * PK;
+    a.grid = nullptr;
+    const int grid = ns < wave ? ns : wave;
+    hough_scan_kernel<<<grid, kThreads, sizeof(HoughSmem), h->stream>>>(a);
+    hough_lines_kernel<<<(ns + kLinesWarps - 1) / kLinesWarps, kLinesWarps * 32, 0, h->stream>>>(
+        a.peaks, a.values, h->d_lines + s0 * dev_lines, h->d_nlines + s0, dev_lines, ns);
+    HG_CK(h, cudaGetLastError());
+    HG_CK(h, cudaEventRecord(h->ev_k[c], h->stream));
+    HG_CK(h, cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+    if (lines && take > 0)
+      HG_CK(h, cudaMemcpy2DAsync(lines + s0 * max_lines, (size_t)max_lines * sizeof(ekf_hough_line), h->d_lines + s0 * dev_lines,
+                                 (size_t)dev_lines * sizeof(ekf_hough_line), (size_t)take * sizeof(ekf_hough_line), ns,
+                                 cudaMemcpyDeviceToHost, h->s_out));
+    if (n_lines) HG_CK(h, cudaMemcpyAsync(n_lines + s0, h->d_nlines + s0, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
+    if (peaks) HG_CK(h, cudaMemcpyAsync(peaks + s0 * PK, h->d_peaks + s0 * PK, (size_t)ns * PK * sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
+    if (values) HG_CK(h, cudaMemcpyAsync(values + s0 * PK, h->d_values + s0 * PK, (size_t)ns * PK * sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
+  }
+  HG_CK(h, cudaStreamSynchronize(h->s_out));
+  HG_CK(h, cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
 int ekf_hough_get_lines(ekf_hough h, int n_scans, int n_points, const double* x, const double* y, const uint32_t* range,
                         ekf_hough_line* lines, int max_lines, int32_t* n_lines, int32_t* peaks, int32_t* values,
                         uint8_t* grid) {
+  if (!h) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (!grid) return get_lines_pipelined(h, n_scans, n_points, x, y, range, lines, max_lines, n_lines, peaks, values);
   int rc = ekf_hough_upload(h, n_scans, n_points, x, y, range);
   if (rc != EKF_OK) return rc;
   rc = launch(h, grid != nullptr, max_lines);

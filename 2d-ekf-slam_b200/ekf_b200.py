@@ -593,13 +593,14 @@ class HoughBatch:
         assert X.ndim == 2 and X.shape == Y.shape == R.shape
         return X, Y, R
 
-    def get_lines(self, X, Y, R, max_lines=64, want_grid=False, want_peaks=True, split=True):
+    def get_lines(self, X, Y, R, max_lines=64, want_grid=False, want_peaks=True, split=True, out=None):
         """X, Y, R [n_scans][n_points]. -> dict(lines, n_lines, peaks, values, grid); lines is a list of
-        per-scan (n, 3) arrays, or the raw [n_scans][max_lines][3] buffer when split=False."""
+        per-scan (n, 3) arrays, or the raw [n_scans][max_lines][3] buffer when split=False.
+        out = (lines, n_lines) reuses caller buffers (e.g. pinned ones from PinnedArray)."""
         X, Y, R = self._inputs(X, Y, R)
         S, P = X.shape
-        lines = np.empty((S, max_lines, 3))
-        n_lines = np.empty(S, np.int32)
+        lines = out[0] if out is not None else np.empty((S, max_lines, 3))
+        n_lines = out[1] if out is not None else np.empty(S, np.int32)
         peaks = np.zeros((S, HOUGH_PEAKS), np.int32) if want_peaks else None
         values = np.zeros((S, HOUGH_PEAKS), np.int32) if want_peaks else None
         grid = np.zeros((S, HOUGH_THETA * HOUGH_RADIUS), np.uint8) if want_grid else None

@@ -310,11 +310,24 @@ def hough_leg(ekf, n_scans, hbm_peak, device, with_cpu=True):
     hb.sync()
     ms, n = hb.kernel_time()
     lines, n_lines = hb.download()
+    # end to end: pinned host buffers in, lines out (chunked H2D / kernels / D2H pipeline inside the call)
+    pin = [ekf.PinnedArray(X.shape, np.float64), ekf.PinnedArray(Y.shape, np.float64), ekf.PinnedArray(R.shape, np.uint32),
+           ekf.PinnedArray((n_scans, 32, 3), np.float64), ekf.PinnedArray((n_scans,), np.int32)]
+    pin[0].array[:] = X
+    pin[1].array[:] = Y
+    pin[2].array[:] = R
+    hb.get_lines(pin[0].array, pin[1].array, pin[2].array, max_lines=32, want_peaks=False, split=False,
+                 out=(pin[3].array, pin[4].array))
     t0 = time.perf_counter()
-    for _ in range(3):
-        got = hb.get_lines(X, Y, R, max_lines=32, want_peaks=False, split=False)   # host buffers in, lines out
-    e2e_s = (time.perf_counter() - t0) / 3
+    for _ in range(5):
+        got = hb.get_lines(pin[0].array, pin[1].array, pin[2].array, max_lines=32, want_peaks=False, split=False,
+                           out=(pin[3].array, pin[4].array))
+    e2e_s = (time.perf_counter() - t0) / 5
+    assert np.array_equal(pin[4].array, n_lines)
+    got = {"lines": pin[3].array.copy(), "n_lines": pin[4].array.copy()}
     hb.close()
+    for pa in pin:
+        pa.free()
     points = X.shape[1]
     alg = n_scans * (points * 20 + 2 * 2 * 200 * 4 + float(n_lines.mean()) * 24 + 4)   # readings in; peak slots + counts out and in again; lines out
     res = {"workload": "%d scans x %d readings (synthetic LMS-200, 180 x 1601 accumulator, 200 peaks)" % (n_scans, points),

@@ -44,6 +44,26 @@ def test_more_scans_than_sms(ekf, ho):
     _check(ekf, ho, X, Y, R, want_grid=False)
 
 
+def test_pipelined_chunks_and_resident_path_agree(ekf, ho):
+    """More scans than two waves of CTAs: ekf_hough_get_lines splits them into chunks over three
+    streams; upload / run_resident / download is one launch. Both must equal the oracle."""
+    base = scan_synth.make_scans(96, seed=9)
+    reps = 20                                            # 1,920 scans: two chunks on a 148-SM part
+    X, Y, R = (np.ascontiguousarray(np.tile(a, (reps, 1))) for a in base)
+    hb = ekf.HoughBatch(len(X))
+    got = hb.get_lines(X, Y, R, max_lines=40)
+    hb.upload(X, Y, R)
+    hb.run_resident(40)
+    lines2, n2 = hb.download(40)
+    hb.close()
+    want = [ho.get_lines(base[0][k], base[1][k], base[2][k]) for k in range(96)]
+    for s in range(len(X)):
+        lines, peaks, _ = want[s % 96]
+        assert np.array_equal(got["peaks"][s], peaks), "scan %d" % s
+        assert got["n_lines"][s] == len(lines) == n2[s]
+        assert np.array_equal(got["lines"][s], lines[:40]) and np.array_equal(lines2[s, :len(lines[:40])], lines[:40])
+
+
 def test_edge_cases(ekf, ho):
     ang = np.deg2rad(np.arange(181) - 90.0)
     rows = []
