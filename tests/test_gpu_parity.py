@@ -331,3 +331,38 @@ def test_propagate_only_run(ekf, oracle, kernel):
     x, P = fb.get_state(1)
     assert len(x) == 3 and np.array_equal(P, P.T) and np.linalg.eigvalsh(P).min() > 0
     fb.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["smem", "tile", "stile"])
+def test_randomised_configuration_sweep(ekf, oracle, kernel):
+    """Random map sizes / capacities / measurements per step / compass rates / lap lengths through each
+    fused kernel (every tile-count template gets hit), state compared at the end of two laps."""
+    rng = np.random.default_rng(1234 + kernel)
+    limit = 62 if kernel != 1 else 80
+    done = 0
+    for trial in range(16):
+        N = int(rng.integers(1, 55))
+        M = int(rng.integers(1, 4))
+        T = int(rng.integers(40, 260))
+        compass = int(rng.choice([0, 3, 7, 20]))
+        F = int(rng.integers(1, 5))
+        syn = ekf.Synth(N, steps_per_lap=T, max_meas=M, compass_every=compass)
+        lap = syn.generate(F, T)
+        rec = np.ascontiguousarray(np.concatenate([lap, lap], axis=1))
+        want = oracle.run_batch(rec, M, 90, pose_trace=True, final_state=True)
+        assert not want["bad"]
+        need = int(want["final_nlm"].max())       # spurious New associations included (a property of the world)
+        if need > limit:
+            continue
+        cap = int(min(limit, need + rng.integers(0, 4)))
+        fb = ekf.FilterBatch(F, cap, batch_kernel=kernel)
+        got = fb.run(rec, M, trace=True, pose_trace=True)
+        done += 1
+        what = "N=%d cap=%d M=%d T=%d compass=%d F=%d" % (N, cap, M, T, compass, F)
+        assert_trace_equal(got, want, what)
+        assert np.array_equal(got["final_nlm"], want["final_nlm"]), what
+        assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL, what
+        for f, ((x, P), (xr, Pr)) in enumerate(zip(_final_states(fb, F), _oracle_states(want, F))):
+            assert_state_close(x, P, xr, Pr, what + " filter %d" % f)
+        fb.close()
+    assert done >= 8
