@@ -38,6 +38,22 @@ def test_scans_match_the_oracle_bit_for_bit(ekf, ho):
     assert got["n_lines"].min() >= 1 and got["n_lines"].max() >= 4
 
 
+def test_cuda_matches_the_golden_vectors(ekf):
+    """tests/golden/hough/*.npz were produced by the reference's own houghtransform.cpp."""
+    from test_hough_golden import GOLDEN, golden_grid
+    assert GOLDEN
+    for path in GOLDEN:
+        g = np.load(path)
+        hb = ekf.HoughBatch(len(g["x"]))
+        got = hb.get_lines(g["x"], g["y"], g["range"], max_lines=200, want_grid=True)
+        hb.close()
+        for k in range(len(g["x"])):
+            n = int(g["n_lines"][k])
+            assert np.array_equal(got["grid"][k], golden_grid(g, k)), "accumulator, scan %d" % k
+            assert np.array_equal(got["peaks"][k], g["peaks"][k]), "peak array, scan %d" % k
+            assert got["n_lines"][k] == n and np.array_equal(got["lines"][k], g["lines"][k][:n]), "lines, scan %d" % k
+
+
 def test_more_scans_than_sms(ekf, ho):
     """A persistent grid: 400 scans over 148 CTAs; every scan must still come out exact."""
     X, Y, R = scan_synth.make_scans(400, seed=5, n_boxes=5)
