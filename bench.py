@@ -32,6 +32,7 @@ N_LM = 50
 CAP_LM = 50          # landmark capacity per filter: 182 shared-memory tiles, 4 CTAs (filters) per SM
 T_LAP = 1000
 MAX_MEAS = 1
+COMPASS_EVERY = 0
 
 
 def load_product():
@@ -174,7 +175,7 @@ def run_reference_arm(args):
         return
     ekf = load_product()
     cores = os.cpu_count() or 1
-    syn = ekf.Synth(N_LM, steps_per_lap=T_LAP, max_meas=MAX_MEAS)
+    syn = ekf.Synth(N_LM, steps_per_lap=T_LAP, max_meas=MAX_MEAS, compass_every=COMPASS_EVERY)
     n_f = max(cores, 2 * cores)
     lap = syn.generate(n_f, T_LAP)
     from oracle_lib import Oracle, Ref
@@ -370,11 +371,14 @@ def main():
     ap.add_argument("--shard-devices", default="", help="comma list of device ordinals for --sharded-map (default: all visible)")
     ap.add_argument("--hough", type=int, default=4096, help="scans in the Hough front-end leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compass-every", type=int, default=0,
+                    help="structural-compass update (doUpdateCompass) every k-th step; 0 = none (the headline)")
     ap.add_argument("--meas", type=int, default=1,
                     help="measurements (doUpdate calls) per step; the headline is 1, SURVEY 8d also asks for 4")
     args = ap.parse_args()
-    global MAX_MEAS
+    global MAX_MEAS, COMPASS_EVERY
     MAX_MEAS = args.meas
+    COMPASS_EVERY = args.compass_every
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -393,7 +397,7 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     # ---- inputs: this rank's filter range, generated once on the host into pinned memory ------------
-    syn = ekf.Synth(N_LM, steps_per_lap=T_LAP, max_meas=MAX_MEAS)
+    syn = ekf.Synth(N_LM, steps_per_lap=T_LAP, max_meas=MAX_MEAS, compass_every=COMPASS_EVERY)
     L = syn.record_len
     pinned = ekf.PinnedArray((F, T_LAP, L))
     syn.generate(F, T_LAP, f0=rank * F, out=pinned.array)
@@ -433,6 +437,8 @@ def main():
     n = 3 + 2 * N_LM
     # F_min: one propagate per step, gating per measurement, downdate per Old update
     flops_per_launch = n_steps_lap * (8 * N_LM + 170) + n_meas * 150 * N_LM + n_old * (2 * n * n + 42 * n)
+    if COMPASS_EVERY > 0:   # rank-1 symmetric downdate (half the matrix, one fma per pair) + gain / state, per compass step
+        flops_per_launch += (n_steps_lap // COMPASS_EVERY) * (n * n + 6 * n)
     value = world * F * T_LAP * args.steps / (ms_max * 1e-3)
 
     # ---- end-to-end through the C ABI with host buffers ("e2e") ---------------------------------------
@@ -474,7 +480,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "filters_per_gpu": F, "landmarks": N_LM,
-                       "landmark_capacity": CAP_LM, "steps_per_lap": T_LAP, "measurements_per_step": MAX_MEAS,
+                       "landmark_capacity": CAP_LM, "steps_per_lap": T_LAP, "measurements_per_step": MAX_MEAS, "compass_every": COMPASS_EVERY,
                        "old_fraction": n_old / max(n_meas, 1), "updates_per_step": n_meas / n_steps_lap, "dropped_new_associations_last_lap_rank0": n_dropped,
                        "l2": "inputs larger than L2: %.0f MB of step records + %.0f MB of covariance per pass"
                              % (rec.nbytes / 1e6, F * (3 + 2 * CAP_LM) * (4 + 2 * CAP_LM) * 8 / 1e6)},
