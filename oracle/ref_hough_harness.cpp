@@ -111,3 +111,53 @@ long refh_run_scans(int n_scans, int n, const double* x, const double* y, const 
 }
 
 }  // extern "C"
+
+// ---- the rest of the measurement front-end: FeatureDetector (features/featuredetector.cpp) ---------
+// FeatureDetector::getFeatures (featuredetector.cpp:16-70) is: getLines, clearHoughGrid,
+// fitLineSegments, extractCorners, getStructCompass. It cannot be called as a whole here (its
+// getLines call ends in the trap described above, inside a frame we cannot resume), so the harness
+// runs the same five stages in the same order through the class's own (private) methods.
+#define private public
+#include "featuredetector.h"
+#undef private
+
+extern "C" {
+
+// One scan through the stages of getFeatures. Outputs: features (x, y) pairs [max_feats],
+// returns their number; segments_out (optional) 7 doubles each: radius, theta, startX, startY,
+// endX, endY, numPoints [max_segs], *n_segs; compass_out: getStructCompass(lines, cur_phi) with the
+// detector's COMPASS_OFFSET preset to *offset_io (100.0 = unset) and written back.
+int reff_get_features(int n, const double* x, const double* y, const unsigned int* range, double cur_phi,
+                      double* offset_io, double* feats_out, int max_feats, double* segments_out, int max_segs,
+                      int* n_segs, double* compass_out) {
+  std::vector<ArSensorReading> readings;
+  readings.reserve(n);
+  for (int i = 0; i < n; ++i) readings.push_back(ArSensorReading(x[i], y[i], range[i]));
+  ArSick sick;
+  FeatureDetector fd(&sick);
+  if (offset_io) fd.COMPASS_OFFSET = *offset_io;
+  std::vector<struct houghLine> lines;
+  call_get_lines(*fd.hough, &readings, &lines);                       // featuredetector.cpp:39-40
+  fd.hough->clearHoughGrid();                                        // :41
+  std::vector<FeatureDetector::lineSegment> segs;
+  fd.fitLineSegments(&readings, &lines, &segs);                      // :44-45
+  std::vector<Feature> feats;
+  fd.extractCorners(&feats, &segs);                                  // :60
+  const double compass = fd.getStructCompass(&lines, cur_phi);       // :69
+  if (compass_out) *compass_out = compass;
+  if (offset_io) *offset_io = fd.COMPASS_OFFSET;
+  if (n_segs) *n_segs = (int)segs.size();
+  if (segments_out)
+    for (int i = 0; i < (int)segs.size() && i < max_segs; ++i) {
+      double* o = segments_out + 7 * i;
+      o[0] = segs[i].radius; o[1] = segs[i].theta; o[2] = segs[i].startX; o[3] = segs[i].startY;
+      o[4] = segs[i].endX; o[5] = segs[i].endY; o[6] = segs[i].numPoints;
+    }
+  for (int i = 0; i < (int)feats.size() && i < max_feats; ++i) {
+    feats_out[2 * i] = feats[i].x;
+    feats_out[2 * i + 1] = feats[i].y;
+  }
+  return (int)feats.size();
+}
+
+}  // extern "C"

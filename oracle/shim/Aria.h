@@ -30,4 +30,21 @@ class ArSensorReading {
   unsigned int range_ = 0;
 };
 
+// FeatureDetector (features/featuredetector.{h,cpp}) additionally names the laser device and a
+// time stamp; only FeatureDetector::getFeatures touches them, and the harness calls the stages
+// behind it directly, so these only have to exist.
+#include <vector>
+class ArTime {
+ public:
+  bool isAt(const ArTime&) const { return false; }
+};
+class ArSick {
+ public:
+  int lockDevice() { return 0; }
+  int unlockDevice() { return 0; }
+  std::vector<ArSensorReading>* getRawReadingsAsVector() { return &readings_; }
+  ArTime getLastReadingTime() const { return ArTime(); }
+  std::vector<ArSensorReading> readings_;
+};
+
 #endif  // EKF_SHIM_ARIA_H

@@ -61,6 +61,29 @@ class HoughOracle:
         R = np.ascontiguousarray(R, np.uint32)
         return self.lib.hough_oracle_run_scans(X.shape[0], X.shape[1], _p(X, c_dp), _p(Y, c_dp), _p(R, c_up))
 
+    def get_features(self, x, y, rng, cur_phi=0.0, offset=100.0):
+        """The stages of FeatureDetector::getFeatures after getLines.
+        -> features [n][2] (mm, robot frame), segments [m][7], compass, new offset, lines"""
+        L = self.lib
+        L.features_oracle_segments.argtypes = [C.c_int, c_dp, c_dp, c_up, c_dp, C.c_int, c_dp, C.c_int]
+        L.features_oracle_corners.argtypes = [c_dp, C.c_int, c_dp, C.c_int]
+        L.features_oracle_compass.argtypes = [c_dp, C.c_int, C.c_double, c_dp]
+        L.features_oracle_compass.restype = C.c_double
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        rng = np.ascontiguousarray(rng, np.uint32)
+        lines, _, _ = self.get_lines(x, y, rng)
+        lines = np.ascontiguousarray(lines)
+        segs = np.zeros((512, 7))
+        m = L.features_oracle_segments(len(x), _p(x, c_dp), _p(y, c_dp), _p(rng, c_up), _p(lines, c_dp), len(lines),
+                                       _p(segs, c_dp), 512)
+        segs = np.ascontiguousarray(segs[:m])
+        feats = np.zeros((512, 2))
+        n = L.features_oracle_corners(_p(segs, c_dp), m, _p(feats, c_dp), 512)
+        off = C.c_double(offset)
+        compass = L.features_oracle_compass(_p(lines, c_dp), len(lines), cur_phi, C.byref(off))
+        return feats[:n].copy(), segs, compass, off.value, lines
+
 
 class HoughRef:
     PATH = os.path.join(ORACLE_DIR, "_ref", "libhough_ref.so")
@@ -102,3 +125,19 @@ class HoughRef:
         Y = np.ascontiguousarray(Y, np.float64)
         R = np.ascontiguousarray(R, np.uint32)
         return self.lib.refh_run_scans(X.shape[0], X.shape[1], _p(X, c_dp), _p(Y, c_dp), _p(R, c_up))
+
+    def get_features(self, x, y, rng, cur_phi=0.0, offset=100.0):
+        """getLines, fitLineSegments, extractCorners, getStructCompass of the reference itself."""
+        L = self.lib
+        L.reff_get_features.argtypes = [C.c_int, c_dp, c_dp, c_up, C.c_double, c_dp, c_dp, C.c_int, c_dp, C.c_int, c_ip, c_dp]
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        rng = np.ascontiguousarray(rng, np.uint32)
+        feats = np.zeros((512, 2))
+        segs = np.zeros((512, 7))
+        m = C.c_int()
+        off = C.c_double(offset)
+        compass = C.c_double()
+        n = L.reff_get_features(len(x), _p(x, c_dp), _p(y, c_dp), _p(rng, c_up), cur_phi, C.byref(off), _p(feats, c_dp), 512,
+                                _p(segs, c_dp), 512, C.byref(m), C.byref(compass))
+        return feats[:n].copy(), segs[:m.value].copy(), compass.value, off.value

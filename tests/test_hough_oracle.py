@@ -62,3 +62,22 @@ def test_edge_cases(ho, hr):
         assert np.array_equal(ga, gb) and np.array_equal(pa, pb) and np.array_equal(la, lb), "case %d" % k
     assert len(ho.get_lines(*cases[0])[0]) == 0
     assert ho.get_lines(*cases[3], want_grid=True)[2].max() == 181
+
+
+def test_feature_stages_match_the_reference(ho, hr):
+    """fitLineSegments, extractCorners and getStructCompass (featuredetector.cpp:74-362) behind the
+    Hough transform: segments, corner features and the compass value, bit for bit; the compass
+    offset is carried from scan to scan as the detector object would."""
+    X, Y, R = scan_synth.make_scans(60, seed=17, n_boxes=4)
+    rng = np.random.default_rng(0)
+    off_a = off_b = 100.0
+    n_feats = 0
+    for k in range(len(X)):
+        phi = float(rng.uniform(-7, 7))
+        fa, sa, ca, off_a, _ = ho.get_features(X[k], Y[k], R[k], phi, off_a)
+        fb, sb, cb, off_b = hr.get_features(X[k], Y[k], R[k], phi, off_b)
+        assert sa.shape == sb.shape and np.array_equal(sa, sb), "segments, scan %d" % k
+        assert fa.shape == fb.shape and np.array_equal(fa, fb), "features, scan %d" % k
+        assert ca == cb and off_a == off_b, "compass, scan %d" % k
+        n_feats += len(fa)
+    assert n_feats >= 30
