@@ -465,6 +465,220 @@ __global__ void __launch_bounds__(kLinesWarps * 32) hough_lines_kernel(const int
   if (lane == 0) n_lines[s] = n;
 }
 
+// ---- FeatureDetector stages behind getLines (featuredetector.cpp:74-362), one warp per scan ----------
+// fitLineSegments: the closest line of every reading is found in parallel (one reading per lane);
+// the segment lists are per line and only ever touched by readings of that line, so each lane then
+// walks the readings of its own line(s) in scan order (the list logic is sequential by nature).
+// extractCorners: for every segment i the pairs (i, j > i) go one per lane, a ballot keeps the
+// features in the reference's (i, j) order. getStructCompass: a handful of lines, one lane.
+// sin / cos of the line angles are the device's double routines rounded to float; they can differ
+// from glibc's where the double result sits within an ulp of a float rounding boundary (~1e-8 per
+// value) - everything else is the reference's arithmetic (float products for the determinant).
+constexpr int kFeatWarps = 2;
+constexpr int F_POINT_DIST = 600, F_MIN_POINTS = 3, F_CORNER_DIST = 90000, F_MIN_DIST = 1000 * 1000;
+struct FeatSmem {
+  double px[MAXP], py[MAXP];
+  double rad[PK], th[PK];
+  double s_sx[MAXP], s_sy[MAXP], s_ex[MAXP], s_ey[MAXP];
+  float sn[PK], cs[PK];
+  int head[PK];
+  int good_off[PK];
+  int pt_line[MAXP];
+  int s_line[MAXP], s_np[MAXP], s_next[MAXP];
+  int order[MAXP];
+  int pool_count;
+};
+
+struct FeatArgs {
+  const double* x;
+  const double* y;
+  const unsigned int* range;
+  const ekf_hough_line* lines;   // [n_scans][lines_stride]
+  const int* n_lines;
+  int lines_stride;
+  int n_scans, n_points;
+  const double* cur_phi;         // [n_scans] or null
+  double* offset;                // [n_scans] in/out or null
+  ekf_feature* feats;            // [n_scans][max_feats]
+  int* n_feats;
+  int max_feats;
+  double* compass;               // [n_scans] or null
+  double* segs;                  // [n_scans][max_segs][7] or null
+  int* n_segs;
+  int max_segs;
+};
+
+__global__ void __launch_bounds__(kFeatWarps * 32) hough_features_kernel(const FeatArgs a) {
+  __shared__ FeatSmem smem[kFeatWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int s = blockIdx.x * kFeatWarps + wib;
+  if (s >= a.n_scans) return;
+  FeatSmem& g = smem[wib];
+  const int n_points = a.n_points;
+  int nl = a.n_lines[s];
+  if (nl > a.lines_stride) nl = a.lines_stride;
+  const ekf_hough_line* L = a.lines + (size_t)s * a.lines_stride;
+  for (int l = lane; l < nl; l += 32) {
+    g.rad[l] = L[l].radius;
+    g.th[l] = L[l].theta;
+    g.sn[l] = (float)sin(L[l].theta);            // featuredetector.cpp:88-89
+    g.cs[l] = (float)cos(L[l].theta);
+    g.head[l] = -1;
+  }
+  if (lane == 0) g.pool_count = 0;
+  __syncwarp();
+  // ---- closest line of every reading (:97-118) -----------------------------------------------------
+  for (int p = lane; p < n_points; p += 32) {
+    const double px = a.x[(size_t)s * n_points + p], py = a.y[(size_t)s * n_points + p];
+    g.px[p] = px;
+    g.py[p] = py;
+    int line = -1;
+    if (a.range[(size_t)s * n_points + p] <= (unsigned int)EKF_HOUGH_MAX_DIST) {
+      double best = 1000000.0;
+      int arg = 0;
+      for (int l = 0; l < nl; ++l) {
+        const double r = px * (double)g.cs[l] + py * (double)g.sn[l];
+        const double d = fabs(g.rad[l] - r);
+        if (d < best) { best = d; arg = l; }
+      }
+      if (!(best > (double)F_POINT_DIST)) line = arg;
+    }
+    g.pt_line[p] = line;
+  }
+  __syncwarp();
+  // ---- segment lists, one line per lane, readings in scan order (:120-201) -------------------------
+  for (int line = lane; line < nl; line += 32) {
+    const bool by_x = fabsf(g.sn[line]) > fabsf(g.cs[line]);
+    for (int p = 0; p < n_points; ++p) {
+      if (g.pt_line[p] != line) continue;
+      const double px = g.px[p], py = g.py[p];
+      const double v = by_x ? px : py;
+      int q = g.head[line];
+      while (q >= 0) {
+        const double sv = by_x ? g.s_sx[q] : g.s_sy[q], ev = by_x ? g.s_ex[q] : g.s_ey[q];
+        if (v <= sv && v >= ev) { g.s_np[q]++; break; }
+        if (v > sv && fabs(v - sv) <= (double)F_POINT_DIST) { g.s_sx[q] = px; g.s_sy[q] = py; g.s_np[q]++; break; }
+        if (v < ev && fabs(v - ev) <= (double)F_POINT_DIST) { g.s_ex[q] = px; g.s_ey[q] = py; g.s_np[q]++; break; }
+        q = g.s_next[q];
+      }
+      if (q < 0) {
+        q = atomicAdd(&g.pool_count, 1);
+        g.s_line[q] = line;
+        g.s_np[q] = 1;
+        g.s_sx[q] = g.s_ex[q] = px;
+        g.s_sy[q] = g.s_ey[q] = py;
+        g.s_next[q] = g.head[line];
+        g.head[line] = q;
+      }
+    }
+    int good = 0;                                  // :205-221 keeps segments with more than MIN_POINTS readings
+    for (int q = g.head[line]; q >= 0; q = g.s_next[q]) good += g.s_np[q] > F_MIN_POINTS;
+    g.good_off[line] = good;
+  }
+  __syncwarp();
+  int n_segs = 0;
+  if (lane == 0) {                                 // lines in order, each list newest first
+    for (int l = 0; l < nl; ++l) { const int c = g.good_off[l]; g.good_off[l] = n_segs; n_segs += c; }
+  }
+  n_segs = __shfl_sync(0xffffffffu, n_segs, 0);
+  __syncwarp();
+  for (int line = lane; line < nl; line += 32) {
+    int o = g.good_off[line];
+    for (int q = g.head[line]; q >= 0; q = g.s_next[q])
+      if (g.s_np[q] > F_MIN_POINTS) g.order[o++] = q;
+  }
+  __syncwarp();
+  if (a.segs) {
+    double* so = a.segs + (size_t)s * a.max_segs * 7;
+    for (int k = lane; k < n_segs && k < a.max_segs; k += 32) {
+      const int q = g.order[k], l = g.s_line[q];
+      so[7 * k + 0] = g.rad[l]; so[7 * k + 1] = g.th[l]; so[7 * k + 2] = g.s_sx[q]; so[7 * k + 3] = g.s_sy[q];
+      so[7 * k + 4] = g.s_ex[q]; so[7 * k + 5] = g.s_ey[q]; so[7 * k + 6] = (double)g.s_np[q];
+    }
+  }
+  if (a.n_segs && lane == 0) a.n_segs[s] = n_segs;
+  // ---- corners (:230-292): pairs (i, j > i) in order ---------------------------------------------------
+  const double corner_theta = 22.0 * 3.141592654 / 180.0;
+  ekf_feature* fo = a.feats + (size_t)s * a.max_feats;
+  int n_feats = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const int qi = g.order[i], li = g.s_line[qi];
+    const double r1 = g.rad[li], t1 = g.th[li];
+    const float sni = g.sn[li], csi = g.cs[li];
+    for (int base = i + 1; base < n_segs; base += 32) {
+      const int j = base + lane;
+      bool hit = false;
+      double cx = 0.0, cy = 0.0;
+      if (j < n_segs) {
+        const int qj = g.order[j], lj = g.s_line[qj];
+        double dth = fabs(t1 - g.th[lj]);
+        if (dth > 3.141592654) dth = fabs(dth - 6.283185307);
+        if (dth > 1.570796327) dth = fabs(dth - 3.141592654);
+        if (!(dth < corner_theta)) {
+          const float snj = g.sn[lj], csj = g.cs[lj];
+          const double det = (double)__fsub_rn(__fmul_rn(csi, snj), __fmul_rn(sni, csj));   // float arithmetic (float arrays)
+          const double r2 = g.rad[lj];
+          cx = (r1 * (double)snj - r2 * (double)sni) / det;
+          cy = (r2 * (double)csi - r1 * (double)csj) / det;
+          double dx, dy;
+          dx = g.s_sx[qi] - cx; dy = g.s_sy[qi] - cy; const bool start1 = (dx * dx + dy * dy) < (double)F_CORNER_DIST;
+          dx = g.s_ex[qi] - cx; dy = g.s_ey[qi] - cy; const bool end1 = (dx * dx + dy * dy) < (double)F_CORNER_DIST;
+          dx = g.s_sx[qj] - cx; dy = g.s_sy[qj] - cy; const bool start2 = (dx * dx + dy * dy) < (double)F_CORNER_DIST;
+          dx = g.s_ex[qj] - cx; dy = g.s_ey[qj] - cy; const bool end2 = (dx * dx + dy * dy) < (double)F_CORNER_DIST;
+          hit = (start1 || end1) && (start2 || end2) && (cx * cx + cy * cy) > (double)F_MIN_DIST;
+        }
+      }
+      const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+      const int pos = n_feats + __popc(hits & ((1u << lane) - 1u));
+      if (hit && pos < a.max_feats) { fo[pos].x = cx; fo[pos].y = cy; }
+      n_feats += __popc(hits);
+    }
+  }
+  if (lane == 0) a.n_feats[s] = n_feats;
+  // ---- structural compass (:297-362) ------------------------------------------------------------------
+  if (a.compass && lane == 0) {
+    // groups reuse the segment scratch (no longer needed): s_sx = weighted angle sums, s_sy = weights
+    double* g_theta = g.s_sx;
+    double* g_weight = g.s_sy;
+    int ng = 0;
+    const double thresh = 10 * 3.141592654 / 180.0;
+    for (int i = 0; i < nl; ++i) {
+      const double th = g.th[i] - 1.570796327 * floor(g.th[i] / 1.570796327);
+      const double w = L[i].weight;
+      bool merged = false;
+      for (int j = 0; j < ng; ++j) {                 // no break: a line joins every group it is close to
+        const double mean = g_theta[j] / g_weight[j];
+        if (fabs(th - mean) < thresh) { g_theta[j] += th * w; g_weight[j] += w; merged = true; }
+      }
+      if (!merged && ng < MAXP) { g_theta[ng] = th * w; g_weight[ng] = w; ++ng; }
+    }
+    double best_theta = 0.0, best_w = 0.0;
+    for (int j = 0; j < ng; ++j)
+      if (g_weight[j] > best_w) { best_theta = g_theta[j]; best_w = g_weight[j]; }
+    double result = 100.0;                           // NO_COMPASS
+    if (best_w != 0.0) {
+      double cardinal = -(best_theta / best_w);
+      double off = a.offset ? a.offset[s] : 100.0;
+      if (off == 100.0) off = cardinal;
+      if (a.offset) a.offset[s] = off;
+      cardinal -= off;
+      cardinal -= 1.570796327 * floor(cardinal / 1.570796327);
+      double phi = a.cur_phi ? a.cur_phi[s] : 0.0;
+      phi -= 6.283185307 * floor(phi / 6.283185307);
+      const double e1 = fabs(phi - cardinal), e2 = fabs(phi - cardinal - 1.570796327);
+      const double e3 = fabs(phi - cardinal - 3.141592654), e4 = fabs(phi - cardinal - 4.71238898);
+      const double e5 = fabs(phi - cardinal - 6.283185307), e6 = fabs(phi - cardinal + 1.570796327);
+      if (e1 <= e2 && e1 <= e3 && e1 <= e4 && e1 <= e5 && e1 <= e6) result = cardinal;
+      else if (e2 <= e3 && e2 <= e4 && e2 <= e5 && e2 <= e6) result = cardinal + 1.570796327;
+      else if (e3 <= e4 && e3 <= e5 && e3 <= e6) result = cardinal + 3.141592654;
+      else if (e4 <= e5 && e4 <= e6) result = cardinal + 4.71238898;
+      else if (e5 <= e6) result = cardinal;
+      else result = cardinal + 4.71238898;
+    }
+    a.compass[s] = result;
+  }
+}
+
 std::string g_hough_create_error;
 constexpr int kHoughChunks = 16;
 
@@ -767,6 +981,80 @@ int ekf_hough_get_lines(ekf_hough h, int n_scans, int n_points, const double* x,
   if (rc != EKF_OK) return rc;
   if (grid) HG_CK(h, cudaMemcpyAsync(grid, h->d_grid, (size_t)n_scans * TH * RS, cudaMemcpyDeviceToHost, h->stream));
   return ekf_hough_download(h, lines, max_lines, n_lines, peaks, values);
+}
+
+int ekf_hough_get_features(ekf_hough h, int n_scans, int n_points, const double* x, const double* y, const uint32_t* range,
+                           const double* cur_phi, double* compass_offset, ekf_feature* feats, int max_feats, int32_t* n_feats,
+                           double* compass, ekf_hough_line* lines, int max_lines, int32_t* n_lines, double* segments,
+                           int max_segs, int32_t* n_segs) {
+  if (!h || !feats || !n_feats || max_feats < 1 || (segments && max_segs < 1) || (lines && max_lines < 1))
+    return hfail(h, EKF_ERR_BAD_ARG, "ekf_hough_get_features: feats, n_feats and max_feats >= 1 required");
+  cudaSetDevice(h->device);
+  int rc = ekf_hough_upload(h, n_scans, n_points, x, y, range);
+  if (rc != EKF_OK) return rc;
+  rc = launch(h, false, PK);                       // every line is kept: the segment stage needs them all
+  if (rc != EKF_OK) return rc;
+  const size_t S = (size_t)n_scans;
+  // scratch for this call (freed before returning; the call is synchronous anyway)
+  ekf_feature* d_feats = nullptr;
+  int* d_nfeats = nullptr;
+  int* d_nsegs = nullptr;
+  double* d_phi = nullptr;
+  double* d_off = nullptr;
+  double* d_compass = nullptr;
+  double* d_segs = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_feats); cudaFree(d_nfeats); cudaFree(d_nsegs); cudaFree(d_phi); cudaFree(d_off); cudaFree(d_compass); cudaFree(d_segs);
+  };
+#define HF_CK(call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      cleanup();                                                                                 \
+      return hfail(h, EKF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+    }                                                                                            \
+  } while (0)
+  HF_CK(cudaMalloc(&d_feats, S * max_feats * sizeof(ekf_feature)));
+  HF_CK(cudaMalloc(&d_nfeats, S * sizeof(int)));
+  HF_CK(cudaMalloc(&d_nsegs, S * sizeof(int)));
+  if (compass) {
+    HF_CK(cudaMalloc(&d_compass, S * sizeof(double)));
+    HF_CK(cudaMalloc(&d_phi, S * sizeof(double)));
+    HF_CK(cudaMalloc(&d_off, S * sizeof(double)));
+    if (cur_phi) HF_CK(cudaMemcpyAsync(d_phi, cur_phi, S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else HF_CK(cudaMemsetAsync(d_phi, 0, S * sizeof(double), h->stream));
+    std::vector<double> unset;
+    if (compass_offset) HF_CK(cudaMemcpyAsync(d_off, compass_offset, S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else {
+      unset.assign(S, 100.0);
+      HF_CK(cudaMemcpyAsync(d_off, unset.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      HF_CK(cudaStreamSynchronize(h->stream));
+    }
+  }
+  if (segments) HF_CK(cudaMalloc(&d_segs, S * max_segs * 7 * sizeof(double)));
+  FeatArgs a;
+  a.x = h->d_x; a.y = h->d_y; a.range = h->d_range;
+  a.lines = h->d_lines; a.n_lines = h->d_nlines; a.lines_stride = h->run_max_lines;
+  a.n_scans = n_scans; a.n_points = n_points;
+  a.cur_phi = d_phi; a.offset = d_off;
+  a.feats = d_feats; a.n_feats = d_nfeats; a.max_feats = max_feats;
+  a.compass = d_compass;
+  a.segs = d_segs; a.n_segs = d_nsegs; a.max_segs = max_segs;
+  hough_features_kernel<<<(n_scans + kFeatWarps - 1) / kFeatWarps, kFeatWarps * 32, 0, h->stream>>>(a);
+  HF_CK(cudaGetLastError());
+  HF_CK(cudaMemcpyAsync(feats, d_feats, S * max_feats * sizeof(ekf_feature), cudaMemcpyDeviceToHost, h->stream));
+  HF_CK(cudaMemcpyAsync(n_feats, d_nfeats, S * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (n_segs) HF_CK(cudaMemcpyAsync(n_segs, d_nsegs, S * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (segments) HF_CK(cudaMemcpyAsync(segments, d_segs, S * max_segs * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (compass) {
+    HF_CK(cudaMemcpyAsync(compass, d_compass, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (compass_offset) HF_CK(cudaMemcpyAsync(compass_offset, d_off, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  HF_CK(cudaStreamSynchronize(h->stream));
+#undef HF_CK
+  cleanup();
+  if (lines || n_lines) return ekf_hough_download(h, lines, lines ? max_lines : 0, n_lines, nullptr, nullptr);
+  return EKF_OK;
 }
 
 int ekf_hough_kernel_time(ekf_hough h, float* total_ms, int* n_launches) {

@@ -131,6 +131,8 @@ def core_lib():
         L.ekf_hough_tables.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.ekf_hough_tables.restype = None
         L.ekf_hough_get_lines.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, c_u32p, c_dp, C.c_int, c_ip, c_ip, c_ip, c_u8p]
+        L.ekf_hough_get_features.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, c_u32p, c_dp, c_dp, c_dp, C.c_int, c_ip, c_dp,
+                                             c_dp, C.c_int, c_ip, c_dp, C.c_int, c_ip]
         L.ekf_hough_upload.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, c_u32p]
         L.ekf_hough_run_resident.argtypes = [H, C.c_int]
         L.ekf_hough_download.argtypes = [H, c_dp, C.c_int, c_ip, c_ip, c_ip]
@@ -609,6 +611,27 @@ class HoughBatch:
                                              grid.ctypes.data_as(C.POINTER(C.c_uint8)) if want_grid else None))
         return {"lines": [lines[s, :min(n_lines[s], max_lines)].copy() for s in range(S)] if split else lines,
                 "n_lines": n_lines, "peaks": peaks, "values": values, "grid": grid}
+
+    def get_features(self, X, Y, R, cur_phi=None, offset=None, max_feats=32, want_compass=True, want_segments=False,
+                     max_segs=64, max_lines=64):
+        """FeatureDetector::getFeatures for a batch: -> dict(feats [S][max_feats][2], n_feats, compass, offset,
+        lines, n_lines, segments, n_segs). cur_phi / offset: per-scan filter heading and COMPASS_OFFSET (100 = unset)."""
+        X, Y, R = self._inputs(X, Y, R)
+        S, P = X.shape
+        feats = np.zeros((S, max_feats, 2))
+        n_feats = np.zeros(S, np.int32)
+        compass = np.zeros(S) if want_compass else None
+        phi = np.ascontiguousarray(cur_phi, np.float64) if cur_phi is not None else None
+        off = np.array(offset, np.float64, copy=True) if offset is not None else (np.full(S, 100.0) if want_compass else None)
+        lines = np.zeros((S, max_lines, 3))
+        n_lines = np.zeros(S, np.int32)
+        segs = np.zeros((S, max_segs, 7)) if want_segments else None
+        n_segs = np.zeros(S, np.int32)
+        self._chk(self.L.ekf_hough_get_features(self.h, S, P, _dp(X), _dp(Y), R.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                _dp(phi), _dp(off), _dp(feats), max_feats, _ip(n_feats), _dp(compass),
+                                                _dp(lines), max_lines, _ip(n_lines), _dp(segs), max_segs, _ip(n_segs)))
+        return {"feats": feats, "n_feats": n_feats, "compass": compass, "offset": off, "lines": lines, "n_lines": n_lines,
+                "segments": segs, "n_segs": n_segs}
 
     def upload(self, X, Y, R):
         X, Y, R = self._inputs(X, Y, R)

@@ -38,6 +38,13 @@ typedef struct ekf_hough_line {
   double weight;
 } ekf_hough_line;
 
+/* Feature.x, Feature.y (featuredetector.h:16-19): a corner in the robot frame, mm. */
+typedef struct ekf_feature {
+  double x, y;
+} ekf_feature;
+
+#define EKF_HOUGH_NO_COMPASS 100.0   /* FeatureDetector::NO_COMPASS (featuredetector.h:25) */
+
 /* Status codes are the EKF_* codes of ekf_slam_b200.h (0 = ok). */
 int ekf_hough_create(ekf_hough* out, int device, int max_scans);
 int ekf_hough_destroy(ekf_hough h);
@@ -57,6 +64,21 @@ void ekf_hough_tables(float* cos_out, float* sin_out);
 int ekf_hough_get_lines(ekf_hough h, int n_scans, int n_points, const double* x, const double* y,
                         const uint32_t* range, ekf_hough_line* lines, int max_lines, int32_t* n_lines,
                         int32_t* peaks, int32_t* values, uint8_t* grid);
+
+/* FeatureDetector::getFeatures (featuredetector.cpp:16-70) minus the device lock / time-stamp checks,
+ * for n_scans scans: getLines, fitLineSegments (:74-226), extractCorners (:230-292) and, when
+ * compass != NULL, getStructCompass (:297-362) - all on the GPU. feats [n_scans][max_feats] and
+ * n_feats [n_scans] (full count) are the corner features slam.cpp:150-160 turns into (z, R).
+ * cur_phi [n_scans] is the filter heading handed to getStructCompass (NULL = 0); compass_offset
+ * [n_scans] is the detector's COMPASS_OFFSET, in/out (100.0 = not yet set; NULL = always unset);
+ * compass [n_scans] receives the compass value or EKF_HOUGH_NO_COMPASS. Optional outputs: lines /
+ * n_lines as above, segments [n_scans][max_segs][7] = {radius, theta, startX, startY, endX, endY,
+ * numPoints} and n_segs. Integer and IEEE arithmetic as the reference's, except that sin / cos of the
+ * line angles come from the device's double routines. */
+int ekf_hough_get_features(ekf_hough h, int n_scans, int n_points, const double* x, const double* y,
+                           const uint32_t* range, const double* cur_phi, double* compass_offset, ekf_feature* feats,
+                           int max_feats, int32_t* n_feats, double* compass, ekf_hough_line* lines, int max_lines,
+                           int32_t* n_lines, double* segments, int max_segs, int32_t* n_segs);
 
 /* The same in three steps, for timing with the inputs resident in HBM: upload, run (kernels only,
  * asynchronous; at most max_lines lines per scan are kept), download (synchronises). */

@@ -104,6 +104,29 @@ def test_edge_cases(ekf, ho):
         _check(ekf, ho, Xs[:, idx], Ys[:, idx], Rs[:, idx], want_grid=True)
 
 
+def test_feature_stages_match_the_oracle(ekf, ho):
+    """fitLineSegments / extractCorners / getStructCompass on the GPU (ekf_hough_get_features) against the
+    restatement that is pinned to the reference's featuredetector.cpp: segments, corner features and
+    the compass value. (The device's sin/cos of a line angle, rounded to float, could in principle
+    differ from glibc's at a float rounding boundary, about 1e-8 per value; none does here.)"""
+    X, Y, R = scan_synth.make_scans(300, seed=21, n_boxes=4)
+    rng = np.random.default_rng(3)
+    phi = rng.uniform(-7, 7, len(X))
+    off = np.where(rng.random(len(X)) < 0.5, 100.0, rng.uniform(-1.5, 0.0, len(X)))
+    hb = ekf.HoughBatch(len(X))
+    got = hb.get_features(X, Y, R, cur_phi=phi, offset=off, max_feats=32, want_segments=True, max_segs=64, max_lines=64)
+    hb.close()
+    total = 0
+    for k in range(len(X)):
+        feats, segs, compass, new_off, lines = ho.get_features(X[k], Y[k], R[k], float(phi[k]), float(off[k]))
+        assert got["n_lines"][k] == len(lines) and np.array_equal(got["lines"][k, :len(lines)], lines), "lines, scan %d" % k
+        assert got["n_segs"][k] == len(segs) and np.array_equal(got["segments"][k, :len(segs)], segs), "segments, scan %d" % k
+        assert got["n_feats"][k] == len(feats) and np.array_equal(got["feats"][k, :len(feats)], feats), "features, scan %d" % k
+        assert got["compass"][k] == compass and got["offset"][k] == new_off, "compass, scan %d" % k
+        total += len(feats)
+    assert total >= 150
+
+
 def test_argument_validation(ekf):
     hb = ekf.HoughBatch(4)
     X, Y, R = scan_synth.make_scans(5, seed=1)
