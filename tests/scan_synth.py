@@ -55,3 +55,22 @@ def make_scans(n_scans, seed=0, noise_mm=8.0, room=(9000.0, 7000.0), n_boxes=3, 
         X[s] = r * np.cos(ang)
         Y[s] = r * np.sin(ang)
     return X, Y, R
+
+
+def make_room(seed=0, room=(9000.0, 7000.0), n_boxes=3):
+    """A fixed room: the outer rectangle plus a few boxes, as a list of wall segments (mm)."""
+    rng = np.random.default_rng(seed)
+    W, H = room
+    segs = _box(W / 2, H / 2, W, H)
+    for _ in range(n_boxes):
+        segs += _box(rng.uniform(0.2 * W, 0.8 * W), rng.uniform(0.2 * H, 0.8 * H), rng.uniform(500, 1200), rng.uniform(500, 1200))
+    return segs
+
+
+def scan_from_pose(segs, px, py, phi, rng, noise_mm=8.0, max_range=8191):
+    """One LMS-200 scan taken at pose (px, py [mm], phi [rad]) in the room `segs`."""
+    ang = np.deg2rad(np.arange(N_BEAMS) - 90.0)
+    d = _ray_segments(px, py, np.cos(phi + ang), np.sin(phi + ang), segs)
+    d = d + rng.normal(0.0, noise_mm, N_BEAMS)
+    r = np.where(np.isfinite(d), np.clip(np.rint(d), 1, max_range), max_range).astype(np.uint32)
+    return r * np.cos(ang), r * np.sin(ang), r
