@@ -31,6 +31,17 @@ def main():
     R = np.vstack([R, r, np.full(181, 8191, np.uint32)])
     c, s = ref.tables()
     peaks, nz_cell, nz_val, nz_off, lines, n_lines = [], [], [], [0], [], []
+    # the stages behind getLines (fitLineSegments, extractCorners, getStructCompass), offset carried along
+    phi = np.linspace(-5.0, 5.0, len(X))
+    feats, n_feats, segs, n_segs, compass, off_in, off_out = [], [], [], [], [], [], []
+    off = 100.0
+    for k in range(len(X)):
+        f, sg, cp, new_off = ref.get_features(X[k], Y[k], R[k], float(phi[k]), off)
+        fp = np.zeros((64, 2)); fp[:len(f)] = f
+        sp = np.zeros((64, 7)); sp[:len(sg)] = sg
+        feats.append(fp); n_feats.append(len(f)); segs.append(sp); n_segs.append(len(sg))
+        compass.append(cp); off_in.append(off); off_out.append(new_off)
+        off = new_off
     for k in range(len(X)):
         ln, pk, grid = ref.get_lines(X[k], Y[k], R[k], want_grid=True)
         cells = np.flatnonzero(grid).astype(np.int32)
@@ -45,8 +56,11 @@ def main():
     out = os.path.join(HERE, "hough", "ref_8scans.npz")
     np.savez_compressed(out, x=X, y=Y, range=R, cos=c, sin=s, peaks=np.array(peaks, np.int32),
                         nz_cell=np.concatenate(nz_cell), nz_val=np.concatenate(nz_val), nz_off=np.array(nz_off, np.int64),
-                        lines=np.array(lines), n_lines=np.array(n_lines, np.int32))
-    print(out, os.path.getsize(out), "bytes;", "lines per scan:", n_lines)
+                        lines=np.array(lines), n_lines=np.array(n_lines, np.int32),
+                        phi=phi, feats=np.array(feats), n_feats=np.array(n_feats, np.int32), segs=np.array(segs),
+                        n_segs=np.array(n_segs, np.int32), compass=np.array(compass), off_in=np.array(off_in),
+                        off_out=np.array(off_out))
+    print(out, os.path.getsize(out), "bytes;", "lines per scan:", n_lines, "features per scan:", n_feats)
 
 
 if __name__ == "__main__":

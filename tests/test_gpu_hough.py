@@ -52,6 +52,15 @@ def test_cuda_matches_the_golden_vectors(ekf):
             assert np.array_equal(got["grid"][k], golden_grid(g, k)), "accumulator, scan %d" % k
             assert np.array_equal(got["peaks"][k], g["peaks"][k]), "peak array, scan %d" % k
             assert got["n_lines"][k] == n and np.array_equal(got["lines"][k], g["lines"][k][:n]), "lines, scan %d" % k
+        hb = ekf.HoughBatch(len(g["x"]))
+        f = hb.get_features(g["x"], g["y"], g["range"], cur_phi=g["phi"], offset=g["off_in"], max_feats=64,
+                            want_segments=True, max_segs=64)
+        hb.close()
+        for k in range(len(g["x"])):
+            n, m = int(g["n_feats"][k]), int(g["n_segs"][k])
+            assert f["n_segs"][k] == m and np.array_equal(f["segments"][k, :m], g["segs"][k][:m]), "segments, scan %d" % k
+            assert f["n_feats"][k] == n and np.array_equal(f["feats"][k, :n], g["feats"][k][:n]), "features, scan %d" % k
+            assert f["compass"][k] == g["compass"][k] and f["offset"][k] == g["off_out"][k], "compass, scan %d" % k
 
 
 def test_more_scans_than_sms(ekf, ho):

@@ -38,3 +38,14 @@ def test_oracle_matches_golden(ho, path):
         assert np.array_equal(peaks, g["peaks"][k]), "peak array, scan %d" % k
         n = int(g["n_lines"][k])
         assert len(lines) == n and np.array_equal(lines, g["lines"][k][:n]), "lines, scan %d" % k
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_feature_stages_match_golden(ho, path):
+    g = np.load(path)
+    for k in range(len(g["x"])):
+        feats, segs, compass, off, _ = ho.get_features(g["x"][k], g["y"][k], g["range"][k], float(g["phi"][k]), float(g["off_in"][k]))
+        n, m = int(g["n_feats"][k]), int(g["n_segs"][k])
+        assert len(segs) == m and np.array_equal(segs, g["segs"][k][:m]), "segments, scan %d" % k
+        assert len(feats) == n and np.array_equal(feats, g["feats"][k][:n]), "features, scan %d" % k
+        assert compass == g["compass"][k] and off == g["off_out"][k], "compass, scan %d" % k
