@@ -700,6 +700,16 @@ struct ekf_hough_s {
   size_t grid_cap = 0;
   ekf_hough_line* d_lines = nullptr;
   int* d_nlines = nullptr;
+  // feature stages (allocated on first use, grown on demand)
+  ekf_feature* d_feats = nullptr;
+  size_t feats_cap = 0;
+  double* d_segs = nullptr;
+  size_t segs_cap = 0;
+  int* d_nfeats = nullptr;
+  int* d_nsegs = nullptr;
+  double* d_phi = nullptr;
+  double* d_off = nullptr;
+  double* d_compass = nullptr;
   int lines_cap = 0;          // lines per scan the device buffer holds
   int run_max_lines = 0;      // of the last run
   int n_scans = 0, n_points = 0;
@@ -859,6 +869,8 @@ int ekf_hough_destroy(ekf_hough h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_range); cudaFree(h->d_peaks); cudaFree(h->d_values);
   cudaFree(h->d_cos); cudaFree(h->d_sin); cudaFree(h->d_grid); cudaFree(h->d_lines); cudaFree(h->d_nlines);
+  cudaFree(h->d_feats); cudaFree(h->d_segs); cudaFree(h->d_nfeats); cudaFree(h->d_nsegs); cudaFree(h->d_phi); cudaFree(h->d_off);
+  cudaFree(h->d_compass);
   if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
   if (h->ev_done) {
     cudaEventDestroy(h->ev_done);
@@ -994,44 +1006,46 @@ int ekf_hough_get_features(ekf_hough h, int n_scans, int n_points, const double*
   if (rc != EKF_OK) return rc;
   rc = launch(h, false, PK);                       // every line is kept: the segment stage needs them all
   if (rc != EKF_OK) return rc;
-  const size_t S = (size_t)n_scans;
-  // scratch for this call (freed before returning; the call is synchronous anyway)
-  ekf_feature* d_feats = nullptr;
-  int* d_nfeats = nullptr;
-  int* d_nsegs = nullptr;
-  double* d_phi = nullptr;
-  double* d_off = nullptr;
-  double* d_compass = nullptr;
-  double* d_segs = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_feats); cudaFree(d_nfeats); cudaFree(d_nsegs); cudaFree(d_phi); cudaFree(d_off); cudaFree(d_compass); cudaFree(d_segs);
-  };
-#define HF_CK(call)                                                                              \
-  do {                                                                                           \
-    cudaError_t e__ = (call);                                                                    \
-    if (e__ != cudaSuccess) {                                                                    \
-      cleanup();                                                                                 \
-      return hfail(h, EKF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
-    }                                                                                            \
-  } while (0)
-  HF_CK(cudaMalloc(&d_feats, S * max_feats * sizeof(ekf_feature)));
-  HF_CK(cudaMalloc(&d_nfeats, S * sizeof(int)));
-  HF_CK(cudaMalloc(&d_nsegs, S * sizeof(int)));
+  const size_t S = (size_t)n_scans, MS = (size_t)h->max_scans;
+#define HF_CK(call) HG_CK(h, call)
+  if (!h->d_nfeats) {
+    HF_CK(cudaMalloc(&h->d_nfeats, MS * sizeof(int)));
+    HF_CK(cudaMalloc(&h->d_nsegs, MS * sizeof(int)));
+    HF_CK(cudaMalloc(&h->d_phi, MS * sizeof(double)));
+    HF_CK(cudaMalloc(&h->d_off, MS * sizeof(double)));
+    HF_CK(cudaMalloc(&h->d_compass, MS * sizeof(double)));
+  }
+  if (MS * max_feats > h->feats_cap) {
+    cudaFree(h->d_feats);
+    h->d_feats = nullptr;
+    h->feats_cap = 0;
+    HF_CK(cudaMalloc(&h->d_feats, MS * max_feats * sizeof(ekf_feature)));
+    h->feats_cap = MS * max_feats;
+  }
+  if (segments && MS * max_segs * 7 > h->segs_cap) {
+    cudaFree(h->d_segs);
+    h->d_segs = nullptr;
+    h->segs_cap = 0;
+    HF_CK(cudaMalloc(&h->d_segs, MS * max_segs * 7 * sizeof(double)));
+    h->segs_cap = MS * max_segs * 7;
+  }
+  ekf_feature* d_feats = h->d_feats;
+  int* d_nfeats = h->d_nfeats;
+  int* d_nsegs = h->d_nsegs;
+  double* d_phi = compass ? h->d_phi : nullptr;
+  double* d_off = compass ? h->d_off : nullptr;
+  double* d_compass = compass ? h->d_compass : nullptr;
+  double* d_segs = segments ? h->d_segs : nullptr;
   if (compass) {
-    HF_CK(cudaMalloc(&d_compass, S * sizeof(double)));
-    HF_CK(cudaMalloc(&d_phi, S * sizeof(double)));
-    HF_CK(cudaMalloc(&d_off, S * sizeof(double)));
     if (cur_phi) HF_CK(cudaMemcpyAsync(d_phi, cur_phi, S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     else HF_CK(cudaMemsetAsync(d_phi, 0, S * sizeof(double), h->stream));
-    std::vector<double> unset;
     if (compass_offset) HF_CK(cudaMemcpyAsync(d_off, compass_offset, S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     else {
-      unset.assign(S, 100.0);
+      std::vector<double> unset(S, 100.0);
       HF_CK(cudaMemcpyAsync(d_off, unset.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       HF_CK(cudaStreamSynchronize(h->stream));
     }
   }
-  if (segments) HF_CK(cudaMalloc(&d_segs, S * max_segs * 7 * sizeof(double)));
   FeatArgs a;
   a.x = h->d_x; a.y = h->d_y; a.range = h->d_range;
   a.lines = h->d_lines; a.n_lines = h->d_nlines; a.lines_stride = h->run_max_lines;
@@ -1052,7 +1066,6 @@ int ekf_hough_get_features(ekf_hough h, int n_scans, int n_points, const double*
   }
   HF_CK(cudaStreamSynchronize(h->stream));
 #undef HF_CK
-  cleanup();
   if (lines || n_lines) return ekf_hough_download(h, lines, lines ? max_lines : 0, n_lines, nullptr, nullptr);
   return EKF_OK;
 }

@@ -613,7 +613,7 @@ class HoughBatch:
                 "n_lines": n_lines, "peaks": peaks, "values": values, "grid": grid}
 
     def get_features(self, X, Y, R, cur_phi=None, offset=None, max_feats=32, want_compass=True, want_segments=False,
-                     max_segs=64, max_lines=64):
+                     max_segs=64, max_lines=64, want_lines=True):
         """FeatureDetector::getFeatures for a batch: -> dict(feats [S][max_feats][2], n_feats, compass, offset,
         lines, n_lines, segments, n_segs). cur_phi / offset: per-scan filter heading and COMPASS_OFFSET (100 = unset)."""
         X, Y, R = self._inputs(X, Y, R)
@@ -623,8 +623,8 @@ class HoughBatch:
         compass = np.zeros(S) if want_compass else None
         phi = np.ascontiguousarray(cur_phi, np.float64) if cur_phi is not None else None
         off = np.array(offset, np.float64, copy=True) if offset is not None else (np.full(S, 100.0) if want_compass else None)
-        lines = np.zeros((S, max_lines, 3))
-        n_lines = np.zeros(S, np.int32)
+        lines = np.zeros((S, max_lines, 3)) if want_lines else None
+        n_lines = np.zeros(S, np.int32) if want_lines else None
         segs = np.zeros((S, max_segs, 7)) if want_segments else None
         n_segs = np.zeros(S, np.int32)
         self._chk(self.L.ekf_hough_get_features(self.h, S, P, _dp(X), _dp(Y), R.ctypes.data_as(C.POINTER(C.c_uint32)),

@@ -326,6 +326,12 @@ def hough_leg(ekf, n_scans, hbm_peak, device, with_cpu=True):
     e2e_s = (time.perf_counter() - t0) / 5
     assert np.array_equal(pin[4].array, n_lines)
     got = {"lines": pin[3].array.copy(), "n_lines": pin[4].array.copy()}
+    # the whole front end (lines, segments, corners, structural compass), host arrays in, features out
+    feat = hb.get_features(pin[0].array, pin[1].array, pin[2].array, max_feats=16, want_lines=False)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        feat = hb.get_features(pin[0].array, pin[1].array, pin[2].array, max_feats=16, want_lines=False)
+    feat_s = (time.perf_counter() - t0) / 3
     hb.close()
     for pa in pin:
         pa.free()
@@ -336,6 +342,8 @@ def hough_leg(ekf, n_scans, hbm_peak, device, with_cpu=True):
            "e2e": {"value": n_scans / e2e_s, "unit": "scans/s", "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + R.nbytes),
                    "d2h_bytes_per_step": int(got["lines"].nbytes + got["n_lines"].nbytes)},
            "mean_lines_per_scan": float(n_lines.mean()),
+           "features_e2e": {"value": n_scans / feat_s, "unit": "scans/s", "mean_features_per_scan": float(feat["n_feats"].mean()),
+                            "what": "ekf_hough_get_features: Hough lines + fitLineSegments + extractCorners + getStructCompass"},
            "roofline": {"bound": "hbm", "kernel": "hough_scan_kernel + hough_lines_kernel", "achieved": alg / (ms / n * 1e-3) / 1e9, "peak": hbm_peak,
                         "unit": "GB/s", "frac": alg / (ms / n * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                         "note": "the accumulator (288 KB per scan) never leaves shared memory, so HBM traffic is 5 KB per scan "
