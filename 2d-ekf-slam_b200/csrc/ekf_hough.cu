@@ -41,7 +41,7 @@
 namespace {
 
 #ifndef EKF_HOUGH_PARTS
-#define EKF_HOUGH_PARTS 12
+#define EKF_HOUGH_PARTS 30
 #endif
 #ifndef EKF_HOUGH_THREADS
 #define EKF_HOUGH_THREADS 128
@@ -89,20 +89,27 @@ __device__ __forceinline__ void zero_acc(HoughSmem& sm, int t0, int nt) {
   for (int w = t0; w < ACC_WORDS_PAD; w += nt) sm.acc[w] = 0u;
 }
 
-// houghtransform.cpp:240-256 for the angles of one half
+// houghtransform.cpp:240-256 for the angles of one slice. A thread keeps one angle (its cos / sin
+// as doubles in registers) and walks every G-th reading; round() is spelled out (truncate, then
+// adjust by the exact fractional part: half away from zero, as round() does).
 __device__ __forceinline__ void vote(HoughSmem& sm, int part, int n_points, int t0, int nt) {
-  const int total = n_points * TPP;
-  for (int q = t0; q < total; q += nt) {
-    const int p = q / TPP, tl = q - p * TPP;
+  const int G = nt / TPP;
+  const int g = t0 / TPP, tl = t0 - g * TPP;
+  if (g >= G) return;
+  const int t = part * TPP + tl;
+  const double c = (double)sm.cs[t], s = (double)sm.sn[t];
+  unsigned int* row = sm.acc;
+  const int row0 = tl * RS + ADD;
+  for (int p = g; p < n_points; p += G) {
     if (!sm.valid[p]) continue;
-    const int t = part * TPP + tl;
-    const double rho = sm.px[p] * (double)sm.cs[t] + sm.py[p] * (double)sm.sn[t];
-    int r = (int)round(rho);
+    const double rho = sm.px[p] * c + sm.py[p] * s;
+    const double tr = trunc(rho);
+    const double fr = rho - tr;                      // exact
+    int r = (int)tr + (fr >= 0.5 ? 1 : 0) - (fr <= -0.5 ? 1 : 0);
     r /= EKF_HOUGH_DISTANCE;
-    r += ADD;
-    if ((unsigned)r < (unsigned)RS) {
-      const int b = tl * RS + r;
-      atomicAdd(&sm.acc[b >> 2], 1u << ((b & 3) * 8));
+    if ((unsigned)(r + ADD) < (unsigned)RS) {
+      const int b = row0 + r;
+      atomicAdd(&row[b >> 2], 1u << ((b & 3) * 8));
     }
   }
 }
