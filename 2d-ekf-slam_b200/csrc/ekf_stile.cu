@@ -191,12 +191,17 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
     int dropped = 0;
     {
       const int n_int = 4 + 2 * n_lm;
-      if (is_tile) {
-#pragma unroll 4
-        for (int e = 0; e < 32; ++e) {
-          const int r = 4 * I + (e & 3), c = 8 * J + (e >> 2);
-          const bool live = r != 3 && c != 3 && r < n_int && c < n_int;
-          Tt[e * NT] = live ? gP[ext_index(r) + (size_t)ext_index(c) * ld] : 0.0;
+      // Column by column (a warp per column, a lane per row): the HBM reads are contiguous runs and
+      // the scatter into the plane-major tiles is conflict-free. Column c of the stored triangle
+      // starts at row 8*(c/8) (its diagonal tile is stored whole); dead entries are zeroed.
+      for (int c = warp; c < C::NI; c += C::NW) {
+        const int rlo = c & ~7;
+        const bool col_live = c != 3 && c < n_int;
+        const double* gc = gP + (size_t)ext_index(c) * ld;
+        const int cb = 4 * (c & 7) * NT, cj = c >> 3;
+        for (int r = rlo + lane; r < C::NI; r += 32) {
+          const bool live = col_live && r != 3 && r < n_int;
+          T[((r & 3)) * NT + cb + tile_number<NB>(r >> 2, cj)] = live ? gc[ext_index(r)] : 0.0;
         }
       }
       for (int r = tid; r < C::NI; r += C::THREADS) sm.xs[r] = (r != 3 && r < n_int) ? gx[ext_index(r)] : 0.0;
@@ -560,15 +565,14 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
     // ---- write back to HBM (external layout, both triangles) -------------------------------------
     {
       const int n_int = 4 + 2 * n_lm;
-      if (is_tile) {
-#pragma unroll 4
-        for (int e = 0; e < 32; ++e) {
-          const int r = 4 * I + (e & 3), c = 8 * J + (e >> 2);
-          if (r != 3 && c != 3 && r < n_int && c <= r) {
-            const double v = Tt[e * NT];
-            gP[ext_index(r) + (size_t)ext_index(c) * ld] = v;
-            gP[ext_index(c) + (size_t)ext_index(r) * ld] = v;
-          }
+      // full columns of the external matrix, a warp per column and a lane per row (contiguous HBM
+      // writes); entries above the diagonal come from the mirrored position of the stored triangle
+      for (int c = warp; c < n_int; c += C::NW) {
+        if (c == 3) continue;
+        double* gc = gP + (size_t)ext_index(c) * ld;
+        for (int r = lane; r < n_int; r += 32) {
+          if (r == 3) continue;
+          gc[ext_index(r)] = T[pidx<NB>(r, c)];
         }
       }
       for (int r = tid; r < n_int; r += C::THREADS)
