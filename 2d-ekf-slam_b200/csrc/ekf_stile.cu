@@ -4,12 +4,14 @@
 // The north star's "one CTA per filter instance, covariance resident in shared memory", laid
 // out so that FOUR filters fit on an SM at once (N_cap <= 50): only the lower block triangle of
 // the (padded) covariance is stored, as NB(NB+1) tiles of 4x8 doubles in plane-major order
-// T[a + 4b][tile] (46.6 KB instead of 84.9 KB for the full matrix). Element (r, c), r >= c, lives
-// in tile (r/4, c/8); symmetric accesses swap indices. The O(n) phases read the entries they
-// need directly from this storage (no staging copies); the O(n^2) downdate is one thread per
-// tile: 32 conflict-free loads, 64 fma, 32 stores. Registers hold nothing across phases, so the
-// kernel runs at <= 80 registers per thread and occupancy is set by shared memory: with ~7000
-// cycles of dependent FP64 latency per filter-step, throughput is filters-in-flight per SM.
+// T[a + 4b][tile] (48.1 KB with the padded plane stride, instead of 84.9 KB for the full matrix).
+// Element (r, c), r >= c, lives in tile (r/4, c/8); symmetric accesses swap indices. The O(n)
+// phases read the entries they need directly from this storage (no staging copies); the O(n^2)
+// downdate is one thread per tile: 32 conflict-free loads, 64 fma, 32 stores. Registers hold
+// nothing across phases, so the kernel runs at 72 registers per thread (224 threads: six tile warps
+// and a helper warp) and four CTAs fill both the shared memory and the register file of an SM:
+// with ~8000 cycles of dependent FP64 latency per filter-step, throughput is filters-in-flight per SM.
+// The covariance enters and leaves shared memory column by column (contiguous HBM accesses).
 //
 // Internally the state is padded with one dummy entry after the robot pose
 // ([X,Y,Phi,pad,L1x,L1y,...]) so every landmark pair is 2-aligned and never straddles a tile;
@@ -17,16 +19,16 @@
 //
 // Phase structure per step (slam.cpp:130-182 order), same arithmetic as the other kernels
 // (ekf_small.cuh), bit-identical results:
-//   scalar chains   two spare lanes of the last warp share one sincos stream: odometry -> Q, Phi,
+//   scalar chains   two lanes of the helper warp share one sincos stream: odometry -> Q, Phi,
 //                   G, new pose (kalmanfilter.cpp:17-37, Propagate.cpp:33-48) and the rotation blocks
 //                   of the update (Update.cpp:89-95); they run during the previous step's downdate
-//   propagate       nine spare lanes do the 3x3 robot block (Propagate.cpp:53,66-67) and the q
+//   propagate       nine helper lanes do the 3x3 robot block (Propagate.cpp:53,66-67) and the q
 //                   partial sums; one thread per strip row applies Phi (Propagate.cpp:56-60)
 //   gating          Update.cpp:103-148, one landmark per lane on two warp groups in parallel
 //                   (A: H_R P_RR H_R^T + H_Li P_LiR H_R^T, B: the other two terms of S), REDUX
 //                   warp argmin, lowest index wins ties
 //   gain            one state row per thread: P H^T (before S^-1 is known), then K, x, W
-//                   (Update.cpp:186-187); S^-1 and L D L^T of S come from a spare lane meanwhile
+//                   (Update.cpp:186-187); S^-1 and L D L^T of S come from a helper lane meanwhile
 //   downdate        one tile per thread, P_tile += u_rows (x) W_cols (Update.cpp:188,193-194 in the
 //                   bit-symmetric form described in ekf_cta.cuh)
 #include "ekf_cta.cuh"
