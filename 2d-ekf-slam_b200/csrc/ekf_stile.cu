@@ -196,14 +196,31 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
       // Column by column (a warp per column, a lane per row): the HBM reads are contiguous runs and
       // the scatter into the plane-major tiles is conflict-free. Column c of the stored triangle
       // starts at row 8*(c/8) (its diagonal tile is stored whole); dead entries are zeroed.
-      for (int c = warp; c < C::NI; c += C::NW) {
-        const int rlo = c & ~7;
-        const bool col_live = c != 3 && c < n_int;
-        const double* gc = gP + (size_t)ext_index(c) * ld;
-        const int cb = 4 * (c & 7) * NT, cj = c >> 3;
-        for (int r = rlo + lane; r < C::NI; r += 32) {
-          const bool live = col_live && r != 3 && r < n_int;
-          T[((r & 3)) * NT + cb + tile_number<NB>(r >> 2, cj)] = live ? gc[ext_index(r)] : 0.0;
+      for (int c0 = warp; c0 < C::NI; c0 += 2 * C::NW) {        // two columns per pass: eight loads in flight per lane
+        double v[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = c0 + h * C::NW;
+          const bool col_live = c < C::NI && c != 3 && c < n_int;
+          const double* gc = gP + (size_t)ext_index(c < C::NI ? c : 0) * ld;
+          const int rlo = c & ~7;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = rlo + lane + 32 * k;
+            const bool live = col_live && r != 3 && r < n_int;
+            v[h][k] = live ? gc[ext_index(r)] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = c0 + h * C::NW;
+          if (c >= C::NI) continue;
+          const int rlo = c & ~7, cb = 4 * (c & 7) * NT, cj = c >> 3;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = rlo + lane + 32 * k;
+            if (r < C::NI) T[(r & 3) * NT + cb + tile_number<NB>(r >> 2, cj)] = v[h][k];
+          }
         }
       }
       for (int r = tid; r < C::NI; r += C::THREADS) sm.xs[r] = (r != 3 && r < n_int) ? gx[ext_index(r)] : 0.0;
