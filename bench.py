@@ -505,7 +505,10 @@ def main():
         line["large_map"] = legs
         line["roofline_hbm"] = dict(legs[-1]["roofline"], peak_source=hbm_src)
     if world == 1 and args.hough > 0:
-        line["hough"] = hough_leg(ekf, args.hough, hbm_peak, local, with_cpu=not args.no_cpu_baseline)
+        try:                                   # an auxiliary leg must never cost the headline line
+            line["hough"] = hough_leg(ekf, args.hough, hbm_peak, local, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:                 # noqa: BLE001
+            line["hough"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world == 1 and args.sharded_map:
         devs = [int(t) for t in args.shard_devices.split(",") if t.strip()] or list(range(ekf.device_count()))
         steps = 400 if int(args.sharded_map) <= 4000 else 60
