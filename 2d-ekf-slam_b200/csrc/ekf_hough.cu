@@ -672,15 +672,18 @@ __global__ void __launch_bounds__(kFeatWarps * 32) hough_features_kernel(const F
       cardinal -= 1.570796327 * floor(cardinal / 1.570796327);
       double phi = a.cur_phi ? a.cur_phi[s] : 0.0;
       phi -= 6.283185307 * floor(phi / 6.283185307);
-      const double e1 = fabs(phi - cardinal), e2 = fabs(phi - cardinal - 1.570796327);
-      const double e3 = fabs(phi - cardinal - 3.141592654), e4 = fabs(phi - cardinal - 4.71238898);
-      const double e5 = fabs(phi - cardinal - 6.283185307), e6 = fabs(phi - cardinal + 1.570796327);
-      if (e1 <= e2 && e1 <= e3 && e1 <= e4 && e1 <= e5 && e1 <= e6) result = cardinal;
-      else if (e2 <= e3 && e2 <= e4 && e2 <= e5 && e2 <= e6) result = cardinal + 1.570796327;
-      else if (e3 <= e4 && e3 <= e5 && e3 <= e6) result = cardinal + 3.141592654;
-      else if (e4 <= e5 && e4 <= e6) result = cardinal + 4.71238898;
-      else if (e5 <= e6) result = cardinal;
-      else result = cardinal + 4.71238898;
+      // six candidate errors (:346-351); the answer is the first candidate that is no worse than every
+      // later one (:356-361), candidates 5 and 6 being the roll-overs of 1 and 4
+      const double shift[5] = {0.0, 1.570796327, 3.141592654, 4.71238898, 6.283185307};
+      const double add[6] = {0.0, 1.570796327, 3.141592654, 4.71238898, 0.0, 4.71238898};
+      double err[6];
+      for (int k = 0; k < 5; ++k) err[k] = fabs((phi - cardinal) - shift[k]);
+      err[5] = fabs((phi - cardinal) + 1.570796327);
+      for (int k = 0; k < 6; ++k) {
+        bool best = true;
+        for (int j = k + 1; j < 6; ++j) best = best && err[k] <= err[j];
+        if (best) { result = add[k] == 0.0 ? cardinal : cardinal + add[k]; break; }
+      }
     }
     a.compass[s] = result;
   }

@@ -146,13 +146,17 @@ double features_oracle_compass(const double* lines, int n_lines, double cur_phi,
   cardinal -= *offset_io;
   cardinal -= 1.570796327 * floor(cardinal / 1.570796327);
   cur_phi -= 6.283185307 * floor(cur_phi / 6.283185307);
-  const double e1 = fabs(cur_phi - cardinal), e2 = fabs(cur_phi - cardinal - 1.570796327);
-  const double e3 = fabs(cur_phi - cardinal - 3.141592654), e4 = fabs(cur_phi - cardinal - 4.71238898);
-  const double e5 = fabs(cur_phi - cardinal - 6.283185307), e6 = fabs(cur_phi - cardinal + 1.570796327);
-  if (e1 <= e2 && e1 <= e3 && e1 <= e4 && e1 <= e5 && e1 <= e6) return cardinal;
-  if (e2 <= e3 && e2 <= e4 && e2 <= e5 && e2 <= e6) return cardinal + 1.570796327;
-  if (e3 <= e4 && e3 <= e5 && e3 <= e6) return cardinal + 3.141592654;
-  if (e4 <= e5 && e4 <= e6) return cardinal + 4.71238898;
-  if (e5 <= e6) return cardinal;
-  return cardinal + 4.71238898;
+  /* :346-361: six candidate errors; the result is the first candidate that is no worse than every
+   * LATER one (earlier ones are not compared again), candidates 5 and 6 standing for the roll-overs */
+  static const double shift[5] = {0.0, 1.570796327, 3.141592654, 4.71238898, 6.283185307};
+  static const double add[6] = {0.0, 1.570796327, 3.141592654, 4.71238898, 0.0, 4.71238898};
+  double err[6];
+  for (int k = 0; k < 5; ++k) err[k] = fabs((cur_phi - cardinal) - shift[k]);
+  err[5] = fabs((cur_phi - cardinal) + 1.570796327);
+  for (int k = 0; k < 6; ++k) {
+    int best = 1;
+    for (int j = k + 1; j < 6; ++j) best = best && err[k] <= err[j];
+    if (best) return add[k] == 0.0 ? cardinal : cardinal + add[k];
+  }
+  return cardinal;   /* not reached: k = 5 always qualifies */
 }
