@@ -75,3 +75,28 @@ def test_log_files_match_the_reference_formats(ekf, ref, tmp_path):
                 assert abs(float(va) - float(vb)) <= 2e-6 * max(abs(float(vb)), 1e-30), (name, la, lb)
             diff += 1
         assert diff <= len(b) // 100, "%s: %d of %d lines differ in the last printed digit" % (name, diff, len(b))
+
+
+def test_hough_example_through_the_c_header(tmp_path):
+    """examples/hough_synthetic.cpp: include/ekf_hough_b200.h from plain C++, a room corner 3 m ahead
+    and 2.5 m to the left must come out as a corner feature near (3000, 2500) rotated by the turn."""
+    exe = str(tmp_path / "hough_synthetic")
+    lib = os.path.join(ROOT, "2d-ekf-slam_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "hough_synthetic.cpp"), "-L" + lib, "-lekf_slam_b200",
+                    "-Wl,-rpath," + lib, "-o", exe], check=True)
+    out = subprocess.run([exe, "4"], stdout=subprocess.PIPE, text=True, check=True).stdout.strip().split("\n")
+    scans = [ln for ln in out if ln.startswith("scan")]
+    assert len(scans) == 4
+    found = 0
+    s = -1
+    for ln in out:
+        if ln.startswith("scan"):
+            s += 1
+            continue
+        fx, fy = (float(v) for v in ln.split()[1:])
+        t = np.deg2rad(5.0 * s)
+        cx, cy = 3000 * np.cos(t) + 2500 * np.sin(t), -3000 * np.sin(t) + 2500 * np.cos(t)   # the corner in the robot frame
+        if np.hypot(fx - cx, fy - cy) < 60:
+            found += 1
+    assert found >= 3, out
