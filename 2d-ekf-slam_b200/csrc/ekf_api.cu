@@ -101,18 +101,21 @@ int check_status(ekf_handle h) {
 }
 
 // Which fused kernel a batch-regime run uses: 1 = shared-memory full matrix, 2 = register tiles,
-// 3 = shared-memory tiled triangle.
+// 3 = shared-memory tiled triangle, 4 = tiled triangle with the deferred downdate.
 int pick_batch_kernel(ekf_handle h) {
   const int want = h->cfg.batch_kernel;
   const int cap = h->st.cap_lm;
   if (want == EKF_BATCH_KERNEL_SMEM) return 1;
   if (want == EKF_BATCH_KERNEL_TILE) return cap <= ekf_tile_max_landmarks() ? 2 : -1;
   if (want == EKF_BATCH_KERNEL_STILE) return cap <= ekf_stile_max_landmarks() ? 3 : -1;
+  if (want == EKF_BATCH_KERNEL_DTILE) return cap <= ekf_dtile_max_landmarks() ? 4 : -1;
+  if (cap <= ekf_dtile_max_landmarks()) return 4;
   if (cap <= ekf_stile_max_landmarks()) return 3;
   return 1;
 }
 
 cudaError_t launch_batch_kernel(ekf_handle h, int kern, const EkfState& st, const EkfRunIO& io) {
+  if (kern == 4) return ekf_dtile_run(st, io, h->k, h->sm_count, h->stream);
   if (kern == 3) return ekf_stile_run(st, io, h->k, h->sm_count, h->stream);
   if (kern == 2) return ekf_tile_run(st, io, h->k, h->sm_count, h->stream);
   return ekf_batch_run(st, io, h->k, h->grid_cap, h->stream);
@@ -151,7 +154,7 @@ int launch_run(ekf_handle h, bool want_trace, bool want_pose) {
   if (h->regime == EKF_REGIME_BATCH) {
     const int kern = pick_batch_kernel(h);
     if (kern < 0)
-      return fail(h, EKF_ERR_UNSUPPORTED, "the tiled fused kernels support max_landmarks <= " + std::to_string(ekf_tile_max_landmarks()));
+      return fail(h, EKF_ERR_UNSUPPORTED, "the requested fused kernel does not support max_landmarks = " + std::to_string(h->st.cap_lm) + " (TILE / STILE: <= " + std::to_string(ekf_tile_max_landmarks()) + ", DTILE: <= " + std::to_string(ekf_dtile_max_landmarks()) + ")");
     kernel_event_begin(h);
     EKF_CK(h, launch_batch_kernel(h, kern, h->st, io));
     kernel_event_end(h);
@@ -358,7 +361,7 @@ int ekf_n_filters(ekf_handle h) { return h ? h->st.F : 0; }
 int ekf_max_landmarks(ekf_handle h) { return h ? h->st.cap_lm : 0; }
 int ekf_regime(ekf_handle h) { return h ? h->regime : 0; }
 int ekf_set_batch_kernel(ekf_handle h, int batch_kernel) {
-  if (!h || batch_kernel < EKF_BATCH_KERNEL_AUTO || batch_kernel > EKF_BATCH_KERNEL_STILE) return EKF_ERR_BAD_ARG;
+  if (!h || batch_kernel < EKF_BATCH_KERNEL_AUTO || batch_kernel > EKF_BATCH_KERNEL_DTILE) return EKF_ERR_BAD_ARG;
   h->cfg.batch_kernel = batch_kernel;
   return EKF_OK;
 }
@@ -577,10 +580,11 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
   if (want_pose) EKF_CK(h, h->t_pose.reserve(FT * 3));
   const int kern = pick_batch_kernel(h);
   if (kern < 0)
-    return fail(h, EKF_ERR_UNSUPPORTED, "the tiled fused kernels support max_landmarks <= " + std::to_string(ekf_tile_max_landmarks()));
+    return fail(h, EKF_ERR_UNSUPPORTED, "the requested fused kernel does not support max_landmarks = " + std::to_string(h->st.cap_lm) + " (TILE / STILE: <= " + std::to_string(ekf_tile_max_landmarks()) + ", DTILE: <= " + std::to_string(ekf_dtile_max_landmarks()) + ")");
   // chunk = a multiple of the co-resident CTA count (2 filters per CTA), at most kMaxChunks chunks
-  const size_t wave = (size_t)(kern == 3 ? ekf_stile_ctas_per_sm(st.cap_lm) * h->sm_count
-                                         : (kern == 2 ? 2 * h->sm_count : h->grid_cap));
+  const size_t wave = (size_t)(kern == 4 ? ekf_dtile_ctas_per_sm() * h->sm_count
+                               : kern == 3 ? ekf_stile_ctas_per_sm(st.cap_lm) * h->sm_count
+                                           : (kern == 2 ? 2 * h->sm_count : h->grid_cap));
   size_t chunk = 2 * wave;
   while ((F + chunk - 1) / chunk > (size_t)kMaxChunks) chunk += wave;
   const int n_chunks = (int)((F + chunk - 1) / chunk);

@@ -1,0 +1,957 @@
+// ekf_dtile.cu — regime A, fused multi-step kernel with a DEFERRED covariance downdate (sm_100a).
+// One CTA (128 threads = one warp per SM sub-partition) per filter, persistent over filters, four
+// CTAs per SM, T steps with the covariance resident in shared memory.
+//
+// What is different from ekf_stile.cu (same arithmetic, bit-identical results):
+//
+//  * Deferred downdate. The landmark-landmark block P_LL is only MODIFIED by the rank-2 downdates
+//    (Update.cpp:188,193-194) and only READ when one of the two landmarks is the associated one
+//    (the two gain columns of Update.cpp:186) - the gating loop (Update.cpp:103-148) needs just the
+//    robot strip P_LR, P_RR and the 2x2 diagonal blocks. So P_LL is kept as "stored tiles + up to
+//    KH pending rank-2 updates": each Old update appends its downdate vector W to a history in
+//    shared memory, the strip / P_RR / diagonal blocks are updated eagerly (O(n)), the two gain
+//    columns are corrected on the fly when read, and the tiles are swept once per KH updates,
+//    applying the pending updates to every element in order. Every element sees the same fma
+//    sequence as with an immediate sweep, so the bits are the same; the O(n^2) shared-memory
+//    traffic per update drops by KH.
+//  * Storage. Pose, P_RR (3x3), strip SR (3 x 2N), the 2x2 diagonal blocks Dd and the 2x2 block
+//    between the two landmarks of an aligned pair Do live in small arrays ("eager" entries). The
+//    rest of the lower triangle of P_LL lives in 4x12 tiles (row blocks of 4, column blocks of 12;
+//    tile (I,J) exists for I >= 3J+1), plane-major T[(a+4b)*PS + b + slot]: a sweep thread owns one
+//    tile (conflict-free for any plane), the column walk of the gain phase (consecutive rows) and
+//    the row walk (consecutive columns) both spread over the banks (PS = 12 mod 16 and the +b skew).
+//    108 tiles for 50 landmarks: four warps sweep them, one tile per lane.
+//  * Gating on one warp, exact on demand. The "front" warp gates two landmarks per lane with a
+//    fused (fma, symmetric) evaluation of S, the condition gate and the Mahalanobis distance plus a
+//    running bound of its own rounding error, which proves for all but a few landmarks (normally
+//    all but one) that they cannot be the argmin / are definitely kept or skipped. The survivors
+//    are re-evaluated in the reference's exact operation order, four lanes per landmark (one
+//    element of S each, ekf_gate_S_element), and the decision, S, residual and H_R come from that
+//    exact evaluation - so decisions and everything downstream carry the reference's bits.
+//  * Roles rotate with the CTA's slot on its SM (front warp, helper warp), so the four CTAs of an
+//    SM load the four FP64 pipes evenly.
+//
+// Phase structure per step (slam.cpp:130-182 order):
+//   helper warp   sincos of the two headings, odometry -> Q, Phi, G, new pose (kalmanfilter.cpp:17-37,
+//                 Propagate.cpp:33-48), P_RR <- Phi P_RR Phi^T + G Q G^T (Propagate.cpp:53,66-67),
+//                 the landmark-independent part of the update (Update.cpp:89-95); runs during the
+//                 previous step's gain phase
+//   row threads   strip <- Phi * strip (Propagate.cpp:56-60)
+//   front warp    gating, decision (Update.cpp:103-152,181,191), S^-1, L D L^T, the pose rows of
+//                 the gain and the pose correction
+//   row threads   gain column correction, K, x, W (Update.cpp:186-187), eager downdate of strip and
+//                 diagonal blocks; every KH-th update all warps sweep the tiles
+#include "ekf_cta.cuh"
+#include "ekf_internal.h"
+
+namespace {
+
+constexpr int KH = 4;            // pending downdates between two sweeps of the tiles
+constexpr int DT_THREADS = 128;
+
+#ifdef EKF_DTILE_TIMING
+__device__ long long g_dtile_ts[4][16];
+#define DTILE_TS(kk)                                                                              \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && f == 0 && t == 501 && (threadIdx.x & 31) == 0) g_dtile_ts[threadIdx.x >> 5][kk] = clock64(); \
+  } while (0)
+#else
+#define DTILE_TS(kk) do { } while (0)
+#endif
+
+__device__ int g_sm_slot[1024];   // CTAs started per SM so far (role rotation)
+
+template <int RB>                // RB row blocks of 4 rows = 2*RB landmarks
+struct DCfg {
+  static constexpr int NQ = 4 * RB;                   // rows / columns of P_LL
+  static constexpr int NL = 2 * RB;                   // landmark capacity
+  static constexpr int NP = RB;                       // aligned landmark pairs
+  static constexpr int NJ = (RB - 2) / 3 + 1;         // column blocks that own tiles
+  static constexpr int NT = NJ * (RB - 1) - 3 * NJ * (NJ - 1) / 2;   // tiles
+  static constexpr int PS = NT + ((4 - NT % 8) + 8) % 8;   // plane stride: NT rounded up to 4 or 12 (mod 16)
+  static constexpr int TSIZE = 47 * PS + 11 + NT;     // doubles of tile storage (48 planes, skew b)
+  static_assert(PS % 16 == 4 || PS % 16 == 12, "plane stride must be 4 or 12 (mod 16)");
+  static_assert(NT <= DT_THREADS, "one tile per thread");
+  static_assert(NQ + 3 <= DT_THREADS, "one state row per thread");
+  static_assert(NL <= 64, "two landmarks per gating lane");
+};
+
+template <int RB>
+__device__ __forceinline__ int dt_slot(int I, int J) { return J * (RB - 1) - 3 * J * (J - 1) / 2 + I - 3 * J - 1; }
+// storage index of P_LL(r, c), r > c, r and c in different aligned pairs
+template <int RB>
+__device__ __forceinline__ int dt_addr(int r, int c) {
+  const int J = (c * 43) >> 9;            // c / 12 for c < 128
+  const int b = c - 12 * J;
+  return ((r & 3) + 4 * b) * DCfg<RB>::PS + b + dt_slot<RB>(r >> 2, J);
+}
+
+struct DDec {                    // what the front warp publishes for the row threads / the helper
+  int decision, c0, pad0, pad1;  // c0 = first P_LL row of the associated landmark
+  double h3[2], res[2], Si[4];
+  double Ct[4], mCt[4];          // H_Li and the first two columns of H_R of THIS update (sm.upd is rewritten early)
+  double l, sq0, sq1;
+  unsigned sm0, sm1;             // sign-bit masks of the downdate (u = mask ^ W)
+  double2 WR[3];                 // downdate vectors of the three pose rows
+  double nl[2], h3n[2], PLL[4];  // New branch
+  double cres, cS;               // compass
+};
+
+template <int RB>
+struct DSmem {
+  using C = DCfg<RB>;
+  double2 H[KH][C::NQ];          // pending downdate vectors
+  double SR[3][C::NQ];           // strip: SR[j][q] = P(3+q, j)
+  double Dd[3][C::NL];           // P(2l,2l), P(2l+1,2l), P(2l+1,2l+1)
+  double Do[4][C::NP];           // Do[i+2j][m] = P(4m+2+i, 4m+j)
+  double xl[C::NQ];              // landmark part of the state
+  double xr[4];                  // pose
+  double PRR[9];                 // column-major, both triangles
+  double PhiS[9], GS[6];
+  PropSetup prop;
+  UpdateSetup upd;
+  DDec dec;
+  unsigned hs0[KH], hs1[KH];     // sign masks of the pending updates
+  int hrank[KH];                 // 2, or 1 for a compass update
+  int list[64];                  // landmarks the exact pass has to visit
+};
+
+struct DRunArgs {
+  EkfState st;
+  EkfRunIO io;
+  EkfConst k;
+};
+
+__device__ __forceinline__ uint32_t dt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dt_cp_async8(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dt_smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void dt_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ double dt_flip(double v, unsigned mask) {
+  return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+}
+__device__ __forceinline__ double dt_rcp_fast(double d) {   // ~1e-16 relative for normal d; screen only
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+// order-preserving 64-bit key of a double (total order, -0 < +0, NaNs at the ends)
+__device__ __forceinline__ unsigned long long dt_key(double v) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned long long dt_warp_min_key(unsigned long long key) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+
+// ---- the screen: fused evaluation of one landmark-loop iteration with an error bound -----------
+// Mathematically the same quantities as Update.cpp:108-136 (S symmetric, so three entries), evaluated
+// with fma and with the landmark-independent products hoisted; NOT the reference's rounding. It is
+// only used to prove statements that hold for the exact values too:
+//   state 1  "cond >= cond_max for sure"      (skipped by Update.cpp:131)
+//   state 0  "cond <  cond_max for sure", and the exact Mahalanobis distance lies in [tlo, thi]
+//   state 2  anything else (not provable: NaN / inf, near the condition threshold, heavy
+//            cancellation) - the exact evaluation decides.
+// Error model: every entry of S is a sum of at most 13 products h*p*h' (|h| <= hmax = 3+|h3_0|+|h3_1|
+// bounds a row sum of |H|, |p| <= pmax) plus R, evaluated with <= 16 roundings, and the exact path's
+// own roundings are bounded the same way: |dS| <= EPSB*(hmax^2*pmax + rmax) with EPSB = 64*2^-53
+// covers both with a factor of two to spare. With ninv >= ||S^-1||: the relative error of the quadratic
+// form is <= rho = |dS|*ninv (first order; rho <= 2^-24 is required, so second order is < 2^-48), the
+// relative error of cond <= 2*rho, and the residual's rounding dr <= EPSB*(|z|+2|d|) moves the form by
+// <= ninv*dr*(2|r|+dr).
+struct ScreenU {
+  double c, s, x0, x1, z0, z1, R00, R01, R11;
+  double U0[3], U1[3], p2[3];
+  double klo, khi, zsum, rmax;
+  unsigned prr_hi;
+  bool cond_ok;
+};
+
+__device__ __forceinline__ void dt_screen_setup(ScreenU& w, const UpdateSetup& u, double cond_max) {
+  w.c = u.c; w.s = u.s; w.x0 = u.x0; w.x1 = u.x1; w.z0 = u.z0; w.z1 = u.z1;
+  w.R00 = u.R[0]; w.R01 = 0.5 * (u.R[1] + u.R[2]); w.R11 = u.R[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    // columns 0,1 of H_R are (-c, s) and (-s, -c): U_a = P_RR(:,0)*H_R(a,0) + P_RR(:,1)*H_R(a,1)
+    w.U0[j] = fma(u.PRR[j + 3], -u.s, u.PRR[j] * -u.c);
+    w.U1[j] = fma(u.PRR[j + 3], -u.c, u.PRR[j] * u.s);
+    w.p2[j] = u.PRR[j + 6];
+  }
+  const double kap = cond_max + 1.0 / cond_max;       // cond + 1/cond is increasing for cond >= 1
+  w.klo = kap * (1.0 - 0x1p-16);
+  w.khi = kap * (1.0 + 0x1p-16);
+  w.cond_ok = cond_max > 1.0;
+  w.zsum = fabs(u.z0) + fabs(u.z1);
+  w.rmax = fmax(fmax(fabs(u.R[0]), fabs(u.R[3])), fmax(fabs(u.R[1]), fabs(u.R[2])));
+  unsigned m = 0;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) m = max(m, (unsigned)__double2hiint(u.PRR[q]) & 0x7fffffffu);
+  w.prr_hi = m;
+}
+
+// sr[r + 2j] = P(Li + r, j); dd = {P(Li,Li), P(Li+1,Li), P(Li+1,Li+1)}
+__device__ __forceinline__ void dt_screen(const ScreenU& w, double lx, double ly, const double* sr, const double* dd,
+                                          double& tlo, double& thi, int& state) {
+  const double c = w.c, s = w.s;
+  const double d0 = lx - w.x0, d1 = ly - w.x1;
+  const double zh0 = fma(c, d0, s * d1), zh1 = fma(c, d1, -(s * d0));
+  const double r0 = w.z0 - zh0, r1 = w.z1 - zh1;
+  const double h30 = zh1, h31 = -zh0;               // -C^T J d = (zh1, -zh0)
+  double GR0[3], GR1[3];                            // (P_RR H_R^T + P_RL H_L^T)(:, a)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    GR0[j] = fma(sr[1 + 2 * j], s, fma(sr[2 * j], c, fma(w.p2[j], h30, w.U0[j])));
+    GR1[j] = fma(sr[1 + 2 * j], c, fma(sr[2 * j], -s, fma(w.p2[j], h31, w.U1[j])));
+  }
+  double GL0[2], GL1[2];                            // (P_LR H_R^T + P_LL H_L^T)(r, a)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const double pl0 = r ? dd[1] : dd[0], pl1 = r ? dd[2] : dd[1];
+    GL0[r] = fma(pl1, s, fma(pl0, c, fma(sr[r + 4], h30, fma(sr[r + 2], -s, sr[r] * -c))));
+    GL1[r] = fma(pl1, c, fma(pl0, -s, fma(sr[r + 4], h31, fma(sr[r + 2], -c, sr[r] * s))));
+  }
+  const double S00 = fma(s, GL0[1], fma(c, GL0[0], fma(h30, GR0[2], fma(-s, GR0[1], fma(-c, GR0[0], w.R00)))));
+  const double S01 = fma(s, GL1[1], fma(c, GL1[0], fma(h30, GR1[2], fma(-s, GR1[1], fma(-c, GR1[0], w.R01)))));
+  const double S11 = fma(c, GL1[1], fma(-s, GL1[0], fma(h31, GR1[2], fma(-c, GR1[1], fma(s, GR1[0], w.R11)))));
+  const double b2 = S01 * S01;
+  const double det = fma(S00, S11, -b2);
+  const double fro = fma(S00, S00, fma(S11, S11, b2 + b2));     // sigma1^2 + sigma2^2; |det| = sigma1*sigma2
+  const double adet = fabs(det);
+  const double yinv = dt_rcp_fast(det);
+  const double num = fma(S11 * r0, r0, fma(S00 * r1, r1, -2.0 * (S01 * r0) * r1));
+  const double tt = num * yinv;
+  // error bound
+  unsigned m = w.prr_hi;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) m = max(m, (unsigned)__double2hiint(sr[q]) & 0x7fffffffu);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) m = max(m, (unsigned)__double2hiint(dd[q]) & 0x7fffffffu);
+  const double pmax = __hiloint2double((int)((m + 0x00100000u) & 0x7ff00000u), 0);   // power of two >= every |P| entry used
+  constexpr double EPSB = 0x1p-47;
+  const double hmax = 3.0 + fabs(h30) + fabs(h31);
+  const double dS = EPSB * fma(hmax * hmax, pmax, w.rmax);
+  const double ninv = (fabs(S00) + fabs(S11) + 2.0 * fabs(S01)) * fabs(yinv);
+  const double rho = dS * ninv;
+  const double dr = EPSB * (w.zsum + 2.0 * (fabs(d0) + fabs(d1)));
+  const double err = fma(fabs(tt), 4.0 * rho, ninv * dr * (2.0 * (fabs(r0) + fabs(r1)) + dr)) + 0x1p-40 * fabs(tt);
+  const bool sane = rho <= 0x1p-24 && err < INFINITY && tt == tt && w.cond_ok;   // false for any NaN
+  const bool keep = sane && fro < w.klo * adet;
+  const bool skip = sane && fro > w.khi * adet;
+  state = skip ? 1 : (keep ? 0 : 2);
+  tlo = keep ? tt - err : -INFINITY;
+  thi = keep ? tt + err : INFINITY;
+}
+
+// ---- tile sweep: apply the pending downdates to this thread's tile, in order ---------------------
+template <int RB>
+__device__ __forceinline__ void dt_sweep_tile(double* __restrict__ Tt, const DSmem<RB>& sm, int I, int J, int npend) {
+  constexpr int PS = DCfg<RB>::PS;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    double t[4][6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) t[a][b] = Tt[(a + 4 * (b + 6 * half)) * PS + (b + 6 * half)];
+#pragma unroll 1
+    for (int p = 0; p < npend; ++p) {
+      const double2* W = sm.H[p];
+      const unsigned s0 = sm.hs0[p], s1 = sm.hs1[p];
+      const bool rank2 = sm.hrank[p] == 2;
+      double u0[4], u1[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double2 wi = W[4 * I + a];
+        u0[a] = dt_flip(wi.x, s0);
+        u1[a] = dt_flip(wi.y, s1);
+      }
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const double2 wj = W[12 * J + 6 * half + b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          double v = t[a][b];
+          if (rank2) v = fma(u1[a], wj.y, v);
+          v = fma(u0[a], wj.x, v);
+          t[a][b] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 6; ++b)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) Tt[(a + 4 * (b + 6 * half)) * PS + (b + 6 * half)] = t[a][b];
+  }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DRunArgs a) {
+  using C = DCfg<RB>;
+  constexpr int PS = C::PS, NQ = C::NQ;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DSmem<RB>& sm = *reinterpret_cast<DSmem<RB>*>(smem_raw);
+  double* T = reinterpret_cast<double*>(smem_raw + ((sizeof(DSmem<RB>) + 15) & ~(size_t)15));
+  double* recbuf = T + ((C::TSIZE + 1) & ~1);                                                  // [2][Lp]
+  __shared__ int s_rot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_rot = atomicAdd(&g_sm_slot[smid & 1023], 1) & 3;
+  }
+  __syncthreads();
+  const int rot = s_rot;
+  const bool front = warp == rot;                    // gating / decision warp
+  const bool helper = warp == ((rot + 2) & 3);       // scalar chains / P_RR warp
+  const bool is_tile = tid < C::NT;
+  int I = 0, J = 0;
+  if (is_tile) {                                     // inverse of dt_slot
+    int s = tid;
+    while (s >= RB - 1 - 3 * J) { s -= RB - 1 - 3 * J; ++J; }
+    I = 3 * J + 1 + s;
+  }
+  double* Tt = T + tid;                              // this thread's tile
+  const int q = tid;                                 // this thread's P_LL row (tid < NQ)
+  const int ld = a.st.ld, L = a.io.L, T_steps = a.io.T, M = a.io.M;
+  const int Lp = (L + 1) & ~1;
+  const EkfConst& k = a.k;
+  const int cap_lm = a.st.cap_lm < C::NL ? a.st.cap_lm : C::NL;
+
+  // storage of P_LL(r, c), r >= c
+  auto pll_ref = [&](int r, int c) -> double* {
+    if ((r >> 1) == (c >> 1)) return &sm.Dd[(r & 1) + (c & 1)][r >> 1];
+    if ((r >> 2) == (c >> 2)) return &sm.Do[(r & 1) + 2 * (c & 1)][r >> 2];
+    return T + dt_addr<RB>(r, c);
+  };
+
+  for (int f = blockIdx.x; f < a.st.F; f += gridDim.x) {
+    double* gP = a.st.P + (size_t)f * a.st.slab;
+    double* gx = a.st.x + (size_t)f * a.st.xs;
+    const double* grec = a.io.records + (size_t)f * T_steps * L;
+    int n_lm = a.st.nlm[f];
+    int npend = 0;
+    int dropped = 0;
+    // ---- load: HBM (external layout, lower triangle, column by column) -> shared memory ------------
+    {
+      const int n = 3 + 2 * n_lm;
+      for (int i = tid; i < C::TSIZE; i += DT_THREADS) T[i] = 0.0;
+      for (int i = tid; i < 3 * NQ; i += DT_THREADS) (&sm.SR[0][0])[i] = 0.0;
+      for (int i = tid; i < 3 * C::NL; i += DT_THREADS) (&sm.Dd[0][0])[i] = 0.0;
+      for (int i = tid; i < 4 * C::NP; i += DT_THREADS) (&sm.Do[0][0])[i] = 0.0;
+      if (tid < NQ) sm.xl[tid] = tid < 2 * n_lm ? gx[3 + tid] : 0.0;
+      if (tid < 3) sm.xr[tid] = gx[tid];
+      for (int i = tid; i < L; i += DT_THREADS) dt_cp_async8(recbuf + i, grec + i);
+      __syncthreads();
+      for (int c = warp; c < n; c += DT_THREADS / 32) {
+        const double* gc = gP + (size_t)c * ld;
+        for (int r = c + lane; r < n; r += 32) {
+          const double v = gc[r];
+          if (c < 3) {
+            if (r < 3) { sm.PRR[r + 3 * c] = v; sm.PRR[c + 3 * r] = v; }
+            else sm.SR[c][r - 3] = v;
+          } else {
+            *pll_ref(r - 3, c - 3) = v;
+          }
+        }
+      }
+      dt_cp_async_wait_all();
+    }
+    __syncthreads();
+
+    // ---- helper warp: everything of a step that does not depend on the landmarks -------------------
+    // Reads the pose / P_RR left by the previous update, applies the eager downdate of P_RR if that was
+    // an Old update (or compass), then doPropagation's scalars, the propagated pose and P_RR, and the
+    // landmark-independent part of the first measurement's update.
+    auto prr_eager = [&](int slot) {               // lanes 0..8: P_RR(i,j) += u_i . W_j of pending update `slot`
+      if (lane < 9) {
+        const int i = lane % 3, j = lane / 3;
+        const double2 wi = sm.dec.WR[i], wj = sm.dec.WR[j];
+        double v = sm.PRR[i + 3 * j];
+        if (sm.hrank[slot] == 2) v = fma(dt_flip(wi.y, sm.hs1[slot]), wj.y, v);
+        v = fma(dt_flip(wi.x, sm.hs0[slot]), wj.x, v);
+        sm.PRR[i + 3 * j] = v;
+      }
+      __syncwarp();
+    };
+    auto helper_chain = [&](const double* rec) {
+      if (lane < 2) {
+        const double RTV = rec[1] * k.deg2rad_pi / 180.0;
+        const double phi = lane == 0 ? sm.xr[2] : sm.xr[2] + rec[2] * RTV;   // same expression as the pose update
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        if (lane == 0) {
+          PropSetup ps;
+          ekf_build_prop_sc(ps, rec[0], rec[1], rec[2], sn, cs, k);
+          sm.prop = ps;
+          sm.PhiS[0] = 1.0; sm.PhiS[1] = 0.0; sm.PhiS[2] = 0.0;           // Propagate.cpp:42-44
+          sm.PhiS[3] = 0.0; sm.PhiS[4] = 1.0; sm.PhiS[5] = 0.0;
+          sm.PhiS[6] = ps.phi02; sm.PhiS[7] = ps.phi12; sm.PhiS[8] = 1.0;
+          sm.GS[0] = ps.g00; sm.GS[1] = ps.g10; sm.GS[2] = 0.0;            // :46-48
+          sm.GS[3] = 0.0; sm.GS[4] = 0.0; sm.GS[5] = ps.g21;
+          const double xm0 = ps.v * ps.c, xm1 = ps.v * ps.s, xm2 = ps.w;   // Propagate.cpp:33-37
+          const double n0 = sm.xr[0] + ps.dt * xm0, n1 = sm.xr[1] + ps.dt * xm1, n2 = sm.xr[2] + ps.dt * xm2;
+          sm.xr[0] = n0; sm.xr[1] = n1; sm.xr[2] = n2;
+          sm.upd.x0 = n0; sm.upd.x1 = n1;
+        } else {
+          UpdateTrig tg;
+          ekf_build_trig_sc(tg, sn, cs);
+          UpdateSetup& u = sm.upd;
+          u.c = tg.c; u.s = tg.s;
+          for (int w = 0; w < 4; ++w) { u.Ct[w] = tg.Ct[w]; u.mCt[w] = tg.mCt[w]; u.mCtJ[w] = tg.mCtJ[w]; }
+          if ((int)rec[5] > 0) {
+            u.z0 = rec[8]; u.z1 = rec[9];
+            for (int w = 0; w < 4; ++w) u.R[w] = rec[10 + w];
+          }
+        }
+      }
+      __syncwarp();
+      {
+        // 3x3 robot block, one element per lane (Propagate.cpp:53, then :66-67)
+        const int e = lane % 9, i = e % 3, j = e / 3;
+        double PRR[9];
+#pragma unroll
+        for (int w = 0; w < 9; ++w) PRR[w] = sm.PRR[w];
+        const double mij = ekf_prop_prr_elem(sm.PhiS, sm.GS, sm.prop.Q, PRR, i, j);
+        const double mji = __shfl_sync(0xffffffffu, mij, j + 3 * i);
+        const double pn = 0.5 * (mij + mji);
+        const int qe = e % 6, qi = qe % 2, qj = qe / 2;
+        const double p0j = __shfl_sync(0xffffffffu, pn, 0 + 3 * qj);
+        const double p1j = __shfl_sync(0xffffffffu, pn, 1 + 3 * qj);
+        const double qv = sm.upd.mCt[qi] * p0j + sm.upd.mCt[qi + 2] * p1j;
+        __syncwarp();
+        if (lane < 9) {
+          sm.PRR[e] = pn;
+          sm.upd.PRR[e] = pn;
+          if (e < 6) sm.upd.q[qe] = qv;
+        }
+      }
+    };
+    if (helper) helper_chain(recbuf);
+    bool setup_valid = true;
+
+    for (int t = 0; t < T_steps; ++t) {
+      const double* cur = recbuf + (size_t)(t & 1) * Lp;
+      if (t + 1 < T_steps) {
+        const double* g = grec + (size_t)(t + 1) * L;
+        double* nxt = recbuf + (size_t)((t + 1) & 1) * Lp;
+        for (int i = tid; i < L; i += DT_THREADS) dt_cp_async8(nxt + i, g + i);
+      }
+      const int nz = (int)cur[5] < M ? (int)cur[5] : M;
+      DTILE_TS(0);
+      __syncthreads();                                   // B1: helper results of this step visible
+      // ---- doPropagation, strip part (Propagate.cpp:56-60) ------------------------------------------
+      if (q < 2 * n_lm) {
+        double a0 = sm.SR[0][q], a1 = sm.SR[1][q], a2 = sm.SR[2][q];
+        ekf_prop_col(sm.prop, a0, a1, a2);
+        sm.SR[0][q] = a0; sm.SR[1][q] = a1; sm.SR[2][q] = a2;
+      }
+      bool next_ready = false;                           // helper chain of step t+1 already issued
+      // ---- doUpdateCompass (slam.cpp:144-147, kalmanfilter.cpp:96-130): a rank-1 pending update -----
+      if (cur[6] != 0.0) {
+        if (tid == 0) {
+          sm.dec.cres = ekf_compass_residual(sm.xr[2], cur[3], k);
+          sm.dec.cS = sm.PRR[8] + cur[4];
+          sm.hs0[npend] = sm.dec.cS < 0 ? 0u : 0x80000000u;
+          sm.hs1[npend] = 0u;
+          sm.hrank[npend] = 1;
+        }
+        __syncthreads();
+        {
+          const double res = sm.dec.cres, S = sm.dec.cS, invS = 1 / S, sq = sqrt(fabs(S));
+          if (tid < NQ) {
+            double2 w = make_double2(0.0, 0.0);
+            if (q < 2 * n_lm) {
+              const double Ki = invS * sm.SR[2][q];
+              sm.xl[q] = sm.xl[q] + res * Ki;
+              w = make_double2(sq * Ki, 0.0);
+            }
+            sm.H[npend][q] = w;
+          } else if (tid < NQ + 3) {
+            const int r = tid - NQ;
+            const double Ki = invS * sm.PRR[r + 6];
+            sm.xr[r] = sm.xr[r] + res * Ki;
+            sm.dec.WR[r] = make_double2(sq * Ki, 0.0);
+          }
+        }
+        __syncthreads();
+        if (q < 2 * n_lm) {                              // eager rank-1 downdate of strip and diagonal blocks
+          const unsigned s0 = sm.hs0[npend];
+          const double2* Hc = sm.H[npend];
+          const double u0 = dt_flip(Hc[q].x, s0);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) sm.SR[j][q] = fma(u0, sm.dec.WR[j].x, sm.SR[j][q]);
+          const int aa = q & 3, l = q >> 1, m = q >> 2;
+          if ((aa & 1) == 0) sm.Dd[0][l] = fma(u0, Hc[q].x, sm.Dd[0][l]);
+          else {
+            sm.Dd[1][l] = fma(u0, Hc[q - 1].x, sm.Dd[1][l]);
+            sm.Dd[2][l] = fma(u0, Hc[q].x, sm.Dd[2][l]);
+          }
+          if (aa >= 2) {
+            sm.Do[(aa & 1)][m] = fma(u0, Hc[4 * m].x, sm.Do[(aa & 1)][m]);
+            sm.Do[(aa & 1) + 2][m] = fma(u0, Hc[4 * m + 1].x, sm.Do[(aa & 1) + 2][m]);
+          }
+        }
+        if (helper) prr_eager(npend);
+        npend += 1;
+        setup_valid = false;
+        __syncthreads();
+        if (npend == KH) {
+          if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
+          npend = 0;
+          __syncthreads();
+        }
+      }
+
+      // ---- doUpdate per measurement (slam.cpp:150-171, Update.cpp:80-195) -------------------------
+      for (int m = 0; m < M; ++m) {
+        if (m >= nz) {
+          if (tid == 0) {
+            const size_t oi = ((size_t)f * T_steps + t) * M + m;
+            if (a.io.decision) a.io.decision[oi] = EKF_DEC_NONE;
+            if (a.io.index) a.io.index[oi] = -1;
+            if (a.io.mahal) a.io.mahal[oi] = 0.0;
+          }
+          continue;
+        }
+        const double* zr = cur + 8 + 6 * m;
+        __syncthreads();                                 // B2: strip propagated / previous update complete
+        DTILE_TS(1);
+        if (front) {
+          // ================= front warp: gating + decision =========================================
+          if (!setup_valid) {
+            if (lane == 0) {
+              UpdateSetup u;
+              double PRR[9];
+              for (int w = 0; w < 9; ++w) PRR[w] = sm.PRR[w];
+              ekf_build_setup(u, sm.xr[2], sm.xr[0], sm.xr[1], PRR, zr[0], zr[1], zr + 2);
+              sm.upd = u;
+            }
+            __syncwarp();
+          }
+          const UpdateSetup& u = sm.upd;
+          ScreenU w;
+          dt_screen_setup(w, u, k.cond_max);
+          double tlo[2], thi[2];
+          int state[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int lm = lane + 32 * h;
+            tlo[h] = INFINITY; thi[h] = INFINITY; state[h] = 1;
+            if (lm < n_lm) {
+              const double2 xy = *reinterpret_cast<const double2*>(&sm.xl[2 * lm]);
+              double sr[6], dd[3];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(&sm.SR[j][2 * lm]);
+                sr[2 * j] = v.x; sr[2 * j + 1] = v.y;
+              }
+#pragma unroll
+              for (int e = 0; e < 3; ++e) dd[e] = sm.Dd[e][lm];
+              dt_screen(w, xy.x, xy.y, sr, dd, tlo[h], thi[h], state[h]);
+            }
+          }
+          DTILE_TS(2);
+          // upper bound of the minimum over the landmarks that are kept for sure
+          const unsigned long long kmin = dt_warp_min_key(min(dt_key(thi[0]), dt_key(thi[1])));
+          bool flag[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int lm = lane + 32 * h;
+            // candidate unless skipped for sure or provably above the bound (NaN-safe: !(>))
+            flag[h] = lm < n_lm && state[h] != 1 && !(dt_key(tlo[h]) > kmin);
+          }
+          const unsigned mA = __ballot_sync(0xffffffffu, flag[0]), mB = __ballot_sync(0xffffffffu, flag[1]);
+          const int nA = __popc(mA), nTot = nA + __popc(mB);
+          if (flag[0]) sm.list[__popc(mA & ((1u << lane) - 1))] = lane;
+          if (flag[1]) sm.list[nA + __popc(mB & ((1u << lane) - 1))] = lane + 32;
+          __syncwarp();
+          // exact evaluation (reference operation order), four lanes per candidate
+          double bval = INFINITY;
+          int bidx = INT_MAX;
+          double bres0 = 0, bres1 = 0, bS0 = 0, bS1 = 0, bS2 = 0, bS3 = 0, bh0 = 0, bh1 = 0;
+          for (int base = 0; base < nTot; base += 8) {
+            const int gi = base + (lane >> 2), e = lane & 3;
+            const bool have = gi < nTot;
+            const int lm = have ? sm.list[gi] : 0;
+            GatePre pre;
+            double p[6], pll[4];
+            {
+              const double2 xy = *reinterpret_cast<const double2*>(&sm.xl[2 * lm]);
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(&sm.SR[j][2 * lm]);
+                p[2 * j] = v.x; p[2 * j + 1] = v.y;
+              }
+              const double p10 = sm.Dd[1][lm];
+              pll[0] = sm.Dd[0][lm]; pll[1] = p10; pll[2] = p10; pll[3] = sm.Dd[2][lm];
+              ekf_gate_prelude(u, xy.x, xy.y, pre);
+            }
+            const double Sk = ekf_gate_S_element(u, pre, p, pll, e);
+            double Sraw[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) Sraw[kk] = __shfl_sync(0xffffffffu, Sk, (lane & ~3) + kk);
+            GateResult g;
+            ekf_gate_from_S(pre, Sraw, k.cond_max, g);
+            const bool valid = have && !g.skip && (k.mahal_init > g.d2);   // Update.cpp:131,140
+            const double val = valid ? g.d2 : INFINITY;
+            const int my_idx = valid ? 3 + 2 * lm : INT_MAX;
+            int idx;
+            {   // warp argmin, lowest index wins ties (Update.cpp:140)
+              const unsigned long long key = dt_key(val + 0.0);
+              const unsigned long long mk = dt_warp_min_key(key);
+              idx = (int)__reduce_min_sync(0xffffffffu, key == mk ? (unsigned)my_idx : (unsigned)INT_MAX);
+            }
+            if (idx != INT_MAX) {
+              const int src = __ffs(__ballot_sync(0xffffffffu, my_idx == idx)) - 1;
+              const double cv = __shfl_sync(0xffffffffu, val, src);
+              const double c0 = __shfl_sync(0xffffffffu, g.res0, src), c1 = __shfl_sync(0xffffffffu, g.res1, src);
+              const double s0 = __shfl_sync(0xffffffffu, g.S[0], src), s1 = __shfl_sync(0xffffffffu, g.S[1], src);
+              const double s2 = __shfl_sync(0xffffffffu, g.S[2], src), s3 = __shfl_sync(0xffffffffu, g.S[3], src);
+              const double h0 = __shfl_sync(0xffffffffu, g.h3_0, src), h1 = __shfl_sync(0xffffffffu, g.h3_1, src);
+              if (cv < bval || (cv == bval && idx < bidx)) {
+                bval = cv; bidx = idx;
+                bres0 = c0; bres1 = c1; bS0 = s0; bS1 = s1; bS2 = s2; bS3 = s3; bh0 = h0; bh1 = h1;
+              }
+            }
+          }
+          DTILE_TS(3);
+          // ---- decision (Update.cpp:152,181,191) -----------------------------------------------------
+          const int opt_i = (bidx == INT_MAX) ? 0 : bidx;
+          const double mahal = (bidx == INT_MAX) ? k.mahal_init : bval;
+          int decision = ekf_decide(opt_i, mahal, k);
+          if (decision == EKF_DEC_NEW && n_lm >= cap_lm) decision = EKF_DEC_DROPPED;
+          int index = opt_i;
+          DDec& dc = sm.dec;
+          if (decision == EKF_DEC_OLD) {
+            const int c0 = opt_i - 3;
+            // S^-1 and L D L^T of the winning S (all lanes, same values)
+            const double Sm[4] = {bS0, bS1, bS2, bS3};
+            double Si[4];
+            ekf_inv2(Sm, Si);
+            const double d0 = Sm[0], l = Sm[1] / Sm[0], d1 = Sm[3] - l * Sm[1];
+            const double sq0 = sqrt(fabs(d0)), sq1 = sqrt(fabs(d1));
+            const unsigned s0m = d0 < 0 ? 0u : 0x80000000u, s1m = d1 < 0 ? 0u : 0x80000000u;
+            if (lane < 3) {
+              // pose rows of the gain (Update.cpp:186-187): row r of P at the five gain columns
+              const int r = lane;
+              const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = bh0;
+              const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = bh1;
+              const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
+              const double p0 = sm.PRR[r], p1 = sm.PRR[r + 3], p2 = sm.PRR[r + 6];
+              const double pa = sm.SR[r][c0], pb = sm.SR[r][c0 + 1];
+              const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
+              const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
+              const double B0 = pa * c00 + pb * c10;
+              const double B1 = pa * c01 + pb * c11;
+              const double M0 = A0 + B0, M1 = A1 + B1;
+              const double K0 = M0 * Si[0] + M1 * Si[1];
+              const double K1 = M0 * Si[2] + M1 * Si[3];
+              sm.xr[r] = sm.xr[r] + (K0 * bres0 + K1 * bres1);
+              dc.WR[r] = make_double2(sq0 * fma(l, K1, K0), sq1 * K1);
+            }
+            if (lane == 0) {
+              dc.c0 = c0;
+              dc.h3[0] = bh0; dc.h3[1] = bh1;
+              dc.res[0] = bres0; dc.res[1] = bres1;
+              dc.Si[0] = Si[0]; dc.Si[1] = Si[1]; dc.Si[2] = Si[2]; dc.Si[3] = Si[3];
+              dc.l = l; dc.sq0 = sq0; dc.sq1 = sq1;
+              dc.sm0 = s0m; dc.sm1 = s1m;
+              sm.hs0[npend] = s0m; sm.hs1[npend] = s1m; sm.hrank[npend] = 2;
+            }
+          } else if (decision == EKF_DEC_NEW) {
+            index = 3 + 2 * n_lm;
+            if (lane == 0) {
+              // state augmentation blocks (Update.cpp:152-168)
+              const double c = u.c, s = u.s, z0 = zr[0], z1 = zr[1];
+              const double Cz0 = c * z0 + (-s) * z1, Cz1 = s * z0 + c * z1;   // Update.cpp:155
+              const double nl0 = u.x0 + Cz0, nl1 = u.x1 + Cz1;
+              const double dn0 = nl0 - u.x0, dn1 = nl1 - u.x1;
+              const double h30 = u.mCtJ[0] * dn0 + u.mCtJ[2] * dn1;
+              const double h31 = u.mCtJ[1] * dn0 + u.mCtJ[3] * dn1;
+              const double HR[6] = {u.mCt[0], u.mCt[1], u.mCt[2], u.mCt[3], h30, h31};
+              double a1[6], t1[4], in[4], b1[4];
+              for (int j = 0; j < 3; ++j) {
+                a1[0 + 2 * j] = u.q[0 + 2 * j] + h30 * u.PRR[2 + 3 * j];
+                a1[1 + 2 * j] = u.q[1 + 2 * j] + h31 * u.PRR[2 + 3 * j];
+              }
+              for (int j = 0; j < 2; ++j)
+                for (int i = 0; i < 2; ++i)
+                  t1[i + 2 * j] = (a1[i] * HR[j] + a1[i + 2] * HR[j + 2]) + a1[i + 4] * HR[j + 4];
+              for (int w2 = 0; w2 < 4; ++w2) in[w2] = t1[w2] + u.R[w2];
+              const double Cm[4] = {u.Ct[0], u.Ct[2], u.Ct[1], u.Ct[3]};
+              for (int j = 0; j < 2; ++j)
+                for (int i = 0; i < 2; ++i) b1[i + 2 * j] = Cm[i] * in[0 + 2 * j] + Cm[i + 2] * in[1 + 2 * j];
+              for (int j = 0; j < 2; ++j)       // Update.cpp:168
+                for (int i = 0; i < 2; ++i)
+                  dc.PLL[i + 2 * j] = b1[i] * u.Ct[0 + 2 * j] + b1[i + 2] * u.Ct[1 + 2 * j];
+              dc.nl[0] = nl0; dc.nl[1] = nl1;
+              dc.h3n[0] = h30; dc.h3n[1] = h31;
+            }
+          } else if (decision == EKF_DEC_DROPPED) {
+            index = -1;
+          }
+          if (lane < 4) { dc.Ct[lane] = u.Ct[lane]; dc.mCt[lane] = u.mCt[lane]; }
+          if (lane == 0) {
+            dc.decision = decision;
+            const size_t oi = ((size_t)f * T_steps + t) * M + m;
+            if (a.io.decision) a.io.decision[oi] = decision;
+            if (a.io.index) a.io.index[oi] = index;
+            if (a.io.mahal) a.io.mahal[oi] = mahal;
+          }
+        }
+        DTILE_TS(4);
+        const bool last_meas = m == nz - 1;
+        if (last_meas) dt_cp_async_wait_all();           // next step's record visible after the barrier
+        __syncthreads();                                 // B3: decision published
+        DTILE_TS(5);
+        const int decision = sm.dec.decision;
+        setup_valid = false;
+        if (decision == EKF_DEC_OLD) {
+          const int np = npend;
+          const DDec& dc = sm.dec;
+          // ---- gain rows, state, downdate vector (Update.cpp:186-187), one P_LL row per thread -----
+          const bool row = q < 2 * n_lm;
+          double2 w = make_double2(0.0, 0.0);
+          double u0 = 0.0, u1 = 0.0;
+          if (row) {
+            const int c0 = dc.c0;
+            const double p0 = sm.SR[0][q], p1 = sm.SR[1][q], p2 = sm.SR[2][q];
+            double pa, pb;
+            if ((q >> 2) == (c0 >> 2)) {                 // same aligned pair: eager entries, already current
+              if ((q >> 1) == (c0 >> 1)) {
+                const int l = q >> 1;
+                pa = (q & 1) ? sm.Dd[1][l] : sm.Dd[0][l];
+                pb = (q & 1) ? sm.Dd[2][l] : sm.Dd[1][l];
+              } else {
+                const int m2 = q >> 2;
+                if (c0 & 2) {                            // associated landmark is the pair's second: P(q, 4m+2+i) = Do[i + 2(q&1)]
+                  pa = sm.Do[2 * (q & 1)][m2];
+                  pb = sm.Do[2 * (q & 1) + 1][m2];
+                } else {                                 // first: P(4m+2+i, 4m+j) = Do[i + 2j], i = q&1
+                  pa = sm.Do[(q & 1)][m2];
+                  pb = sm.Do[(q & 1) + 2][m2];
+                }
+              }
+            } else {
+              // stored tile entries + the pending downdates, in order (the deferred sweep's fma sequence)
+              if (q > c0) { pa = T[dt_addr<RB>(q, c0)]; pb = T[dt_addr<RB>(q, c0 + 1)]; }
+              else { pa = T[dt_addr<RB>(c0, q)]; pb = T[dt_addr<RB>(c0 + 1, q)]; }
+              for (int p = 0; p < np; ++p) {
+                const double2 wq = sm.H[p][q], wa = sm.H[p][c0], wb = sm.H[p][c0 + 1];
+                const double v0 = dt_flip(wq.x, sm.hs0[p]), v1 = dt_flip(wq.y, sm.hs1[p]);
+                if (sm.hrank[p] == 2) { pa = fma(v1, wa.y, pa); pb = fma(v1, wb.y, pb); }
+                pa = fma(v0, wa.x, pa);
+                pb = fma(v0, wb.x, pb);
+              }
+            }
+            const double h00 = dc.mCt[0], h01 = dc.mCt[2], h02 = dc.h3[0];
+            const double h10 = dc.mCt[1], h11 = dc.mCt[3], h12 = dc.h3[1];
+            const double c00 = dc.Ct[0], c10 = dc.Ct[2], c01 = dc.Ct[1], c11 = dc.Ct[3];
+            const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
+            const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
+            const double B0 = pa * c00 + pb * c10;
+            const double B1 = pa * c01 + pb * c11;
+            const double M0 = A0 + B0, M1 = A1 + B1;
+            const double K0 = M0 * dc.Si[0] + M1 * dc.Si[1];
+            const double K1 = M0 * dc.Si[2] + M1 * dc.Si[3];
+            sm.xl[q] = sm.xl[q] + (K0 * dc.res[0] + K1 * dc.res[1]);
+            w = make_double2(dc.sq0 * fma(dc.l, K1, K0), dc.sq1 * K1);
+            u0 = dt_flip(w.x, dc.sm0);
+            u1 = dt_flip(w.y, dc.sm1);
+            // eager downdate of the strip row (Update.cpp:188,193-194)
+            const double2 w0 = dc.WR[0], w1 = dc.WR[1], w2 = dc.WR[2];
+            sm.SR[0][q] = fma(u0, w0.x, fma(u1, w0.y, p0));
+            sm.SR[1][q] = fma(u0, w1.x, fma(u1, w1.y, p1));
+            sm.SR[2][q] = fma(u0, w2.x, fma(u1, w2.y, p2));
+          }
+          if (tid < NQ) sm.H[np][q] = w;                 // zero for rows beyond the live map
+          __syncwarp();
+          if (row) {                                     // eager downdate of the diagonal / pair blocks
+            const double2* Hc = sm.H[np];
+            const int aa = q & 3, l = q >> 1, m2 = q >> 2;
+            if ((aa & 1) == 0) {
+              sm.Dd[0][l] = fma(u0, w.x, fma(u1, w.y, sm.Dd[0][l]));
+            } else {
+              const double2 wl = Hc[q - 1];
+              sm.Dd[1][l] = fma(u0, wl.x, fma(u1, wl.y, sm.Dd[1][l]));
+              sm.Dd[2][l] = fma(u0, w.x, fma(u1, w.y, sm.Dd[2][l]));
+            }
+            if (aa >= 2) {
+              const double2 wa = Hc[4 * m2], wb = Hc[4 * m2 + 1];
+              sm.Do[(aa & 1)][m2] = fma(u0, wa.x, fma(u1, wa.y, sm.Do[(aa & 1)][m2]));
+              sm.Do[(aa & 1) + 2][m2] = fma(u0, wb.x, fma(u1, wb.y, sm.Do[(aa & 1) + 2][m2]));
+            }
+          }
+          if (helper) {
+            prr_eager(np);
+            if (last_meas && t + 1 < T_steps) {
+              if (a.io.pose_trace && lane == 0) {       // slam.cpp:181, before the pose is propagated
+                double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
+                pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
+              }
+              __syncwarp();
+              helper_chain(recbuf + (size_t)((t + 1) & 1) * Lp);
+            }
+          }
+          if (last_meas && t + 1 < T_steps) next_ready = true;
+          npend += 1;
+          if (npend == KH) {
+            __syncthreads();
+            DTILE_TS(6);
+            if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
+            npend = 0;
+            DTILE_TS(7);
+          }
+        } else if (decision == EKF_DEC_NEW) {
+          // ---- state augmentation (Update.cpp:152-178); pending downdates are applied first ----------
+          if (npend > 0) {
+            if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
+            npend = 0;
+            __syncthreads();
+          }
+          const DDec& dc = sm.dec;
+          const int q0 = 2 * n_lm;                       // P_LL rows of the new landmark
+          const bool pose_row = tid >= NQ && tid < NQ + 3;
+          if (q < q0 || pose_row) {                      // P_xL = -P[:,0:3]*H_R^T*H_Li (:169), existing row
+            const double h00 = dc.mCt[0], h01 = dc.mCt[2], h02 = dc.h3n[0];
+            const double h10 = dc.mCt[1], h11 = dc.mCt[3], h12 = dc.h3n[1];
+            const double ct00 = dc.Ct[0], ct10 = dc.Ct[1], ct01 = dc.Ct[2], ct11 = dc.Ct[3];
+            double e0, e1, e2;
+            if (pose_row) { const int r = tid - NQ; e0 = sm.PRR[r]; e1 = sm.PRR[r + 3]; e2 = sm.PRR[r + 6]; }
+            else { e0 = sm.SR[0][q]; e1 = sm.SR[1][q]; e2 = sm.SR[2][q]; }
+            const double q0v = -e0, q1v = -e1, q2v = -e2;
+            const double t0 = (q0v * h00 + q1v * h01) + q2v * h02;
+            const double t1 = (q0v * h10 + q1v * h11) + q2v * h12;
+            const double v0 = t0 * ct00 + t1 * ct10, v1 = t0 * ct01 + t1 * ct11;
+            if (pose_row) { const int r = tid - NQ; sm.SR[r][q0] = v0; sm.SR[r][q0 + 1] = v1; }
+            else { *pll_ref(q0, q) = v0; *pll_ref(q0 + 1, q) = v1; }
+          }
+          if (tid == 0) {
+            const double off = 0.5 * (dc.PLL[2] + dc.PLL[1]);   // :193-194 on the new 2x2 block
+            sm.Dd[0][n_lm] = dc.PLL[0];
+            sm.Dd[1][n_lm] = off;
+            sm.Dd[2][n_lm] = dc.PLL[3];
+            sm.xl[q0] = dc.nl[0];
+            sm.xl[q0 + 1] = dc.nl[1];
+          }
+          n_lm += 1;
+        } else if (decision == EKF_DEC_DROPPED) {
+          dropped = 1;
+        }
+      }
+      // ---- end of step: pose trace, and the next step's helper chain if no Old update issued it ----
+      if (t + 1 < T_steps) {
+        if (!next_ready) {
+          // the last measurement was not an Old update (or there was none): the pose is final now
+          if (nz == 0) dt_cp_async_wait_all();
+          __syncthreads();
+          if (helper) {
+            if (a.io.pose_trace && lane == 0) {
+              double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
+              pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
+            }
+            __syncwarp();
+            helper_chain(recbuf + (size_t)((t + 1) & 1) * Lp);
+          }
+        }
+        setup_valid = true;
+      } else {
+        __syncthreads();
+        if (a.io.pose_trace && tid == 0) {
+          double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
+          pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
+        }
+      }
+      DTILE_TS(8);
+    }
+
+    // ---- flush the pending downdates, write back to HBM (external layout, both triangles) ---------
+    __syncthreads();
+    if (npend > 0) {
+      if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
+      npend = 0;
+      __syncthreads();
+    }
+    {
+      const int n = 3 + 2 * n_lm;
+      for (int c = warp; c < n; c += DT_THREADS / 32) {
+        double* gc = gP + (size_t)c * ld;
+        for (int r = lane; r < n; r += 32) {
+          const int hi = r > c ? r : c, lo = r > c ? c : r;
+          double v;
+          if (hi < 3) v = sm.PRR[hi + 3 * lo];
+          else if (lo < 3) v = sm.SR[lo][hi - 3];
+          else v = *pll_ref(hi - 3, lo - 3);
+          gc[r] = v;
+        }
+      }
+      if (tid < 2 * n_lm) gx[3 + tid] = sm.xl[tid];
+      if (tid < 3) gx[tid] = sm.xr[tid];
+      if (tid == 0) {
+        a.st.nlm[f] = n_lm;
+        if (dropped) a.st.status[f] |= 1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int RB>
+size_t dtile_smem_bytes(int L) {
+  return ((sizeof(DSmem<RB>) + 15) & ~(size_t)15) + (size_t)((DCfg<RB>::TSIZE + 1) & ~1) * sizeof(double) +
+         (size_t)2 * ((L + 1) & ~1) * sizeof(double);
+}
+
+template <int RB>
+cudaError_t launch_dtile(const DRunArgs& a, int sm_count, cudaStream_t stream) {
+  const size_t bytes = dtile_smem_bytes<RB>(a.io.L);
+  static size_t configured_dev[64] = {0};      // function attributes are per device
+  static int grid_cap_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  size_t& configured = configured_dev[dev];
+  int& grid_cap = grid_cap_dev[dev];
+  if (bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(ekf_batch_dtile_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ekf_batch_dtile_kernel<RB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_batch_dtile_kernel<RB>, DT_THREADS, bytes);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    grid_cap = per_sm * sm_count;
+    configured = bytes;
+  }
+  const int grid = a.st.F < grid_cap ? a.st.F : grid_cap;
+  ekf_batch_dtile_kernel<RB><<<grid, DT_THREADS, bytes, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t ekf_dtile_timestamps(long long* out64) {
+#ifdef EKF_DTILE_TIMING
+  return cudaMemcpyFromSymbol(out64, g_dtile_ts, sizeof(long long) * 64);
+#else
+  for (int i = 0; i < 64; ++i) out64[i] = 0;
+  return cudaSuccess;
+#endif
+}
+
+int ekf_dtile_max_landmarks() { return DCfg<25>::NL; }
+int ekf_dtile_ctas_per_sm() { return 4; }
+
+cudaError_t ekf_dtile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream) {
+  DRunArgs a{st, io, k};
+  if (st.cap_lm <= DCfg<25>::NL) return launch_dtile<25>(a, sm_count, stream);
+  return cudaErrorInvalidValue;
+}

@@ -63,6 +63,13 @@ int ekf_stile_ctas_per_sm(int cap_lm);
 cudaError_t ekf_stile_timestamps(long long* out128);
 cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
 
+// Deferred-downdate variant (ekf_dtile.cu): eager strip / diagonal blocks, P_LL tiles swept once per
+// four updates, gating on one warp with exact re-evaluation on demand; four filters per SM, <= 50 landmarks.
+int ekf_dtile_max_landmarks();
+int ekf_dtile_ctas_per_sm();
+cudaError_t ekf_dtile_timestamps(long long* out64);
+cudaError_t ekf_dtile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
+
 // ---- regime B: whole grid per filter, covariance streamed from HBM (ekf_large.cu) ---------------
 struct EkfLargeWork {      // device scratch owned by the handle
   double2* W;              // [cap_n + 2]  downdate vectors

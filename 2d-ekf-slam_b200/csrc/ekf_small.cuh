@@ -165,18 +165,18 @@ __device__ __forceinline__ void ekf_gate_terms34(const UpdateSetup& u, const Gat
     for (int i = 0; i < 2; ++i) t4[i + 2 * j] = a4[i] * Cm[0 + 2 * j] + a4[i + 2] * Cm[1 + 2 * j];
 }
 
-__device__ __forceinline__ void ekf_gate_finish(const UpdateSetup& u, const GatePre& pre, const double* t12,
-                                                const double* t3, const double* t4, double cond_max, GateResult& g) {
+// Everything of one landmark-loop iteration behind the raw innovation covariance: Sraw[k] =
+// ((t12[k] + t3[k]) + t4[k]) + R[k] (column-major 2x2). Symmetrisation, condition gate, Mahalanobis
+// distance (Update.cpp:123-136). Shared by the one-lane-per-landmark path (ekf_gate_finish) and the
+// four-lanes-per-landmark path of ekf_dtile.cu, so both produce the same bits.
+__device__ __forceinline__ void ekf_gate_from_S(const GatePre& pre, const double* Sraw, double cond_max, GateResult& g) {
   g.res0 = pre.res0; g.res1 = pre.res1;
   g.h3_0 = pre.HR[4]; g.h3_1 = pre.HR[5];
-  double S[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) S[k] = ((t12[k] + t3[k]) + t4[k]) + u.R[k];
   // S = 0.5*(S + S^T) (Update.cpp:123-124)
-  const double s01 = 0.5 * (S[2] + S[1]);
-  const double s10 = 0.5 * (S[1] + S[2]);
-  g.S[0] = 0.5 * (S[0] + S[0]);
-  g.S[3] = 0.5 * (S[3] + S[3]);
+  const double s01 = 0.5 * (Sraw[2] + Sraw[1]);
+  const double s10 = 0.5 * (Sraw[1] + Sraw[2]);
+  g.S[0] = 0.5 * (Sraw[0] + Sraw[0]);
+  g.S[3] = 0.5 * (Sraw[3] + Sraw[3]);
   g.S[2] = s01;
   g.S[1] = s10;
   // condition number via 2x2 singular values (Update.cpp:127-128): cond = (Q+R)/|Q-R| with
@@ -210,6 +210,48 @@ __device__ __forceinline__ void ekf_gate_finish(const UpdateSetup& u, const Gate
   const double r0 = g.res0 * i00 + g.res1 * i10;
   const double r1 = g.res0 * i01 + g.res1 * i11;
   g.d2 = r0 * g.res0 + r1 * g.res1;
+}
+
+__device__ __forceinline__ void ekf_gate_finish(const UpdateSetup& u, const GatePre& pre, const double* t12,
+                                                const double* t3, const double* t4, double cond_max, GateResult& g) {
+  double S[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) S[k] = ((t12[k] + t3[k]) + t4[k]) + u.R[k];
+  ekf_gate_from_S(pre, S, cond_max, g);
+}
+
+// Element k = i + 2j of the raw innovation covariance of one landmark, the way ekf_gate_terms12 /
+// ekf_gate_terms34 / ekf_gate_finish evaluate it (same expressions, same order), for a lane that
+// owns only that element. Operands are picked with selects so nothing is indexed dynamically.
+__device__ __forceinline__ double ekf_gate_S_element(const UpdateSetup& u, const GatePre& g, const double* p,
+                                                     const double* pll, int k) {
+  const bool i1 = (k & 1) != 0, j1 = (k & 2) != 0;
+  const double* HR = g.HR;
+  const double HRj0 = j1 ? HR[1] : HR[0], HRj2 = j1 ? HR[3] : HR[2], HRj4 = j1 ? HR[5] : HR[4];
+  const double HRi0 = i1 ? HR[1] : HR[0], HRi2 = i1 ? HR[3] : HR[2], HRi4 = i1 ? HR[5] : HR[4];
+  const double Cti = i1 ? u.Ct[1] : u.Ct[0], Cti2 = i1 ? u.Ct[3] : u.Ct[2];
+  const double Cm0j = j1 ? u.Ct[1] : u.Ct[0], Cm1j = j1 ? u.Ct[3] : u.Ct[2];   // Cm[0+2j], Cm[1+2j]
+  // t1: a1[i+2c] = q[i+2c] + h3_i*PRR[2+3c]
+  const double a1_0 = (i1 ? u.q[1] : u.q[0]) + HRi4 * u.PRR[2];
+  const double a1_2 = (i1 ? u.q[3] : u.q[2]) + HRi4 * u.PRR[5];
+  const double a1_4 = (i1 ? u.q[5] : u.q[4]) + HRi4 * u.PRR[8];
+  const double t1 = (a1_0 * HRj0 + a1_2 * HRj2) + a1_4 * HRj4;
+  // t2: a2[i+2c] = Ct[i]*p[0+2c] + Ct[i+2]*p[1+2c]
+  const double a2_0 = Cti * p[0] + Cti2 * p[1];
+  const double a2_2 = Cti * p[2] + Cti2 * p[3];
+  const double a2_4 = Cti * p[4] + Cti2 * p[5];
+  const double t2 = (a2_0 * HRj0 + a2_2 * HRj2) + a2_4 * HRj4;
+  const double t12 = t1 + t2;
+  // t3: a3[i+2c] = (HR[i]*p[c] + HR[i+2]*p[c+2]) + HR[i+4]*p[c+4], c = 0..1
+  const double a3_0 = (HRi0 * p[0] + HRi2 * p[2]) + HRi4 * p[4];
+  const double a3_2 = (HRi0 * p[1] + HRi2 * p[3]) + HRi4 * p[5];
+  const double t3 = a3_0 * Cm0j + a3_2 * Cm1j;
+  // t4: a4[i+2c] = Ct[i]*pll[0+2c] + Ct[i+2]*pll[1+2c]
+  const double a4_0 = Cti * pll[0] + Cti2 * pll[1];
+  const double a4_2 = Cti * pll[2] + Cti2 * pll[3];
+  const double t4 = a4_0 * Cm0j + a4_2 * Cm1j;
+  const double Rk = j1 ? (i1 ? u.R[3] : u.R[2]) : (i1 ? u.R[1] : u.R[0]);
+  return ((t12 + t3) + t4) + Rk;
 }
 
 __device__ __forceinline__ void ekf_gate_landmark(const UpdateSetup& u, double lx, double ly, const double* p,

@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 OK, ERR_CUDA, ERR_BAD_ARG, ERR_CAPACITY, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(6)
 DECISION_NONE, DECISION_NEW, DECISION_OLD, DECISION_IGNORE, DECISION_DROPPED = -1, 0, 1, 2, 3
 REGIME_AUTO, REGIME_BATCH, REGIME_LARGE = 0, 1, 2
-BATCH_KERNEL_AUTO, BATCH_KERNEL_SMEM, BATCH_KERNEL_TILE, BATCH_KERNEL_STILE = 0, 1, 2, 3
+BATCH_KERNEL_AUTO, BATCH_KERNEL_SMEM, BATCH_KERNEL_TILE, BATCH_KERNEL_STILE, BATCH_KERNEL_DTILE = 0, 1, 2, 3, 4
 RECORD_HEADER = 8
 
 c_dp = C.POINTER(C.c_double)

@@ -18,7 +18,7 @@ from parity import TOL
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["fused-smem", "fused-tile", "fused-stile", "fused-large", "percall-batch", "percall-large", "sharded3"]
+ENGINES = ["fused-smem", "fused-tile", "fused-stile", "fused-dtile", "fused-large", "percall-batch", "percall-large", "sharded3"]
 
 
 def _records(steps, M):
@@ -44,7 +44,7 @@ def _run_engine(ekf, engine, x0, P0, cap, steps, M):
             out = obj.run(rec, M, trace=True, allow_capacity=True)
             x, P = obj.get_state()
         else:
-            kern = {"fused-smem": 1, "fused-tile": 2, "fused-stile": 3, "fused-large": 0}[engine]
+            kern = {"fused-smem": 1, "fused-tile": 2, "fused-stile": 3, "fused-dtile": 4, "fused-large": 0}[engine]
             obj = ekf.FilterBatch(1, cap, regime=2 if engine == "fused-large" else 1, batch_kernel=kern)
             obj.set_state(0, x0, P0)
             out = obj.run(rec, M, trace=True, allow_capacity=True)

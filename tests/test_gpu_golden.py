@@ -7,7 +7,7 @@ from test_golden import GOLDEN, check_against_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["smem", "tile", "stile"])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4], ids=["smem", "tile", "stile", "dtile"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[p.split("/")[-1][:-4] for p in GOLDEN])
 def test_cuda_matches_golden(ekf, path, kernel):
     g = np.load(path)
