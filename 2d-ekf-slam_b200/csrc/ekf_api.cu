@@ -383,6 +383,7 @@ int ekf_set_state(ekf_handle h, int filter, int n_landmarks, const double* x, co
   EKF_CK(h, cudaMemcpy2DAsync(st.P + (size_t)filter * st.slab, (size_t)st.ld * sizeof(double), P, (size_t)ld * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
   EKF_CK(h, cudaMemcpyAsync(st.nlm + filter, &n_landmarks, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  EKF_CK(h, cudaMemsetAsync(st.status + filter, 0, sizeof(int), h->stream));   // a fresh map has dropped nothing
   if (h->wk.W) EKF_CK(h, cudaMemsetAsync(h->wk.W, 0, ((size_t)st.cap_n + 512) * sizeof(double2), h->stream));
   EKF_CK(h, cudaStreamSynchronize(h->stream));
   return EKF_OK;
@@ -699,6 +700,11 @@ int ekf_kernel_time(ekf_handle h, float* avg_ms, int* n_launches) {
 
 int ekf_debug_phase_cycles(long long* out8) {
   return ekf_tile_phase_cycles(out8) == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
+}
+
+int ekf_debug_dtile_timestamps(long long* out64) {
+  if (!out64) return EKF_ERR_BAD_ARG;
+  return ekf_dtile_timestamps(out64) == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
 }
 
 int ekf_debug_stile_timestamps(long long* out128) {

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 2) ekf_batch_run_kernel(const RunArg
       // slam.cpp:144-147
       if (cur[6] != 0.0) cta_update_compass(Ps, ld, xs, 3 + 2 * n_lm, cur[3], cur[4], Ws, sc, a.k);
       // slam.cpp:150-171
-      const int nz = (int)cur[5];
+      const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
       for (int m = 0; m < M; ++m) {
         UpdateOut o;
         if (m < nz) {
@@ -248,10 +248,20 @@ int ekf_batch_max_landmarks(size_t smem_optin) {
 
 cudaError_t ekf_batch_prepare(int cap_n, int ld, int max_L, int sm_count, int* grid_cap) {
   const size_t bytes = ekf_batch_smem_bytes(cap_n, ld, max_L);
-  cudaError_t e = cudaFuncSetAttribute(ekf_batch_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return e;
+  // The attribute is per function AND per device, and several handles of different capacity may be
+  // alive on one GPU: keep a high-water mark per device and only ever raise it (a later, smaller
+  // handle must not lower the limit under an earlier, larger one).
+  static size_t configured_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& configured = configured_dev[dev & 63];
+  if (bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(ekf_batch_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured = bytes;
+  }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_batch_run_kernel, kThreads, bytes);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_batch_run_kernel, kThreads, bytes);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   *grid_cap = per_sm * sm_count;

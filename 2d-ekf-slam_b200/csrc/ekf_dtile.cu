@@ -294,7 +294,7 @@ __device__ __forceinline__ void dt_sweep_tile(double* __restrict__ Tt, const DSm
 template <int RB>
 __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DRunArgs a) {
   using C = DCfg<RB>;
-  constexpr int PS = C::PS, NQ = C::NQ;
+  constexpr int NQ = C::NQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DSmem<RB>& sm = *reinterpret_cast<DSmem<RB>*>(smem_raw);
   double* T = reinterpret_cast<double*>(smem_raw + ((sizeof(DSmem<RB>) + 15) & ~(size_t)15));
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
         double* nxt = recbuf + (size_t)((t + 1) & 1) * Lp;
         for (int i = tid; i < L; i += DT_THREADS) dt_cp_async8(nxt + i, g + i);
       }
-      const int nz = (int)cur[5] < M ? (int)cur[5] : M;
+      const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
       DTILE_TS(0);
       __syncthreads();                                   // B1: helper results of this step visible
       // ---- doPropagation, strip part (Propagate.cpp:56-60) ------------------------------------------

@@ -54,6 +54,9 @@ constexpr int ACC_BYTES = TPP * RS;
 constexpr int ACC_WORDS = (ACC_BYTES + 3) / 4;
 constexpr int ACC_WORDS_PAD = (ACC_WORDS + 31) / 32 * 32;
 constexpr int MAXP = EKF_HOUGH_MAX_POINTS;
+// Votes go into byte-wide cells through 32-bit atomics on the containing word: a cell can receive at
+// most one vote per reading, so it cannot carry into its neighbour as long as a scan has < 256 readings.
+static_assert(EKF_HOUGH_MAX_POINTS <= 255, "byte-wide Hough cells would carry into the neighbouring cell");
 constexpr int CAND_CAP = MAXP * TPP;                       // a half cannot hold more non-zero cells than votes
 constexpr int SLOTS_PER_LANE = (PK + 31) / 32;             // 7
 

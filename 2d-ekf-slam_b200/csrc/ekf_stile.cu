@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
         double* nxt = recbuf + (size_t)((t + 1) & 1) * Lp;
         for (int i = tid; i < L; i += C::THREADS) cp_async8(nxt + i, g + i);
       }
-      const int nz = (int)cur[5];
+      const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
       bool rec_ready = false;
       STILE_TS(0);
       // ---- doPropagation (slam.cpp:136) ------------------------------------------------------------

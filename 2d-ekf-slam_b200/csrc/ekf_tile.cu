@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
       // ---- doPropagation (slam.cpp:136): the two scalar chains run on different warps. They only
       // need the final state of the previous step and the record, so when the previous step ended
       // with an Old update they have already run, overlapped with that step's covariance downdate.
-      const int nz = (int)cur[5];
+      const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
       if (!scalar_done) {
         scalar_chains(cur);
         __syncthreads();
@@ -693,13 +693,19 @@ __global__ void __launch_bounds__(TileCfg<NB>::THREADS, TileCfg<NB>::MINB) ekf_b
   }
 }
 
-long long* g_phase_cycles = nullptr;   // set by ekf_tile_phase_cycles()
+constexpr int kPhaseCounters = 16;
+long long* g_phase_cycles[64] = {nullptr};   // one buffer per device, set by ekf_tile_phase_cycles()
+inline long long*& phase_buf() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_phase_cycles[dev & 63];
+}
 
 template <int NB>
 cudaError_t launch_tile(RunArgs a, int sm_count, cudaStream_t stream) {
   using C = TileCfg<NB>;
   static int grid_cap = 0;   // occupancy is a property of the kernel binary; every device here is a B200
-  a.phase_cycles = g_phase_cycles;
+  a.phase_cycles = phase_buf();
   if (!grid_cap) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_batch_tile_kernel<NB>, C::THREADS, 0);
@@ -719,15 +725,16 @@ int ekf_tile_max_landmarks() { return TileCfg<16>::MAX_LM; }
 // Profiling aid: enable per-phase cycle accumulation (CTA 0 of every following launch) and read
 // the eight counters back. Passing out == nullptr only enables.
 cudaError_t ekf_tile_phase_cycles(long long* out) {
-  if (!g_phase_cycles) {
-    cudaError_t e = cudaMalloc(&g_phase_cycles, 16 * sizeof(long long));
+  long long*& buf = phase_buf();
+  if (!buf) {
+    cudaError_t e = cudaMalloc(&buf, kPhaseCounters * sizeof(long long));
     if (e != cudaSuccess) return e;
-    cudaMemset(g_phase_cycles, 0, 16 * sizeof(long long));
+    cudaMemset(buf, 0, kPhaseCounters * sizeof(long long));
   }
   if (out) {
-    cudaError_t e = cudaMemcpy(out, g_phase_cycles, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(out, buf, kPhaseCounters * sizeof(long long), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return e;
-    cudaMemset(g_phase_cycles, 0, 16 * sizeof(long long));
+    cudaMemset(buf, 0, kPhaseCounters * sizeof(long long));
   }
   return cudaSuccess;
 }

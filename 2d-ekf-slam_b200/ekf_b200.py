@@ -124,6 +124,7 @@ def core_lib():
         L.ekf_measure_fp64_peak.argtypes = [C.c_int, c_dp]
         L.ekf_debug_phase_cycles.argtypes = [C.POINTER(C.c_longlong)]
         L.ekf_debug_stile_timestamps.argtypes = [C.POINTER(C.c_longlong)]
+        L.ekf_debug_dtile_timestamps.argtypes = [C.POINTER(C.c_longlong)]
         c_u32p = C.POINTER(C.c_uint32)
         c_u8p = C.POINTER(C.c_uint8)
         L.ekf_hough_create.argtypes = [C.POINTER(H), C.c_int, C.c_int]
@@ -680,15 +681,21 @@ def debug_phase_cycles(read=True):
     if not read:
         core_lib().ekf_debug_phase_cycles(None)
         return None
-    buf = (C.c_longlong * 32)()
+    buf = (C.c_longlong * 16)()
     core_lib().ekf_debug_phase_cycles(buf)
-    return list(buf)
+    return list(buf) + [0] * 16
 
 
 def debug_stile_timestamps():
     out = (C.c_longlong * 128)()
     core_lib().ekf_debug_stile_timestamps(out)
     return np.array(out[:], np.int64).reshape(8, 16)
+
+
+def debug_dtile_timestamps():
+    out = (C.c_longlong * 64)()
+    core_lib().ekf_debug_dtile_timestamps(out)
+    return np.array(out[:], np.int64).reshape(4, 16)
 
 
 def measure_fp64_peak(device=0):

@@ -169,15 +169,18 @@ int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, siz
 /* DFMA-chain microbenchmark on `device`: achieved FP64 FLOP/s (2 flop per DFMA). Used as the
  * measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int ekf_measure_fp64_peak(int device, double* flops_per_s);
-/* Profiling aid for the register-tile fused kernel: the first call (out8 may be NULL) enables
- * per-phase cycle accumulation by CTA 0 of every following launch; later calls read and clear the
- * 32 counters {scalar chains, covariance propagate, gating, column publish, gain rows,
- * downdate, step epilogue, unused, then 24 finer probes along thread 0 (only in -DEKF_FINE_TIMING builds)}. */
-int ekf_debug_phase_cycles(long long* out32);
+/* Profiling aid for the register-tile fused kernel, per device (the current one): the first call
+ * (out16 may be NULL) enables per-phase cycle accumulation by CTA 0 of every following launch; later
+ * calls read and clear the 16 counters {scalar chains, covariance propagate, gating, column publish,
+ * gain rows, downdate, step epilogue, unused, then 8 finer probes along thread 0 (only in
+ * -DEKF_FINE_TIMING builds)}. */
+int ekf_debug_phase_cycles(long long* out16);
 /* Profiling aid for the shared-memory tiled fused kernel (-DEKF_STILE_TIMING builds, zeros
  * otherwise): clock64 at which lane 0 of each warp of CTA 0 arrived at each barrier of one step
  * (first filter, step 500), out128 = [8 warps][16 barriers]. */
 int ekf_debug_stile_timestamps(long long* out128);
+/* Same for the deferred-downdate kernel (-DEKF_DTILE_TIMING builds): out64 = [4 warps][16 stamps]. */
+int ekf_debug_dtile_timestamps(long long* out64);
 
 /* ---- one large map sharded over several GPUs ---------------------------- */
 /* The covariance of ONE map is split by columns over n_shards devices (one process drives them;
