@@ -46,14 +46,20 @@
 
 namespace {
 
-constexpr int KH = 4;            // pending downdates between two sweeps of the tiles
+constexpr int KH = 4;            // history ring: a warp sweeps its tiles when three updates are pending
 constexpr int DT_THREADS = 128;
+#ifndef DT_ROTATE
+#define DT_ROTATE 0               // 0: warp w of every CTA has the same role, so each SM sub-partition's instruction cache
+                                  // sees one role's code (measured +13 %); 1: roles rotate with the CTA's slot on its SM
+                                  // (FP64 pipes evenly loaded, but every sub-partition runs every role's code)
+#endif
 
 #ifdef EKF_DTILE_TIMING
 __device__ long long g_dtile_ts[4][16];
 #define DTILE_TS(kk)                                                                              \
   do {                                                                                            \
-    if (blockIdx.x == 0 && f == 0 && t == 501 && (threadIdx.x & 31) == 0) g_dtile_ts[threadIdx.x >> 5][kk] = clock64(); \
+    if (blockIdx.x == 0 && f == 0 && (t == 501 || ((kk) >= 9 && t >= 498 && t < 502)) && (threadIdx.x & 31) == 0) \
+      g_dtile_ts[threadIdx.x >> 5][kk] = clock64();                                               \
   } while (0)
 #else
 #define DTILE_TS(kk) do { } while (0)
@@ -70,6 +76,11 @@ struct DCfg {
   static constexpr int NT = NJ * (RB - 1) - 3 * NJ * (NJ - 1) / 2;   // tiles
   static constexpr int PS = NT + ((4 - NT % 8) + 8) % 8;   // plane stride: NT rounded up to 4 or 12 (mod 16)
   static constexpr int TSIZE = 47 * PS + 11 + NT;     // doubles of tile storage (48 planes, skew b)
+  // History vectors are stored row-in-block major: entry of row q at (q&3)*HP + (q>>2). Consecutive row
+  // blocks (the sweep: one tile per lane) and consecutive rows (the gain phase) both read conflict-free
+  // 16-byte words when HP = 2 (mod 8).
+  static constexpr int HP = RB + ((2 - RB % 8) + 8) % 8;
+  static constexpr int HN = 4 * HP;
   static_assert(PS % 16 == 4 || PS % 16 == 12, "plane stride must be 4 or 12 (mod 16)");
   static_assert(NT <= DT_THREADS, "one tile per thread");
   static_assert(NQ + 3 <= DT_THREADS, "one state row per thread");
@@ -77,17 +88,24 @@ struct DCfg {
 };
 
 template <int RB>
+__device__ __forceinline__ int dt_hidx(int q) { return (q & 3) * DCfg<RB>::HP + (q >> 2); }
+template <int RB>
 __device__ __forceinline__ int dt_slot(int I, int J) { return J * (RB - 1) - 3 * J * (J - 1) / 2 + I - 3 * J - 1; }
 // storage index of P_LL(r, c), r > c, r and c in different aligned pairs
 template <int RB>
-__device__ __forceinline__ int dt_addr(int r, int c) {
+__device__ __forceinline__ int dt_rowterm(int r) { return (r & 3) * DCfg<RB>::PS + (r >> 2); }
+template <int RB>
+__device__ __forceinline__ int dt_colterm(int c) {
   const int J = (c * 43) >> 9;            // c / 12 for c < 128
   const int b = c - 12 * J;
-  return ((r & 3) + 4 * b) * DCfg<RB>::PS + b + dt_slot<RB>(r >> 2, J);
+  return 4 * b * DCfg<RB>::PS + b + dt_slot<RB>(0, J);
 }
+template <int RB>
+__device__ __forceinline__ int dt_addr(int r, int c) { return dt_rowterm<RB>(r) + dt_colterm<RB>(c); }
 
 struct DDec {                    // what the front warp publishes for the row threads / the helper
-  int decision, c0, pad0, pad1;  // c0 = first P_LL row of the associated landmark
+  int decision, c0, rt_c0, ct_c0;  // c0 = first P_LL row of the associated landmark; its row / column address terms
+  int sb_c0, pad0, pad1, pad2;     // first tile slot of its column block
   double h3[2], res[2], Si[4];
   double Ct[4], mCt[4];          // H_Li and the first two columns of H_R of THIS update (sm.upd is rewritten early)
   double l, sq0, sq1;
@@ -100,20 +118,23 @@ struct DDec {                    // what the front warp publishes for the row th
 template <int RB>
 struct DSmem {
   using C = DCfg<RB>;
-  double2 H[KH][C::NQ];          // pending downdate vectors
+  double2 H[KH][C::HN];          // pending downdate vectors, entry of row q at dt_hidx(q)
   double SR[3][C::NQ];           // strip: SR[j][q] = P(3+q, j)
   double Dd[3][C::NL];           // P(2l,2l), P(2l+1,2l), P(2l+1,2l+1)
   double Do[4][C::NP];           // Do[i+2j][m] = P(4m+2+i, 4m+j)
   double xl[C::NQ];              // landmark part of the state
   double xr[4];                  // pose
   double PRR[9];                 // column-major, both triangles
-  double PhiS[9], GS[6];
   PropSetup prop;
+  PropSetup pre;                 // record-only part of the NEXT step's PropSetup (v, w, dt, Q)
+  double pre_dphi;               // dt * RTV of the next step
   UpdateSetup upd;
   DDec dec;
   unsigned hs0[KH], hs1[KH];     // sign masks of the pending updates
   int hrank[KH];                 // 2, or 1 for a compass update
   int list[64];                  // landmarks the exact pass has to visit
+  double scr_tlo[32], scr_thi[32];   // screen results of the second gating warp (landmarks 32..63)
+  int scr_state[32];
 };
 
 struct DRunArgs {
@@ -127,6 +148,8 @@ __device__ __forceinline__ void dt_cp_async8(void* dst_smem, const void* src_gme
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dt_smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void dt_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void dt_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void dt_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ double dt_flip(double v, unsigned mask) {
   return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
 }
@@ -250,45 +273,74 @@ __device__ __forceinline__ void dt_screen(const ScreenU& w, double lx, double ly
 }
 
 // ---- tile sweep: apply the pending downdates to this thread's tile, in order ---------------------
+// Half a tile (4 rows x 6 columns) at a time in registers. Per pending update the ten history words
+// this half needs are loaded back to back (one shared-memory latency), then 48 fma on 24 independent
+// elements.
+// One copy in the binary (the kernel reaches it from five places and its code footprint matters - the
+// SM sub-partitions' instruction caches are the bottleneck of the scalar phases). A third of a tile
+// (4 rows x 4 columns) at a time in registers, the three column groups in a rolled loop: column
+// 12J + 4g + b of a history vector sits at b*HP + 3J + g, so the group only shifts the address. Per
+// pending update the eight history words are loaded back to back, then 32 fma on 16 independent elements.
 template <int RB>
-__device__ __forceinline__ void dt_sweep_tile(double* __restrict__ Tt, const DSmem<RB>& sm, int I, int J, int npend) {
-  constexpr int PS = DCfg<RB>::PS;
+__device__ __noinline__ void dt_sweep_tile(double* __restrict__ Tt, const DSmem<RB>& sm, int I, int J, int from, int to) {
+  constexpr int PS = DCfg<RB>::PS, HP = DCfg<RB>::HP;
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    double t[4][6];
+  for (int g = 0; g < 3; ++g) {
+    double* Tg = Tt + 4 * g * (4 * PS + 1);            // element (a, 4g + b) at Tg[(a + 4b) * PS + b]
+    double t[4][4];
 #pragma unroll
-    for (int b = 0; b < 6; ++b)
+    for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) t[a][b] = Tt[(a + 4 * (b + 6 * half)) * PS + (b + 6 * half)];
+      for (int a = 0; a < 4; ++a) t[a][b] = Tg[(a + 4 * b) * PS + b];
 #pragma unroll 1
-    for (int p = 0; p < npend; ++p) {
+    for (int en = from; en < to; ++en) {
+      const int p = en & (KH - 1);
       const double2* W = sm.H[p];
       const unsigned s0 = sm.hs0[p], s1 = sm.hs1[p];
       const bool rank2 = sm.hrank[p] == 2;
-      double u0[4], u1[4];
+      double2 wi[4], wj[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double2 wi = W[4 * I + a];
-        u0[a] = dt_flip(wi.x, s0);
-        u1[a] = dt_flip(wi.y, s1);
-      }
+      for (int a = 0; a < 4; ++a) wi[a] = W[a * HP + I];               // rows 4I..4I+3
 #pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        const double2 wj = W[12 * J + 6 * half + b];
+      for (int b = 0; b < 4; ++b) wj[b] = W[b * HP + 3 * J + g];       // columns 12J + 4g + b
+      if (rank2 && (s0 & s1 & 0x80000000u)) {
+        // positive definite S (the normal case): u = -W, the negation rides on the fma operand
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) t[a][b] = fma(-wi[a].x, wj[b].x, fma(-wi[a].y, wj[b].y, t[a][b]));
+      } else {
+        double u0[4], u1[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          double v = t[a][b];
-          if (rank2) v = fma(u1[a], wj.y, v);
-          v = fma(u0[a], wj.x, v);
-          t[a][b] = v;
+          u0[a] = dt_flip(wi[a].x, s0);
+          u1[a] = dt_flip(wi[a].y, s1);
         }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            double v = t[a][b];
+            if (rank2) v = fma(u1[a], wj[b].y, v);
+            t[a][b] = fma(u0[a], wj[b].x, v);
+          }
       }
     }
 #pragma unroll
-    for (int b = 0; b < 6; ++b)
+    for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) Tt[(a + 4 * (b + 6 * half)) * PS + (b + 6 * half)] = t[a][b];
+      for (int a = 0; a < 4; ++a) Tg[(a + 4 * b) * PS + b] = t[a][b];
   }
+}
+
+// Record-only scalars of a step (kalmanfilter.cpp:17-37), one lane; evaluated while the front warp gates.
+template <int RB>
+__device__ __noinline__ void dt_helper_pre(DSmem<RB>& sm, const double* rec, const EkfConst& k) {
+  PropSetup ps;
+  ekf_build_prop_pre(ps, rec[0], rec[1], rec[2], k);
+  sm.pre = ps;
+  const double RTV = rec[1] * k.deg2rad_pi / 180.0;
+  sm.pre_dphi = rec[2] * RTV;
 }
 
 template <int RB>
@@ -304,11 +356,12 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
   if (tid == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    s_rot = atomicAdd(&g_sm_slot[smid & 1023], 1) & 3;
+    s_rot = (atomicAdd(&g_sm_slot[smid & 1023], 1) & 3) * DT_ROTATE;
   }
   __syncthreads();
   const int rot = s_rot;
   const bool front = warp == rot;                    // gating / decision warp
+  const bool front2 = warp == ((rot + 1) & 3);       // screens landmarks 32.. for the front warp
   const bool helper = warp == ((rot + 2) & 3);       // scalar chains / P_RR warp
   const bool is_tile = tid < C::NT;
   int I = 0, J = 0;
@@ -319,6 +372,14 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
   }
   double* Tt = T + tid;                              // this thread's tile
   const int q = tid;                                 // this thread's P_LL row (tid < NQ)
+  const int hq = dt_hidx<RB>(q < NQ ? q : 0);        // its slot in a history vector
+  constexpr int HP = C::HP, PS = C::PS;
+  // gain phase: one landmark (two P_LL rows) per thread on the two warps that are neither front nor helper
+  const bool rows_warp = front2 || warp == ((rot + 3) & 3);
+  const int lrow = (front2 ? 0 : 32) + lane;         // landmark of this thread in the gain phase
+  const int q0 = 2 * lrow < NQ ? 2 * lrow : 0;       // its first P_LL row
+  const int rt_l = dt_rowterm<RB>(q0), ct_l = dt_colterm<RB>(q0), sb_l = dt_slot<RB>(0, (q0 * 43) >> 9);
+  const int hq0 = dt_hidx<RB>(q0);
   const int ld = a.st.ld, L = a.io.L, T_steps = a.io.T, M = a.io.M;
   const int Lp = (L + 1) & ~1;
   const EkfConst& k = a.k;
@@ -336,7 +397,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
     double* gx = a.st.x + (size_t)f * a.st.xs;
     const double* grec = a.io.records + (size_t)f * T_steps * L;
     int n_lm = a.st.nlm[f];
-    int npend = 0;
+    int cnt = 0, ap_o = 0, ap_f = 0;   // history entries created; entries applied to the tiles of the non-front warps / the front warp
     int dropped = 0;
     // ---- load: HBM (external layout, lower triangle, column by column) -> shared memory ------------
     {
@@ -369,6 +430,16 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
     // Reads the pose / P_RR left by the previous update, applies the eager downdate of P_RR if that was
     // an Old update (or compass), then doPropagation's scalars, the propagated pose and P_RR, and the
     // landmark-independent part of the first measurement's update.
+    // Apply history entries [from, to) to this thread's tile.
+    auto sweep_own = [&](int from, int to) {
+      if (is_tile && 4 * I < 2 * n_lm && from < to) dt_sweep_tile<RB>(Tt, sm, I, J, from, to);
+    };
+    // Every warp brings its tiles up to date (CTA-wide: New associations, a full history ring, end of run).
+    auto flush_all = [&]() {
+      sweep_own(front ? ap_f : ap_o, cnt);
+      ap_f = ap_o = cnt;
+      __syncthreads();
+    };
     auto prr_eager = [&](int slot) {               // lanes 0..8: P_RR(i,j) += u_i . W_j of pending update `slot`
       if (lane < 9) {
         const int i = lane % 3, j = lane / 3;
@@ -380,21 +451,31 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
       }
       __syncwarp();
     };
+    // Record-only scalars of a step (kalmanfilter.cpp:17-37): evaluated while the front warp gates.
+    auto helper_pre = [&](const double* rec) {
+      dt_cp_async_wait_all();
+      __syncwarp();
+      if (lane == 0) dt_helper_pre<RB>(sm, rec, k);
+      __syncwarp();
+    };
     auto helper_chain = [&](const double* rec) {
+      // operands that do not depend on the headings are loaded first
+      const int e = lane % 9, i = e % 3, j = e / 3;
+      double PRR[9], Q[4];
+#pragma unroll
+      for (int w = 0; w < 9; ++w) PRR[w] = sm.PRR[w];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) Q[w] = sm.pre.Q[w];
+      double sn = 0.0, cs = 1.0;
+      PropSetup ps;
       if (lane < 2) {
-        const double RTV = rec[1] * k.deg2rad_pi / 180.0;
-        const double phi = lane == 0 ? sm.xr[2] : sm.xr[2] + rec[2] * RTV;   // same expression as the pose update
-        double sn, cs;
+        const double phi = lane == 0 ? sm.xr[2] : sm.xr[2] + sm.pre_dphi;   // same expression as the pose update
+        if (lane == 0) ps = sm.pre;
         sincos(phi, &sn, &cs);
         if (lane == 0) {
-          PropSetup ps;
-          ekf_build_prop_sc(ps, rec[0], rec[1], rec[2], sn, cs, k);
-          sm.prop = ps;
-          sm.PhiS[0] = 1.0; sm.PhiS[1] = 0.0; sm.PhiS[2] = 0.0;           // Propagate.cpp:42-44
-          sm.PhiS[3] = 0.0; sm.PhiS[4] = 1.0; sm.PhiS[5] = 0.0;
-          sm.PhiS[6] = ps.phi02; sm.PhiS[7] = ps.phi12; sm.PhiS[8] = 1.0;
-          sm.GS[0] = ps.g00; sm.GS[1] = ps.g10; sm.GS[2] = 0.0;            // :46-48
-          sm.GS[3] = 0.0; sm.GS[4] = 0.0; sm.GS[5] = ps.g21;
+          ekf_build_prop_trig(ps, sn, cs);
+          sm.prop.phi02 = ps.phi02;                                        // all the strip threads need (Propagate.cpp:56)
+          sm.prop.phi12 = ps.phi12;
           const double xm0 = ps.v * ps.c, xm1 = ps.v * ps.s, xm2 = ps.w;   // Propagate.cpp:33-37
           const double n0 = sm.xr[0] + ps.dt * xm0, n1 = sm.xr[1] + ps.dt * xm1, n2 = sm.xr[2] + ps.dt * xm2;
           sm.xr[0] = n0; sm.xr[1] = n1; sm.xr[2] = n2;
@@ -411,21 +492,41 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
           }
         }
       }
-      __syncwarp();
+      // Phi_R, G (Propagate.cpp:42-48) from lane 0, the update's rotation from lane 1, by shuffle
+      const double phi02 = __shfl_sync(0xffffffffu, ps.phi02, 0), phi12 = __shfl_sync(0xffffffffu, ps.phi12, 0);
+      const double g00 = __shfl_sync(0xffffffffu, ps.g00, 0), g10 = __shfl_sync(0xffffffffu, ps.g10, 0);
+      const double g21 = __shfl_sync(0xffffffffu, ps.g21, 0);
+      const double c1 = __shfl_sync(0xffffffffu, cs, 1), s1 = __shfl_sync(0xffffffffu, sn, 1);
       {
         // 3x3 robot block, one element per lane (Propagate.cpp:53, then :66-67)
-        const int e = lane % 9, i = e % 3, j = e / 3;
-        double PRR[9];
-#pragma unroll
-        for (int w = 0; w < 9; ++w) PRR[w] = sm.PRR[w];
-        const double mij = ekf_prop_prr_elem(sm.PhiS, sm.GS, sm.prop.Q, PRR, i, j);
+        const double Phi[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, phi02, phi12, 1.0};
+        const double G[6] = {g00, g10, 0.0, 0.0, 0.0, g21};
+        // the select-free form of ekf_prop_prr_elem(Phi, G, Q, PRR, i, j) for a lane-dependent (i, j)
+        const double Pi0 = i == 0 ? Phi[0] : (i == 1 ? Phi[1] : Phi[2]);
+        const double Pi3 = i == 0 ? Phi[3] : (i == 1 ? Phi[4] : Phi[5]);
+        const double Pi6 = i == 0 ? Phi[6] : (i == 1 ? Phi[7] : Phi[8]);
+        const double Pj0 = j == 0 ? Phi[0] : (j == 1 ? Phi[1] : Phi[2]);
+        const double Pj3 = j == 0 ? Phi[3] : (j == 1 ? Phi[4] : Phi[5]);
+        const double Pj6 = j == 0 ? Phi[6] : (j == 1 ? Phi[7] : Phi[8]);
+        const double Gi0 = i == 0 ? G[0] : (i == 1 ? G[1] : G[2]), Gi3 = i == 0 ? G[3] : (i == 1 ? G[4] : G[5]);
+        const double Gj0 = j == 0 ? G[0] : (j == 1 ? G[1] : G[2]), Gj3 = j == 0 ? G[3] : (j == 1 ? G[4] : G[5]);
+        const double t10 = (Pi0 * PRR[0] + Pi3 * PRR[1]) + Pi6 * PRR[2];
+        const double t11 = (Pi0 * PRR[3] + Pi3 * PRR[4]) + Pi6 * PRR[5];
+        const double t12 = (Pi0 * PRR[6] + Pi3 * PRR[7]) + Pi6 * PRR[8];
+        const double t2 = (t10 * Pj0 + t11 * Pj3) + t12 * Pj6;
+        const double t30 = Gi0 * Q[0] + Gi3 * Q[1];
+        const double t31 = Gi0 * Q[2] + Gi3 * Q[3];
+        const double t4 = t30 * Gj0 + t31 * Gj3;
+        const double mij = t2 + t4;
         const double mji = __shfl_sync(0xffffffffu, mij, j + 3 * i);
         const double pn = 0.5 * (mij + mji);
         const int qe = e % 6, qi = qe % 2, qj = qe / 2;
         const double p0j = __shfl_sync(0xffffffffu, pn, 0 + 3 * qj);
         const double p1j = __shfl_sync(0xffffffffu, pn, 1 + 3 * qj);
-        const double qv = sm.upd.mCt[qi] * p0j + sm.upd.mCt[qi + 2] * p1j;
-        __syncwarp();
+        // mCt = -1.0 * C^T, C^T = {c, -s, s, c} (ekf_build_trig_sc): mCt[qi], mCt[qi + 2]
+        const double mct_a = qi == 0 ? -1.0 * c1 : -1.0 * (-s1);
+        const double mct_b = qi == 0 ? -1.0 * s1 : -1.0 * c1;
+        const double qv = mct_a * p0j + mct_b * p1j;
         if (lane < 9) {
           sm.PRR[e] = pn;
           sm.upd.PRR[e] = pn;
@@ -433,34 +534,52 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
         }
       }
     };
-    if (helper) helper_chain(recbuf);
     bool setup_valid = true;
+    bool pre_done = false;        // helper_pre already ran for the record of the coming step
+    bool sync_first = false;      // the previous step ended on a New association: its row threads still read P_RR
 
     for (int t = 0; t < T_steps; ++t) {
       const double* cur = recbuf + (size_t)(t & 1) * Lp;
-      if (t + 1 < T_steps) {
-        const double* g = grec + (size_t)(t + 1) * L;
-        double* nxt = recbuf + (size_t)((t + 1) & 1) * Lp;
-        for (int i = tid; i < L; i += DT_THREADS) dt_cp_async8(nxt + i, g + i);
+      // ---- helper warp: landmark-independent part of this step (the one call site of helper_chain).
+      // After an Old update the helper warp gets here straight from B3 (it has no gain rows), so this
+      // runs beside the other warps' gain phase of the previous step.
+      if (sync_first) __syncthreads();
+      if (helper) {
+        if (!pre_done) helper_pre(cur);
+        if (t > 0 && a.io.pose_trace && lane == 0) {     // slam.cpp:181 for the previous step, before the pose is propagated
+          double* pt = a.io.pose_trace + ((size_t)f * T_steps + t - 1) * 3;
+          pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
+        }
+        __syncwarp();
+        helper_chain(cur);
+        if (t + 1 < T_steps) {                           // the helper warp owns the record prefetch
+          const double* g = grec + (size_t)(t + 1) * L;
+          double* nxt = recbuf + (size_t)((t + 1) & 1) * Lp;
+          for (int i = lane; i < L; i += 32) dt_cp_async8(nxt + i, g + i);
+        }
       }
-      const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
+      pre_done = false;
+      sync_first = false;
+      setup_valid = true;
       DTILE_TS(0);
-      __syncthreads();                                   // B1: helper results of this step visible
+      __syncthreads();                                   // B1: helper results of this step (and its record) visible
+      const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
       // ---- doPropagation, strip part (Propagate.cpp:56-60) ------------------------------------------
       if (q < 2 * n_lm) {
         double a0 = sm.SR[0][q], a1 = sm.SR[1][q], a2 = sm.SR[2][q];
         ekf_prop_col(sm.prop, a0, a1, a2);
         sm.SR[0][q] = a0; sm.SR[1][q] = a1; sm.SR[2][q] = a2;
       }
-      bool next_ready = false;                           // helper chain of step t+1 already issued
       // ---- doUpdateCompass (slam.cpp:144-147, kalmanfilter.cpp:96-130): a rank-1 pending update -----
       if (cur[6] != 0.0) {
+        if (cnt - min(ap_o, ap_f) > KH - 1) flush_all();   // no free history slot
+        const int sl = cnt & (KH - 1);
         if (tid == 0) {
           sm.dec.cres = ekf_compass_residual(sm.xr[2], cur[3], k);
           sm.dec.cS = sm.PRR[8] + cur[4];
-          sm.hs0[npend] = sm.dec.cS < 0 ? 0u : 0x80000000u;
-          sm.hs1[npend] = 0u;
-          sm.hrank[npend] = 1;
+          sm.hs0[sl] = sm.dec.cS < 0 ? 0u : 0x80000000u;
+          sm.hs1[sl] = 0u;
+          sm.hrank[sl] = 1;
         }
         __syncthreads();
         {
@@ -472,7 +591,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
               sm.xl[q] = sm.xl[q] + res * Ki;
               w = make_double2(sq * Ki, 0.0);
             }
-            sm.H[npend][q] = w;
+            sm.H[sl][hq] = w;
           } else if (tid < NQ + 3) {
             const int r = tid - NQ;
             const double Ki = invS * sm.PRR[r + 6];
@@ -482,31 +601,26 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
         }
         __syncthreads();
         if (q < 2 * n_lm) {                              // eager rank-1 downdate of strip and diagonal blocks
-          const unsigned s0 = sm.hs0[npend];
-          const double2* Hc = sm.H[npend];
-          const double u0 = dt_flip(Hc[q].x, s0);
+          const unsigned s0 = sm.hs0[sl];
+          const double2* Hc = sm.H[sl];
+          const double u0 = dt_flip(Hc[hq].x, s0);
 #pragma unroll
           for (int j = 0; j < 3; ++j) sm.SR[j][q] = fma(u0, sm.dec.WR[j].x, sm.SR[j][q]);
           const int aa = q & 3, l = q >> 1, m = q >> 2;
-          if ((aa & 1) == 0) sm.Dd[0][l] = fma(u0, Hc[q].x, sm.Dd[0][l]);
+          if ((aa & 1) == 0) sm.Dd[0][l] = fma(u0, Hc[hq].x, sm.Dd[0][l]);
           else {
-            sm.Dd[1][l] = fma(u0, Hc[q - 1].x, sm.Dd[1][l]);
-            sm.Dd[2][l] = fma(u0, Hc[q].x, sm.Dd[2][l]);
+            sm.Dd[1][l] = fma(u0, Hc[hq - HP].x, sm.Dd[1][l]);
+            sm.Dd[2][l] = fma(u0, Hc[hq].x, sm.Dd[2][l]);
           }
           if (aa >= 2) {
-            sm.Do[(aa & 1)][m] = fma(u0, Hc[4 * m].x, sm.Do[(aa & 1)][m]);
-            sm.Do[(aa & 1) + 2][m] = fma(u0, Hc[4 * m + 1].x, sm.Do[(aa & 1) + 2][m]);
+            sm.Do[(aa & 1)][m] = fma(u0, Hc[m].x, sm.Do[(aa & 1)][m]);
+            sm.Do[(aa & 1) + 2][m] = fma(u0, Hc[HP + m].x, sm.Do[(aa & 1) + 2][m]);
           }
         }
-        if (helper) prr_eager(npend);
-        npend += 1;
+        if (helper) prr_eager(sl);
+        cnt += 1;
         setup_valid = false;
         __syncthreads();
-        if (npend == KH) {
-          if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
-          npend = 0;
-          __syncthreads();
-        }
       }
 
       // ---- doUpdate per measurement (slam.cpp:150-171, Update.cpp:80-195) -------------------------
@@ -523,9 +637,10 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
         const double* zr = cur + 8 + 6 * m;
         __syncthreads();                                 // B2: strip propagated / previous update complete
         DTILE_TS(1);
-        if (front) {
-          // ================= front warp: gating + decision =========================================
-          if (!setup_valid) {
+        const bool two_warps = n_lm > 32;                 // landmarks 32.. are screened by the second gating warp
+        const bool gate_warp = front || (front2 && two_warps);
+        if (!setup_valid) {                                // pose / P_RR changed since the helper built sm.upd
+          if (front) {
             if (lane == 0) {
               UpdateSetup u;
               double PRR[9];
@@ -535,27 +650,47 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
             }
             __syncwarp();
           }
+          if (gate_warp && two_warps) dt_bar_sync(1, 64);
+        }
+        // ================= screen: one landmark per lane on the gating warps ==============================
+        double tl = INFINITY, th = INFINITY;
+        int st = 1;
+        if (gate_warp) {
           const UpdateSetup& u = sm.upd;
           ScreenU w;
           dt_screen_setup(w, u, k.cond_max);
+          const int lm = lane + (front ? 0 : 32);
+          if (lm < n_lm) {
+            const double2 xy = *reinterpret_cast<const double2*>(&sm.xl[2 * lm]);
+            double sr[6], dd[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const double2 v = *reinterpret_cast<const double2*>(&sm.SR[j][2 * lm]);
+              sr[2 * j] = v.x; sr[2 * j + 1] = v.y;
+            }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) dd[e] = sm.Dd[e][lm];
+            dt_screen(w, xy.x, xy.y, sr, dd, tl, th, st);
+          }
+        }
+        if (front2 && two_warps) {
+          sm.scr_tlo[lane] = tl; sm.scr_thi[lane] = th; sm.scr_state[lane] = st;
+          dt_bar_arrive(2, 64);
+        }
+        // While the front warp gates (it reads no tiles), the other warps bring their tiles up to date.
+        const bool osweep = cnt - ap_o >= KH - 1;
+        if (!front && osweep) sweep_own(ap_o, cnt);
+        if (osweep) ap_o = cnt;
+        if (front) {
+          // ================= front warp: candidates, exact evaluation, decision =========================
+          const UpdateSetup& u = sm.upd;
           double tlo[2], thi[2];
           int state[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int lm = lane + 32 * h;
-            tlo[h] = INFINITY; thi[h] = INFINITY; state[h] = 1;
-            if (lm < n_lm) {
-              const double2 xy = *reinterpret_cast<const double2*>(&sm.xl[2 * lm]);
-              double sr[6], dd[3];
-#pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                const double2 v = *reinterpret_cast<const double2*>(&sm.SR[j][2 * lm]);
-                sr[2 * j] = v.x; sr[2 * j + 1] = v.y;
-              }
-#pragma unroll
-              for (int e = 0; e < 3; ++e) dd[e] = sm.Dd[e][lm];
-              dt_screen(w, xy.x, xy.y, sr, dd, tlo[h], thi[h], state[h]);
-            }
+          tlo[0] = tl; thi[0] = th; state[0] = st;
+          tlo[1] = INFINITY; thi[1] = INFINITY; state[1] = 1;
+          if (two_warps) {
+            dt_bar_sync(2, 64);
+            tlo[1] = sm.scr_tlo[lane]; thi[1] = sm.scr_thi[lane]; state[1] = sm.scr_state[lane];
           }
           DTILE_TS(2);
           // upper bound of the minimum over the landmarks that are kept for sure
@@ -569,17 +704,45 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
           }
           const unsigned mA = __ballot_sync(0xffffffffu, flag[0]), mB = __ballot_sync(0xffffffffu, flag[1]);
           const int nA = __popc(mA), nTot = nA + __popc(mB);
-          if (flag[0]) sm.list[__popc(mA & ((1u << lane) - 1))] = lane;
-          if (flag[1]) sm.list[nA + __popc(mB & ((1u << lane) - 1))] = lane + 32;
-          __syncwarp();
-          // exact evaluation (reference operation order), four lanes per candidate
+          const bool single = nTot == 1;                  // the normal case: one landmark survives the screen
+          if (nTot > 1) {
+            if (flag[0]) sm.list[__popc(mA & ((1u << lane) - 1))] = lane;
+            if (flag[1]) sm.list[nA + __popc(mB & ((1u << lane) - 1))] = lane + 32;
+            __syncwarp();
+          }
+          // winner of the exact evaluation (reference operation order, Update.cpp:108-147)
           double bval = INFINITY;
           int bidx = INT_MAX;
           double bres0 = 0, bres1 = 0, bS0 = 0, bS1 = 0, bS2 = 0, bS3 = 0, bh0 = 0, bh1 = 0;
+          double bSi0 = 0, bSi1 = 0, bSi2 = 0, bSi3 = 0;
+          // L D L^T of the winning S and the pose rows of P H^T (lanes 0..2); with a single candidate they
+          // are evaluated next to the gate so their latencies overlap
+          double ll = 0, sq0 = 0, sq1 = 0, d0 = 0, d1 = 0, M0 = 0, M1 = 0;
+          auto ldl = [&](double S0, double S1, double S3) {
+            d0 = S0; ll = S1 / S0; d1 = S3 - ll * S1;
+            sq0 = sqrt(fabs(d0)); sq1 = sqrt(fabs(d1));
+          };
+          auto pose_rows = [&](int c0, double h0, double h1) {   // Update.cpp:186: row r of P at the five gain columns
+            if (lane < 3) {
+              const int r = lane;
+              const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = h0;
+              const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = h1;
+              const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
+              const double p0 = sm.PRR[r], p1 = sm.PRR[r + 3], p2 = sm.PRR[r + 6];
+              const double pa = sm.SR[r][c0], pb = sm.SR[r][c0 + 1];
+              const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
+              const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
+              const double B0 = pa * c00 + pb * c10;
+              const double B1 = pa * c01 + pb * c11;
+              M0 = A0 + B0; M1 = A1 + B1;
+            }
+          };
+          // four lanes per candidate, eight candidates per round; with a single candidate every quad
+          // evaluates it, so no reduction or broadcast is needed
           for (int base = 0; base < nTot; base += 8) {
             const int gi = base + (lane >> 2), e = lane & 3;
-            const bool have = gi < nTot;
-            const int lm = have ? sm.list[gi] : 0;
+            const bool have = single || gi < nTot;
+            const int lm = single ? (mA ? __ffs(mA) - 1 : 31 + __ffs(mB)) : (have ? sm.list[gi] : 0);
             GatePre pre;
             double p[6], pll[4];
             {
@@ -593,6 +756,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
               pll[0] = sm.Dd[0][lm]; pll[1] = p10; pll[2] = p10; pll[3] = sm.Dd[2][lm];
               ekf_gate_prelude(u, xy.x, xy.y, pre);
             }
+            if (single) pose_rows(2 * lm, pre.HR[4], pre.HR[5]);
             const double Sk = ekf_gate_S_element(u, pre, p, pll, e);
             double Sraw[4];
 #pragma unroll
@@ -602,24 +766,37 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
             const bool valid = have && !g.skip && (k.mahal_init > g.d2);   // Update.cpp:131,140
             const double val = valid ? g.d2 : INFINITY;
             const int my_idx = valid ? 3 + 2 * lm : INT_MAX;
-            int idx;
-            {   // warp argmin, lowest index wins ties (Update.cpp:140)
-              const unsigned long long key = dt_key(val + 0.0);
-              const unsigned long long mk = dt_warp_min_key(key);
-              idx = (int)__reduce_min_sync(0xffffffffu, key == mk ? (unsigned)my_idx : (unsigned)INT_MAX);
-            }
-            if (idx != INT_MAX) {
-              const int src = __ffs(__ballot_sync(0xffffffffu, my_idx == idx)) - 1;
-              const double cv = __shfl_sync(0xffffffffu, val, src);
-              const double c0 = __shfl_sync(0xffffffffu, g.res0, src), c1 = __shfl_sync(0xffffffffu, g.res1, src);
-              const double s0 = __shfl_sync(0xffffffffu, g.S[0], src), s1 = __shfl_sync(0xffffffffu, g.S[1], src);
-              const double s2 = __shfl_sync(0xffffffffu, g.S[2], src), s3 = __shfl_sync(0xffffffffu, g.S[3], src);
-              const double h0 = __shfl_sync(0xffffffffu, g.h3_0, src), h1 = __shfl_sync(0xffffffffu, g.h3_1, src);
-              if (cv < bval || (cv == bval && idx < bidx)) {
-                bval = cv; bidx = idx;
-                bres0 = c0; bres1 = c1; bS0 = s0; bS1 = s1; bS2 = s2; bS3 = s3; bh0 = h0; bh1 = h1;
+            if (single) {
+              ldl(g.S[0], g.S[1], g.S[3]);
+              bval = val; bidx = my_idx;
+              bres0 = g.res0; bres1 = g.res1; bS0 = g.S[0]; bS1 = g.S[1]; bS2 = g.S[2]; bS3 = g.S[3];
+              bh0 = g.h3_0; bh1 = g.h3_1;
+              bSi0 = g.Si[0]; bSi1 = g.Si[1]; bSi2 = g.Si[2]; bSi3 = g.Si[3];
+            } else {
+              int idx;
+              {   // warp argmin, lowest index wins ties (Update.cpp:140)
+                const unsigned long long key = dt_key(val + 0.0);
+                const unsigned long long mk = dt_warp_min_key(key);
+                idx = (int)__reduce_min_sync(0xffffffffu, key == mk ? (unsigned)my_idx : (unsigned)INT_MAX);
+              }
+              if (idx != INT_MAX) {
+                const int src = __ffs(__ballot_sync(0xffffffffu, my_idx == idx)) - 1;
+                const double cv = __shfl_sync(0xffffffffu, val, src);
+                if (cv < bval || (cv == bval && idx < bidx)) {
+                  bval = cv; bidx = idx;
+                  bres0 = __shfl_sync(0xffffffffu, g.res0, src); bres1 = __shfl_sync(0xffffffffu, g.res1, src);
+                  bS0 = __shfl_sync(0xffffffffu, g.S[0], src); bS1 = __shfl_sync(0xffffffffu, g.S[1], src);
+                  bS2 = __shfl_sync(0xffffffffu, g.S[2], src); bS3 = __shfl_sync(0xffffffffu, g.S[3], src);
+                  bh0 = __shfl_sync(0xffffffffu, g.h3_0, src); bh1 = __shfl_sync(0xffffffffu, g.h3_1, src);
+                  bSi0 = __shfl_sync(0xffffffffu, g.Si[0], src); bSi1 = __shfl_sync(0xffffffffu, g.Si[1], src);
+                  bSi2 = __shfl_sync(0xffffffffu, g.Si[2], src); bSi3 = __shfl_sync(0xffffffffu, g.Si[3], src);
+                }
               }
             }
+          }
+          if (!single && bidx != INT_MAX) {
+            ldl(bS0, bS1, bS3);
+            pose_rows(bidx - 3, bh0, bh1);
           }
           DTILE_TS(3);
           // ---- decision (Update.cpp:152,181,191) -----------------------------------------------------
@@ -631,39 +808,26 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
           DDec& dc = sm.dec;
           if (decision == EKF_DEC_OLD) {
             const int c0 = opt_i - 3;
-            // S^-1 and L D L^T of the winning S (all lanes, same values)
-            const double Sm[4] = {bS0, bS1, bS2, bS3};
-            double Si[4];
-            ekf_inv2(Sm, Si);
-            const double d0 = Sm[0], l = Sm[1] / Sm[0], d1 = Sm[3] - l * Sm[1];
-            const double sq0 = sqrt(fabs(d0)), sq1 = sqrt(fabs(d1));
             const unsigned s0m = d0 < 0 ? 0u : 0x80000000u, s1m = d1 < 0 ? 0u : 0x80000000u;
             if (lane < 3) {
-              // pose rows of the gain (Update.cpp:186-187): row r of P at the five gain columns
+              // pose rows of the gain, pose correction, downdate vector (Update.cpp:186-187)
               const int r = lane;
-              const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = bh0;
-              const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = bh1;
-              const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
-              const double p0 = sm.PRR[r], p1 = sm.PRR[r + 3], p2 = sm.PRR[r + 6];
-              const double pa = sm.SR[r][c0], pb = sm.SR[r][c0 + 1];
-              const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
-              const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
-              const double B0 = pa * c00 + pb * c10;
-              const double B1 = pa * c01 + pb * c11;
-              const double M0 = A0 + B0, M1 = A1 + B1;
-              const double K0 = M0 * Si[0] + M1 * Si[1];
-              const double K1 = M0 * Si[2] + M1 * Si[3];
+              const double K0 = M0 * bSi0 + M1 * bSi1;
+              const double K1 = M0 * bSi2 + M1 * bSi3;
               sm.xr[r] = sm.xr[r] + (K0 * bres0 + K1 * bres1);
-              dc.WR[r] = make_double2(sq0 * fma(l, K1, K0), sq1 * K1);
+              dc.WR[r] = make_double2(sq0 * fma(ll, K1, K0), sq1 * K1);
             }
             if (lane == 0) {
               dc.c0 = c0;
+              dc.rt_c0 = dt_rowterm<RB>(c0);
+              dc.ct_c0 = dt_colterm<RB>(c0);
+              dc.sb_c0 = dt_slot<RB>(0, (c0 * 43) >> 9);
               dc.h3[0] = bh0; dc.h3[1] = bh1;
               dc.res[0] = bres0; dc.res[1] = bres1;
-              dc.Si[0] = Si[0]; dc.Si[1] = Si[1]; dc.Si[2] = Si[2]; dc.Si[3] = Si[3];
-              dc.l = l; dc.sq0 = sq0; dc.sq1 = sq1;
+              dc.Si[0] = bSi0; dc.Si[1] = bSi1; dc.Si[2] = bSi2; dc.Si[3] = bSi3;
+              dc.l = ll; dc.sq0 = sq0; dc.sq1 = sq1;
               dc.sm0 = s0m; dc.sm1 = s1m;
-              sm.hs0[npend] = s0m; sm.hs1[npend] = s1m; sm.hrank[npend] = 2;
+              { const int sl = cnt & (KH - 1); sm.hs0[sl] = s0m; sm.hs1[sl] = s1m; sm.hrank[sl] = 2; }
             }
           } else if (decision == EKF_DEC_NEW) {
             index = 3 + 2 * n_lm;
@@ -708,118 +872,136 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
         }
         DTILE_TS(4);
         const bool last_meas = m == nz - 1;
-        if (last_meas) dt_cp_async_wait_all();           // next step's record visible after the barrier
-        __syncthreads();                                 // B3: decision published
+        if (helper && last_meas && t + 1 < T_steps) helper_pre(recbuf + (size_t)((t + 1) & 1) * Lp);   // idle window of the helper warp
+        if (last_meas && t + 1 < T_steps) pre_done = true;
+        __syncthreads();                                 // B3: decision published (and the next record visible)
         DTILE_TS(5);
         const int decision = sm.dec.decision;
         setup_valid = false;
         if (decision == EKF_DEC_OLD) {
-          const int np = npend;
+          if (cnt - min(ap_o, ap_f) > KH - 1) flush_all();   // no free history slot (compass / several measurements per step)
+          const int sl = cnt & (KH - 1);
+          const bool fsweep = cnt - ap_f >= KH - 1;          // the front warp sweeps its tiles behind the row threads' reads
           const DDec& dc = sm.dec;
-          // ---- gain rows, state, downdate vector (Update.cpp:186-187), one P_LL row per thread -----
-          const bool row = q < 2 * n_lm;
-          double2 w = make_double2(0.0, 0.0);
-          double u0 = 0.0, u1 = 0.0;
-          if (row) {
-            const int c0 = dc.c0;
-            const double p0 = sm.SR[0][q], p1 = sm.SR[1][q], p2 = sm.SR[2][q];
-            double pa, pb;
-            if ((q >> 2) == (c0 >> 2)) {                 // same aligned pair: eager entries, already current
-              if ((q >> 1) == (c0 >> 1)) {
-                const int l = q >> 1;
-                pa = (q & 1) ? sm.Dd[1][l] : sm.Dd[0][l];
-                pb = (q & 1) ? sm.Dd[2][l] : sm.Dd[1][l];
+          if (helper) {
+            // ---- P_RR downdate ----------------------------------------------------------------------------
+            prr_eager(sl);                               // then straight on to the next step's chain (top of the loop)
+          }
+          if (rows_warp) {
+            // ---- gain rows, state, downdate vectors (Update.cpp:186-187): one landmark (two rows) per thread
+            const bool live = lrow < n_lm;
+            double2 wA = make_double2(0.0, 0.0), wB = make_double2(0.0, 0.0);
+            double uA0 = 0.0, uA1 = 0.0, uB0 = 0.0, uB1 = 0.0;
+            if (live) {
+              const int c0 = dc.c0, hc0 = dt_hidx<RB>(c0);
+              const double2 s0 = *reinterpret_cast<const double2*>(&sm.SR[0][q0]);
+              const double2 s1 = *reinterpret_cast<const double2*>(&sm.SR[1][q0]);
+              const double2 s2 = *reinterpret_cast<const double2*>(&sm.SR[2][q0]);
+              double paA, pbA, paB, pbB;                 // P(q0, c0), P(q0, c0+1), P(q0+1, c0), P(q0+1, c0+1)
+              if ((q0 >> 2) == (c0 >> 2)) {              // same aligned pair: eager entries, already current
+                if (q0 == c0) {
+                  const double d1v = sm.Dd[1][lrow];
+                  paA = sm.Dd[0][lrow]; pbA = d1v; paB = d1v; pbB = sm.Dd[2][lrow];
+                } else {
+                  const int m2 = q0 >> 2;
+                  const double e0 = sm.Do[0][m2], e1 = sm.Do[1][m2], e2 = sm.Do[2][m2], e3 = sm.Do[3][m2];
+                  if (c0 & 2) { paA = e0; pbA = e1; paB = e2; pbB = e3; }   // this landmark is the pair's first: P(4m+j, 4m+2+i) = Do[i+2j]
+                  else { paA = e0; pbA = e2; paB = e1; pbB = e3; }          // this landmark is the second: P(4m+2+i, 4m+j) = Do[i+2j]
+                }
               } else {
-                const int m2 = q >> 2;
-                if (c0 & 2) {                            // associated landmark is the pair's second: P(q, 4m+2+i) = Do[i + 2(q&1)]
-                  pa = sm.Do[2 * (q & 1)][m2];
-                  pb = sm.Do[2 * (q & 1) + 1][m2];
-                } else {                                 // first: P(4m+2+i, 4m+j) = Do[i + 2j], i = q&1
-                  pa = sm.Do[(q & 1)][m2];
-                  pb = sm.Do[(q & 1) + 2][m2];
+                // stored tile entries + the pending downdates of that tile, in order (the deferred sweep's fma sequence)
+                int tslot;
+                if (q0 > c0) {
+                  const int ad = rt_l + dc.ct_c0;        // (q0, c0)
+                  paA = T[ad]; pbA = T[ad + 4 * PS + 1]; paB = T[ad + PS]; pbB = T[ad + 5 * PS + 1];
+                  tslot = dc.sb_c0 + (q0 >> 2);
+                } else {
+                  const int ad = dc.rt_c0 + ct_l;        // (c0, q0)
+                  paA = T[ad]; pbA = T[ad + PS]; paB = T[ad + 4 * PS + 1]; pbB = T[ad + 5 * PS + 1];
+                  tslot = sb_l + (c0 >> 2);
+                }
+                const int efrom = (tslot >> 5) == rot ? ap_f : ap_o;   // what the tile's owner has applied so far
+                for (int en = efrom; en < cnt; ++en) {
+                  const int p = en & (KH - 1);
+                  const double2 wqa = sm.H[p][hq0], wqb = sm.H[p][hq0 + HP], wa = sm.H[p][hc0], wb = sm.H[p][hc0 + HP];
+                  const unsigned m0 = sm.hs0[p], m1 = sm.hs1[p];
+                  const double va0 = dt_flip(wqa.x, m0), va1 = dt_flip(wqa.y, m1);
+                  const double vb0 = dt_flip(wqb.x, m0), vb1 = dt_flip(wqb.y, m1);
+                  if (sm.hrank[p] == 2) {
+                    paA = fma(va1, wa.y, paA); pbA = fma(va1, wb.y, pbA);
+                    paB = fma(vb1, wa.y, paB); pbB = fma(vb1, wb.y, pbB);
+                  }
+                  paA = fma(va0, wa.x, paA); pbA = fma(va0, wb.x, pbA);
+                  paB = fma(vb0, wa.x, paB); pbB = fma(vb0, wb.x, pbB);
                 }
               }
-            } else {
-              // stored tile entries + the pending downdates, in order (the deferred sweep's fma sequence)
-              if (q > c0) { pa = T[dt_addr<RB>(q, c0)]; pb = T[dt_addr<RB>(q, c0 + 1)]; }
-              else { pa = T[dt_addr<RB>(c0, q)]; pb = T[dt_addr<RB>(c0 + 1, q)]; }
-              for (int p = 0; p < np; ++p) {
-                const double2 wq = sm.H[p][q], wa = sm.H[p][c0], wb = sm.H[p][c0 + 1];
-                const double v0 = dt_flip(wq.x, sm.hs0[p]), v1 = dt_flip(wq.y, sm.hs1[p]);
-                if (sm.hrank[p] == 2) { pa = fma(v1, wa.y, pa); pb = fma(v1, wb.y, pb); }
-                pa = fma(v0, wa.x, pa);
-                pb = fma(v0, wb.x, pb);
+              const double h00 = dc.mCt[0], h01 = dc.mCt[2], h02 = dc.h3[0];
+              const double h10 = dc.mCt[1], h11 = dc.mCt[3], h12 = dc.h3[1];
+              const double c00 = dc.Ct[0], c10 = dc.Ct[2], c01 = dc.Ct[1], c11 = dc.Ct[3];
+              const double2 w0 = dc.WR[0], w1 = dc.WR[1], w2 = dc.WR[2];
+              {   // row q0
+                const double A0 = (s0.x * h00 + s1.x * h01) + s2.x * h02;
+                const double A1 = (s0.x * h10 + s1.x * h11) + s2.x * h12;
+                const double B0 = paA * c00 + pbA * c10;
+                const double B1 = paA * c01 + pbA * c11;
+                const double M0 = A0 + B0, M1 = A1 + B1;
+                const double K0 = M0 * dc.Si[0] + M1 * dc.Si[1];
+                const double K1 = M0 * dc.Si[2] + M1 * dc.Si[3];
+                sm.xl[q0] = sm.xl[q0] + (K0 * dc.res[0] + K1 * dc.res[1]);
+                wA = make_double2(dc.sq0 * fma(dc.l, K1, K0), dc.sq1 * K1);
+                uA0 = dt_flip(wA.x, dc.sm0); uA1 = dt_flip(wA.y, dc.sm1);
+              }
+              {   // row q0 + 1
+                const double A0 = (s0.y * h00 + s1.y * h01) + s2.y * h02;
+                const double A1 = (s0.y * h10 + s1.y * h11) + s2.y * h12;
+                const double B0 = paB * c00 + pbB * c10;
+                const double B1 = paB * c01 + pbB * c11;
+                const double M0 = A0 + B0, M1 = A1 + B1;
+                const double K0 = M0 * dc.Si[0] + M1 * dc.Si[1];
+                const double K1 = M0 * dc.Si[2] + M1 * dc.Si[3];
+                sm.xl[q0 + 1] = sm.xl[q0 + 1] + (K0 * dc.res[0] + K1 * dc.res[1]);
+                wB = make_double2(dc.sq0 * fma(dc.l, K1, K0), dc.sq1 * K1);
+                uB0 = dt_flip(wB.x, dc.sm0); uB1 = dt_flip(wB.y, dc.sm1);
+              }
+              // eager downdate of the strip rows and of the landmark's own 2x2 block (Update.cpp:188,193-194)
+              *reinterpret_cast<double2*>(&sm.SR[0][q0]) = make_double2(fma(uA0, w0.x, fma(uA1, w0.y, s0.x)), fma(uB0, w0.x, fma(uB1, w0.y, s0.y)));
+              *reinterpret_cast<double2*>(&sm.SR[1][q0]) = make_double2(fma(uA0, w1.x, fma(uA1, w1.y, s1.x)), fma(uB0, w1.x, fma(uB1, w1.y, s1.y)));
+              *reinterpret_cast<double2*>(&sm.SR[2][q0]) = make_double2(fma(uA0, w2.x, fma(uA1, w2.y, s2.x)), fma(uB0, w2.x, fma(uB1, w2.y, s2.y)));
+              sm.Dd[0][lrow] = fma(uA0, wA.x, fma(uA1, wA.y, sm.Dd[0][lrow]));
+              sm.Dd[1][lrow] = fma(uB0, wA.x, fma(uB1, wA.y, sm.Dd[1][lrow]));
+              sm.Dd[2][lrow] = fma(uB0, wB.x, fma(uB1, wB.y, sm.Dd[2][lrow]));
+            }
+            if (lrow < C::NL) {                          // zeros for landmarks beyond the live map
+              sm.H[sl][hq0] = wA;
+              sm.H[sl][hq0 + HP] = wB;
+            }
+            if (fsweep) dt_bar_arrive(3, 96);            // this warp's tile reads are done
+            {   // 2x2 block between the two landmarks of an aligned pair: rows of the odd one, columns of the even one
+              const double pAx = __shfl_up_sync(0xffffffffu, wA.x, 1), pAy = __shfl_up_sync(0xffffffffu, wA.y, 1);
+              const double pBx = __shfl_up_sync(0xffffffffu, wB.x, 1), pBy = __shfl_up_sync(0xffffffffu, wB.y, 1);
+              if (live && (lrow & 1)) {
+                const int m2 = lrow >> 1;
+                sm.Do[0][m2] = fma(uA0, pAx, fma(uA1, pAy, sm.Do[0][m2]));   // (4m+2, 4m)
+                sm.Do[1][m2] = fma(uB0, pAx, fma(uB1, pAy, sm.Do[1][m2]));   // (4m+3, 4m)
+                sm.Do[2][m2] = fma(uA0, pBx, fma(uA1, pBy, sm.Do[2][m2]));   // (4m+2, 4m+1)
+                sm.Do[3][m2] = fma(uB0, pBx, fma(uB1, pBy, sm.Do[3][m2]));   // (4m+3, 4m+1)
               }
             }
-            const double h00 = dc.mCt[0], h01 = dc.mCt[2], h02 = dc.h3[0];
-            const double h10 = dc.mCt[1], h11 = dc.mCt[3], h12 = dc.h3[1];
-            const double c00 = dc.Ct[0], c10 = dc.Ct[2], c01 = dc.Ct[1], c11 = dc.Ct[3];
-            const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
-            const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
-            const double B0 = pa * c00 + pb * c10;
-            const double B1 = pa * c01 + pb * c11;
-            const double M0 = A0 + B0, M1 = A1 + B1;
-            const double K0 = M0 * dc.Si[0] + M1 * dc.Si[1];
-            const double K1 = M0 * dc.Si[2] + M1 * dc.Si[3];
-            sm.xl[q] = sm.xl[q] + (K0 * dc.res[0] + K1 * dc.res[1]);
-            w = make_double2(dc.sq0 * fma(dc.l, K1, K0), dc.sq1 * K1);
-            u0 = dt_flip(w.x, dc.sm0);
-            u1 = dt_flip(w.y, dc.sm1);
-            // eager downdate of the strip row (Update.cpp:188,193-194)
-            const double2 w0 = dc.WR[0], w1 = dc.WR[1], w2 = dc.WR[2];
-            sm.SR[0][q] = fma(u0, w0.x, fma(u1, w0.y, p0));
-            sm.SR[1][q] = fma(u0, w1.x, fma(u1, w1.y, p1));
-            sm.SR[2][q] = fma(u0, w2.x, fma(u1, w2.y, p2));
           }
-          if (tid < NQ) sm.H[np][q] = w;                 // zero for rows beyond the live map
-          __syncwarp();
-          if (row) {                                     // eager downdate of the diagonal / pair blocks
-            const double2* Hc = sm.H[np];
-            const int aa = q & 3, l = q >> 1, m2 = q >> 2;
-            if ((aa & 1) == 0) {
-              sm.Dd[0][l] = fma(u0, w.x, fma(u1, w.y, sm.Dd[0][l]));
-            } else {
-              const double2 wl = Hc[q - 1];
-              sm.Dd[1][l] = fma(u0, wl.x, fma(u1, wl.y, sm.Dd[1][l]));
-              sm.Dd[2][l] = fma(u0, w.x, fma(u1, w.y, sm.Dd[2][l]));
-            }
-            if (aa >= 2) {
-              const double2 wa = Hc[4 * m2], wb = Hc[4 * m2 + 1];
-              sm.Do[(aa & 1)][m2] = fma(u0, wa.x, fma(u1, wa.y, sm.Do[(aa & 1)][m2]));
-              sm.Do[(aa & 1) + 2][m2] = fma(u0, wb.x, fma(u1, wb.y, sm.Do[(aa & 1) + 2][m2]));
-            }
+          if (front && fsweep) {
+            dt_bar_sync(3, 96);                          // both row warps have read the tiles
+            sweep_own(ap_f, cnt);
           }
-          if (helper) {
-            prr_eager(np);
-            if (last_meas && t + 1 < T_steps) {
-              if (a.io.pose_trace && lane == 0) {       // slam.cpp:181, before the pose is propagated
-                double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
-                pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
-              }
-              __syncwarp();
-              helper_chain(recbuf + (size_t)((t + 1) & 1) * Lp);
-            }
-          }
-          if (last_meas && t + 1 < T_steps) next_ready = true;
-          npend += 1;
-          if (npend == KH) {
-            __syncthreads();
-            DTILE_TS(6);
-            if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
-            npend = 0;
-            DTILE_TS(7);
-          }
+          if (fsweep) ap_f = cnt;
+          DTILE_TS(6);
+          cnt += 1;
         } else if (decision == EKF_DEC_NEW) {
           // ---- state augmentation (Update.cpp:152-178); pending downdates are applied first ----------
-          if (npend > 0) {
-            if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
-            npend = 0;
-            __syncthreads();
-          }
+          if (cnt > min(ap_o, ap_f)) flush_all();
           const DDec& dc = sm.dec;
-          const int q0 = 2 * n_lm;                       // P_LL rows of the new landmark
+          const int qn = 2 * n_lm;                       // P_LL rows of the new landmark
           const bool pose_row = tid >= NQ && tid < NQ + 3;
-          if (q < q0 || pose_row) {                      // P_xL = -P[:,0:3]*H_R^T*H_Li (:169), existing row
+          if (q < qn || pose_row) {                      // P_xL = -P[:,0:3]*H_R^T*H_Li (:169), existing row
             const double h00 = dc.mCt[0], h01 = dc.mCt[2], h02 = dc.h3n[0];
             const double h10 = dc.mCt[1], h11 = dc.mCt[3], h12 = dc.h3n[1];
             const double ct00 = dc.Ct[0], ct10 = dc.Ct[1], ct01 = dc.Ct[2], ct11 = dc.Ct[3];
@@ -830,43 +1012,21 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
             const double t0 = (q0v * h00 + q1v * h01) + q2v * h02;
             const double t1 = (q0v * h10 + q1v * h11) + q2v * h12;
             const double v0 = t0 * ct00 + t1 * ct10, v1 = t0 * ct01 + t1 * ct11;
-            if (pose_row) { const int r = tid - NQ; sm.SR[r][q0] = v0; sm.SR[r][q0 + 1] = v1; }
-            else { *pll_ref(q0, q) = v0; *pll_ref(q0 + 1, q) = v1; }
+            if (pose_row) { const int r = tid - NQ; sm.SR[r][qn] = v0; sm.SR[r][qn + 1] = v1; }
+            else { *pll_ref(qn, q) = v0; *pll_ref(qn + 1, q) = v1; }
           }
           if (tid == 0) {
             const double off = 0.5 * (dc.PLL[2] + dc.PLL[1]);   // :193-194 on the new 2x2 block
             sm.Dd[0][n_lm] = dc.PLL[0];
             sm.Dd[1][n_lm] = off;
             sm.Dd[2][n_lm] = dc.PLL[3];
-            sm.xl[q0] = dc.nl[0];
-            sm.xl[q0 + 1] = dc.nl[1];
+            sm.xl[qn] = dc.nl[0];
+            sm.xl[qn + 1] = dc.nl[1];
           }
           n_lm += 1;
+          sync_first = true;
         } else if (decision == EKF_DEC_DROPPED) {
           dropped = 1;
-        }
-      }
-      // ---- end of step: pose trace, and the next step's helper chain if no Old update issued it ----
-      if (t + 1 < T_steps) {
-        if (!next_ready) {
-          // the last measurement was not an Old update (or there was none): the pose is final now
-          if (nz == 0) dt_cp_async_wait_all();
-          __syncthreads();
-          if (helper) {
-            if (a.io.pose_trace && lane == 0) {
-              double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
-              pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
-            }
-            __syncwarp();
-            helper_chain(recbuf + (size_t)((t + 1) & 1) * Lp);
-          }
-        }
-        setup_valid = true;
-      } else {
-        __syncthreads();
-        if (a.io.pose_trace && tid == 0) {
-          double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
-          pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
         }
       }
       DTILE_TS(8);
@@ -874,11 +1034,11 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
 
     // ---- flush the pending downdates, write back to HBM (external layout, both triangles) ---------
     __syncthreads();
-    if (npend > 0) {
-      if (is_tile && 4 * I < 2 * n_lm) dt_sweep_tile<RB>(Tt, sm, I, J, npend);
-      npend = 0;
-      __syncthreads();
+    if (a.io.pose_trace && tid == 0 && T_steps > 0) {    // slam.cpp:181 for the last step
+      double* pt = a.io.pose_trace + ((size_t)f * T_steps + T_steps - 1) * 3;
+      pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
     }
+    flush_all();
     {
       const int n = 3 + 2 * n_lm;
       for (int c = warp; c < n; c += DT_THREADS / 32) {

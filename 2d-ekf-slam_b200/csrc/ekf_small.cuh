@@ -80,6 +80,7 @@ struct GateResult {
   double h3_0, h3_1;    // third column of H_R
   bool skip;            // cond >= cond_max (Update.cpp:131)
   double d2;            // res^T S^-1 res (only meaningful when !skip)
+  double Si[4];         // S^-1 as ekf_inv2 returns it (the same expressions): {i00, i10, i01, i11}
 };
 
 // ---- one iteration of the landmark loop, Update.cpp:103-136, in four separable pieces ------------
@@ -210,6 +211,7 @@ __device__ __forceinline__ void ekf_gate_from_S(const GatePre& pre, const double
   const double r0 = g.res0 * i00 + g.res1 * i10;
   const double r1 = g.res0 * i01 + g.res1 * i11;
   g.d2 = r0 * g.res0 + r1 * g.res1;
+  g.Si[0] = i00; g.Si[1] = i10; g.Si[2] = i01; g.Si[3] = i11;
 }
 
 __device__ __forceinline__ void ekf_gate_finish(const UpdateSetup& u, const GatePre& pre, const double* t12,
@@ -290,9 +292,10 @@ struct PropSetup {
   double g00, g10, g21; // G(0,0), G(1,0), G(2,1)
 };
 
-// (s, c) = sincos of the pre-propagation heading, computed by the caller.
-__device__ __forceinline__ void ekf_build_prop_sc(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,
-                                                  double s, double c, const EkfConst& k) {
+// The part of doPropagation's scalars that depends on the odometry record only (kalmanfilter.cpp:17-37):
+// it can be evaluated before the heading is known.
+__device__ __forceinline__ void ekf_build_prop_pre(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,
+                                                   const EkfConst& k) {
   const double RTV = rotvel_deg_s * k.deg2rad_pi / 180.0;   // kalmanfilter.cpp:19
   p.v = vel_mm_s / 1000.0;                                   // :26
   p.w = RTV;
@@ -304,12 +307,22 @@ __device__ __forceinline__ void ekf_build_prop_sc(PropSetup& p, double vel_mm_s,
   for (int i = 0; i < 4; ++i) A[i] = vv * Q0[i];
   for (int j = 0; j < 2; ++j)
     for (int i = 0; i < 2; ++i) p.Q[i + 2 * j] = A[i] * Q0[0 + 2 * j] + A[i + 2] * Q0[1 + 2 * j];
+}
+// The heading-dependent part (Propagate.cpp:42-48); (s, c) = sincos of the pre-propagation heading.
+__device__ __forceinline__ void ekf_build_prop_trig(PropSetup& p, double s, double c) {
+  const double dt = p.dt;
   p.s = s; p.c = c;
   p.phi02 = -dt * p.v * p.s;   // Propagate.cpp:42
   p.phi12 = dt * p.v * p.c;    // :43
   p.g00 = -dt * p.c;           // :46
   p.g10 = -dt * p.s;           // :47
   p.g21 = -dt;                 // :48
+}
+// (s, c) = sincos of the pre-propagation heading, computed by the caller.
+__device__ __forceinline__ void ekf_build_prop_sc(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,
+                                                  double s, double c, const EkfConst& k) {
+  ekf_build_prop_pre(p, vel_mm_s, rotvel_deg_s, dt, k);
+  ekf_build_prop_trig(p, s, c);
 }
 
 __device__ __forceinline__ void ekf_build_prop(PropSetup& p, double vel_mm_s, double rotvel_deg_s, double dt,

@@ -84,7 +84,8 @@ def core_lib():
     """The CUDA library. Raises if it has not been built (no fallback)."""
     global _core
     if _core is None:
-        path = os.path.join(LIB_DIR, "libekf_slam_b200.so")
+        # EKF_B200_LIB: profiling tooling only (instrumented builds, `make timing`); never a fallback
+        path = os.environ.get("EKF_B200_LIB") or os.path.join(LIB_DIR, "libekf_slam_b200.so")
         if not os.path.exists(path):
             raise EkfError(ERR_NO_DEVICE, "CUDA extension missing: %s (run __graft_entry__.build())" % path)
         L = C.CDLL(path)

@@ -62,6 +62,18 @@ def batch(F=592, T=1000, cap=50):
             mx = row[row > 0].max() - t0 if (row > 0).any() else 0
             print("  %-26s %s   %s" % (nm, cells, "" if prev is None else "%5d" % (mx - prev)))
             prev = mx
+    if os.environ.get("EKF_DTILE_TS"):      # -DEKF_DTILE_TIMING builds (make timing; EKF_B200_LIB=.../libekf_slam_b200_timing.so)
+        ts = ekf.debug_dtile_timestamps()
+        names = ["step start (before B1)", "after B2 (strip propagated)", "front: screen done", "front: exact pass done",
+                 "before B3 (front: decision published)", "after B3", "rows / helper chain done", "-", "step end",
+                 "sweep start (a step of 498..501)", "sweep end"]
+        t0 = ts[:, 0][ts[:, 0] > 0].min()
+        print("stamps of CTA 0, first filter, step 501 (cycles since the first warp entered the step); front warp = the one with stamps 2,3:")
+        print("  %-40s %s" % ("", " ".join("    w%d" % w for w in range(4))))
+        for kk, nm in enumerate(names):
+            row = ts[:, kk]
+            ref = t0 if kk < 9 else ts[:, 9][ts[:, 9] > 0].min() if (ts[:, 9] > 0).any() else t0
+            print("  %-40s %s" % (nm, " ".join("%6d" % (v - ref) if v > 0 else "     -" for v in row)))
     assert (out["final_nlm"] == 50).mean() > 0.99
     ms, n = fb.kernel_time()
     print("batch: F=%d T=%d avg kernel %.3f ms over %d launches -> %.3e filter-steps/s"
