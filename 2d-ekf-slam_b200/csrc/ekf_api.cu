@@ -109,8 +109,7 @@ int pick_batch_kernel(ekf_handle h) {
   if (want == EKF_BATCH_KERNEL_TILE) return cap <= ekf_tile_max_landmarks() ? 2 : -1;
   if (want == EKF_BATCH_KERNEL_STILE) return cap <= ekf_stile_max_landmarks() ? 3 : -1;
   if (want == EKF_BATCH_KERNEL_DTILE) return cap <= ekf_dtile_max_landmarks() ? 4 : -1;
-  if (cap <= ekf_dtile_max_landmarks()) return 4;
-  if (cap <= ekf_stile_max_landmarks()) return 3;
+  if (cap <= ekf_stile_max_landmarks()) return 3;   // measured fastest
   return 1;
 }
 

@@ -8,12 +8,12 @@
 //    (Update.cpp:188,193-194) and only READ when one of the two landmarks is the associated one
 //    (the two gain columns of Update.cpp:186) - the gating loop (Update.cpp:103-148) needs just the
 //    robot strip P_LR, P_RR and the 2x2 diagonal blocks. So P_LL is kept as "stored tiles + up to
-//    KH pending rank-2 updates": each Old update appends its downdate vector W to a history in
-//    shared memory, the strip / P_RR / diagonal blocks are updated eagerly (O(n)), the two gain
-//    columns are corrected on the fly when read, and the tiles are swept once per KH updates,
+//    three pending rank-2 updates": each Old update appends its downdate vector W to a history ring
+//    in shared memory, the strip / P_RR / diagonal blocks are updated eagerly (O(n)), the two gain
+//    columns are corrected on the fly when read, and the tiles are swept once per three updates,
 //    applying the pending updates to every element in order. Every element sees the same fma
 //    sequence as with an immediate sweep, so the bits are the same; the O(n^2) shared-memory
-//    traffic per update drops by KH.
+//    traffic per update drops by three.
 //  * Storage. Pose, P_RR (3x3), strip SR (3 x 2N), the 2x2 diagonal blocks Dd and the 2x2 block
 //    between the two landmarks of an aligned pair Do live in small arrays ("eager" entries). The
 //    rest of the lower triangle of P_LL lives in 4x12 tiles (row blocks of 4, column blocks of 12;
@@ -21,51 +21,42 @@
 //    tile (conflict-free for any plane), the column walk of the gain phase (consecutive rows) and
 //    the row walk (consecutive columns) both spread over the banks (PS = 12 mod 16 and the +b skew).
 //    108 tiles for 50 landmarks: four warps sweep them, one tile per lane.
-//  * Gating on one warp, exact on demand. The "front" warp gates two landmarks per lane with a
-//    fused (fma, symmetric) evaluation of S, the condition gate and the Mahalanobis distance plus a
-//    running bound of its own rounding error, which proves for all but a few landmarks (normally
-//    all but one) that they cannot be the argmin / are definitely kept or skipped. The survivors
-//    are re-evaluated in the reference's exact operation order, four lanes per landmark (one
-//    element of S each, ekf_gate_S_element), and the decision, S, residual and H_R come from that
-//    exact evaluation - so decisions and everything downstream carry the reference's bits.
-//  * Roles rotate with the CTA's slot on its SM (front warp, helper warp), so the four CTAs of an
-//    SM load the four FP64 pipes evenly.
+//  * Gating: every landmark in the reference's exact operation order (ekf_small.cuh), two lanes per
+//    landmark on all four warps - lane i evaluates row i of S (two elements, ekf_gate_S_element), the
+//    pair exchanges them by shuffle and both finish the condition gate and the Mahalanobis distance;
+//    S^-1 (a by-product of the distance) and the L D L^T factors of S are evaluated by every lane, so
+//    the winner of the argmin writes a complete decision block and no serial "winner" phase follows.
+//    The strip propagation (Propagate.cpp:56-60) rides on the gating lanes' loads.
+//  * Fixed warp roles: warp 2 runs the landmark-independent scalar chains of the NEXT step (sincos of
+//    the two headings, Phi, G, P_RR, pose) beside the gain phase of warps 1 and 3, so every SM
+//    sub-partition's instruction cache sees one role's code.
 //
 // Phase structure per step (slam.cpp:130-182 order):
-//   helper warp   sincos of the two headings, odometry -> Q, Phi, G, new pose (kalmanfilter.cpp:17-37,
-//                 Propagate.cpp:33-48), P_RR <- Phi P_RR Phi^T + G Q G^T (Propagate.cpp:53,66-67),
-//                 the landmark-independent part of the update (Update.cpp:89-95); runs during the
-//                 previous step's gain phase
-//   row threads   strip <- Phi * strip (Propagate.cpp:56-60)
-//   front warp    gating, decision (Update.cpp:103-152,181,191), S^-1, L D L^T, the pose rows of
-//                 the gain and the pose correction
-//   row threads   gain column correction, K, x, W (Update.cpp:186-187), eager downdate of strip and
-//                 diagonal blocks; every KH-th update all warps sweep the tiles
+//   warp 2        record-only scalars (kalmanfilter.cpp:17-37, one step ahead), sincos of the two headings,
+//                 Phi, G, new pose (Propagate.cpp:33-48), P_RR <- Phi P_RR Phi^T + G Q G^T (Propagate.cpp:53,
+//                 66-67), the landmark-independent part of the update (Update.cpp:89-95)
+//   all warps     (every third update) sweep of the tiles; gating with the strip propagation folded in
+//                 (Propagate.cpp:56-60, Update.cpp:103-148), warp argmin, decision (Update.cpp:152,181,191)
+//   warp 2        pose rows of the gain, pose correction, P_RR downdate - then on to the next step's chain
+//   warps 1, 3    gain column correction, K, x, W (Update.cpp:186-187), eager downdate of strip, diagonal
+//                 and pair blocks, one landmark (two rows) per thread
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
 
 namespace {
 
-constexpr int KH = 4;            // history ring: a warp sweeps its tiles when three updates are pending
+constexpr int KH = 4;            // history ring: the tiles are swept when three updates are pending
 constexpr int DT_THREADS = 128;
-#ifndef DT_ROTATE
-#define DT_ROTATE 0               // 0: warp w of every CTA has the same role, so each SM sub-partition's instruction cache
-                                  // sees one role's code (measured +13 %); 1: roles rotate with the CTA's slot on its SM
-                                  // (FP64 pipes evenly loaded, but every sub-partition runs every role's code)
-#endif
 
 #ifdef EKF_DTILE_TIMING
 __device__ long long g_dtile_ts[4][16];
 #define DTILE_TS(kk)                                                                              \
   do {                                                                                            \
-    if (blockIdx.x == 0 && f == 0 && (t == 501 || ((kk) >= 9 && t >= 498 && t < 502)) && (threadIdx.x & 31) == 0) \
-      g_dtile_ts[threadIdx.x >> 5][kk] = clock64();                                               \
+    if (blockIdx.x == 0 && f == 0 && t == 501 && (threadIdx.x & 31) == 0) g_dtile_ts[threadIdx.x >> 5][kk] = clock64(); \
   } while (0)
 #else
 #define DTILE_TS(kk) do { } while (0)
 #endif
-
-__device__ int g_sm_slot[1024];   // CTAs started per SM so far (role rotation)
 
 template <int RB>                // RB row blocks of 4 rows = 2*RB landmarks
 struct DCfg {
@@ -103,16 +94,19 @@ __device__ __forceinline__ int dt_colterm(int c) {
 template <int RB>
 __device__ __forceinline__ int dt_addr(int r, int c) { return dt_rowterm<RB>(r) + dt_colterm<RB>(c); }
 
-struct DDec {                    // what the front warp publishes for the row threads / the helper
-  int decision, c0, rt_c0, ct_c0;  // c0 = first P_LL row of the associated landmark; its row / column address terms
-  int sb_c0, pad0, pad1, pad2;     // first tile slot of its column block
-  double h3[2], res[2], Si[4];
-  double Ct[4], mCt[4];          // H_Li and the first two columns of H_R of THIS update (sm.upd is rewritten early)
+
+// What the winner of a gating warp publishes: everything the gain phase needs (Opt_* of Update.cpp:140-147
+// plus S^-1, the L D L^T factors of S and the address terms of the associated column pair).
+struct DCand {
+  double val;
+  int idx, c0;                   // state index Opt_i (INT_MAX: none), first P_LL row of the landmark
+  int rt_c0, ct_c0, sb_c0, pad;  // row / column address terms of that row, first tile slot of its column block
+  double res[2], S[4], Si[4], h3[2];
   double l, sq0, sq1;
   unsigned sm0, sm1;             // sign-bit masks of the downdate (u = mask ^ W)
+  double Ct[4], mCt[4];          // H_Li and the first two columns of H_R of THIS update (sm.upd is rewritten early)
+  double xr[4];                  // pose after the update (Update.cpp:187, rows 0..2)
   double2 WR[3];                 // downdate vectors of the three pose rows
-  double nl[2], h3n[2], PLL[4];  // New branch
-  double cres, cS;               // compass
 };
 
 template <int RB>
@@ -123,18 +117,18 @@ struct DSmem {
   double Dd[3][C::NL];           // P(2l,2l), P(2l+1,2l), P(2l+1,2l+1)
   double Do[4][C::NP];           // Do[i+2j][m] = P(4m+2+i, 4m+j)
   double xl[C::NQ];              // landmark part of the state
+  double2 WR[3];                 // downdate vectors of the three pose rows of the current update
   double xr[4];                  // pose
   double PRR[9];                 // column-major, both triangles
   PropSetup prop;
-  PropSetup pre;                 // record-only part of the NEXT step's PropSetup (v, w, dt, Q)
-  double pre_dphi;               // dt * RTV of the next step
+  PropSetup pre[2];              // record-only part of PropSetup (v, w, dt, Q) of steps t, t+1 (by step parity)
+  double pre_dphi[2];            // dt * RTV of those steps
   UpdateSetup upd;
-  DDec dec;
+  DCand cand[4];                 // one per gating warp
+  double nl[2], h3n[2], PLL[4];  // New branch
+  double cres, cS;               // compass
   unsigned hs0[KH], hs1[KH];     // sign masks of the pending updates
   int hrank[KH];                 // 2, or 1 for a compass update
-  int list[64];                  // landmarks the exact pass has to visit
-  double scr_tlo[32], scr_thi[32];   // screen results of the second gating warp (landmarks 32..63)
-  int scr_state[32];
 };
 
 struct DRunArgs {
@@ -148,19 +142,10 @@ __device__ __forceinline__ void dt_cp_async8(void* dst_smem, const void* src_gme
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dt_smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void dt_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void dt_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void dt_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void dt_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void dt_cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ double dt_flip(double v, unsigned mask) {
   return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
-}
-__device__ __forceinline__ double dt_rcp_fast(double d) {   // ~1e-16 relative for normal d; screen only
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  return y;
 }
 // order-preserving 64-bit key of a double (total order, -0 < +0, NaNs at the ends)
 __device__ __forceinline__ unsigned long long dt_key(double v) {
@@ -174,110 +159,9 @@ __device__ __forceinline__ unsigned long long dt_warp_min_key(unsigned long long
   return ((unsigned long long)mhi << 32) | mlo;
 }
 
-// ---- the screen: fused evaluation of one landmark-loop iteration with an error bound -----------
-// Mathematically the same quantities as Update.cpp:108-136 (S symmetric, so three entries), evaluated
-// with fma and with the landmark-independent products hoisted; NOT the reference's rounding. It is
-// only used to prove statements that hold for the exact values too:
-//   state 1  "cond >= cond_max for sure"      (skipped by Update.cpp:131)
-//   state 0  "cond <  cond_max for sure", and the exact Mahalanobis distance lies in [tlo, thi]
-//   state 2  anything else (not provable: NaN / inf, near the condition threshold, heavy
-//            cancellation) - the exact evaluation decides.
-// Error model: every entry of S is a sum of at most 13 products h*p*h' (|h| <= hmax = 3+|h3_0|+|h3_1|
-// bounds a row sum of |H|, |p| <= pmax) plus R, evaluated with <= 16 roundings, and the exact path's
-// own roundings are bounded the same way: |dS| <= EPSB*(hmax^2*pmax + rmax) with EPSB = 64*2^-53
-// covers both with a factor of two to spare. With ninv >= ||S^-1||: the relative error of the quadratic
-// form is <= rho = |dS|*ninv (first order; rho <= 2^-24 is required, so second order is < 2^-48), the
-// relative error of cond <= 2*rho, and the residual's rounding dr <= EPSB*(|z|+2|d|) moves the form by
-// <= ninv*dr*(2|r|+dr).
-struct ScreenU {
-  double c, s, x0, x1, z0, z1, R00, R01, R11;
-  double U0[3], U1[3], p2[3];
-  double klo, khi, zsum, rmax;
-  unsigned prr_hi;
-  bool cond_ok;
-};
-
-__device__ __forceinline__ void dt_screen_setup(ScreenU& w, const UpdateSetup& u, double cond_max) {
-  w.c = u.c; w.s = u.s; w.x0 = u.x0; w.x1 = u.x1; w.z0 = u.z0; w.z1 = u.z1;
-  w.R00 = u.R[0]; w.R01 = 0.5 * (u.R[1] + u.R[2]); w.R11 = u.R[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    // columns 0,1 of H_R are (-c, s) and (-s, -c): U_a = P_RR(:,0)*H_R(a,0) + P_RR(:,1)*H_R(a,1)
-    w.U0[j] = fma(u.PRR[j + 3], -u.s, u.PRR[j] * -u.c);
-    w.U1[j] = fma(u.PRR[j + 3], -u.c, u.PRR[j] * u.s);
-    w.p2[j] = u.PRR[j + 6];
-  }
-  const double kap = cond_max + 1.0 / cond_max;       // cond + 1/cond is increasing for cond >= 1
-  w.klo = kap * (1.0 - 0x1p-16);
-  w.khi = kap * (1.0 + 0x1p-16);
-  w.cond_ok = cond_max > 1.0;
-  w.zsum = fabs(u.z0) + fabs(u.z1);
-  w.rmax = fmax(fmax(fabs(u.R[0]), fabs(u.R[3])), fmax(fabs(u.R[1]), fabs(u.R[2])));
-  unsigned m = 0;
-#pragma unroll
-  for (int q = 0; q < 9; ++q) m = max(m, (unsigned)__double2hiint(u.PRR[q]) & 0x7fffffffu);
-  w.prr_hi = m;
-}
-
-// sr[r + 2j] = P(Li + r, j); dd = {P(Li,Li), P(Li+1,Li), P(Li+1,Li+1)}
-__device__ __forceinline__ void dt_screen(const ScreenU& w, double lx, double ly, const double* sr, const double* dd,
-                                          double& tlo, double& thi, int& state) {
-  const double c = w.c, s = w.s;
-  const double d0 = lx - w.x0, d1 = ly - w.x1;
-  const double zh0 = fma(c, d0, s * d1), zh1 = fma(c, d1, -(s * d0));
-  const double r0 = w.z0 - zh0, r1 = w.z1 - zh1;
-  const double h30 = zh1, h31 = -zh0;               // -C^T J d = (zh1, -zh0)
-  double GR0[3], GR1[3];                            // (P_RR H_R^T + P_RL H_L^T)(:, a)
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    GR0[j] = fma(sr[1 + 2 * j], s, fma(sr[2 * j], c, fma(w.p2[j], h30, w.U0[j])));
-    GR1[j] = fma(sr[1 + 2 * j], c, fma(sr[2 * j], -s, fma(w.p2[j], h31, w.U1[j])));
-  }
-  double GL0[2], GL1[2];                            // (P_LR H_R^T + P_LL H_L^T)(r, a)
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const double pl0 = r ? dd[1] : dd[0], pl1 = r ? dd[2] : dd[1];
-    GL0[r] = fma(pl1, s, fma(pl0, c, fma(sr[r + 4], h30, fma(sr[r + 2], -s, sr[r] * -c))));
-    GL1[r] = fma(pl1, c, fma(pl0, -s, fma(sr[r + 4], h31, fma(sr[r + 2], -c, sr[r] * s))));
-  }
-  const double S00 = fma(s, GL0[1], fma(c, GL0[0], fma(h30, GR0[2], fma(-s, GR0[1], fma(-c, GR0[0], w.R00)))));
-  const double S01 = fma(s, GL1[1], fma(c, GL1[0], fma(h30, GR1[2], fma(-s, GR1[1], fma(-c, GR1[0], w.R01)))));
-  const double S11 = fma(c, GL1[1], fma(-s, GL1[0], fma(h31, GR1[2], fma(-c, GR1[1], fma(s, GR1[0], w.R11)))));
-  const double b2 = S01 * S01;
-  const double det = fma(S00, S11, -b2);
-  const double fro = fma(S00, S00, fma(S11, S11, b2 + b2));     // sigma1^2 + sigma2^2; |det| = sigma1*sigma2
-  const double adet = fabs(det);
-  const double yinv = dt_rcp_fast(det);
-  const double num = fma(S11 * r0, r0, fma(S00 * r1, r1, -2.0 * (S01 * r0) * r1));
-  const double tt = num * yinv;
-  // error bound
-  unsigned m = w.prr_hi;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) m = max(m, (unsigned)__double2hiint(sr[q]) & 0x7fffffffu);
-#pragma unroll
-  for (int q = 0; q < 3; ++q) m = max(m, (unsigned)__double2hiint(dd[q]) & 0x7fffffffu);
-  const double pmax = __hiloint2double((int)((m + 0x00100000u) & 0x7ff00000u), 0);   // power of two >= every |P| entry used
-  constexpr double EPSB = 0x1p-47;
-  const double hmax = 3.0 + fabs(h30) + fabs(h31);
-  const double dS = EPSB * fma(hmax * hmax, pmax, w.rmax);
-  const double ninv = (fabs(S00) + fabs(S11) + 2.0 * fabs(S01)) * fabs(yinv);
-  const double rho = dS * ninv;
-  const double dr = EPSB * (w.zsum + 2.0 * (fabs(d0) + fabs(d1)));
-  const double err = fma(fabs(tt), 4.0 * rho, ninv * dr * (2.0 * (fabs(r0) + fabs(r1)) + dr)) + 0x1p-40 * fabs(tt);
-  const bool sane = rho <= 0x1p-24 && err < INFINITY && tt == tt && w.cond_ok;   // false for any NaN
-  const bool keep = sane && fro < w.klo * adet;
-  const bool skip = sane && fro > w.khi * adet;
-  state = skip ? 1 : (keep ? 0 : 2);
-  tlo = keep ? tt - err : -INFINITY;
-  thi = keep ? tt + err : INFINITY;
-}
-
 // ---- tile sweep: apply the pending downdates to this thread's tile, in order ---------------------
-// Half a tile (4 rows x 6 columns) at a time in registers. Per pending update the ten history words
-// this half needs are loaded back to back (one shared-memory latency), then 48 fma on 24 independent
-// elements.
-// One copy in the binary (the kernel reaches it from five places and its code footprint matters - the
-// SM sub-partitions' instruction caches are the bottleneck of the scalar phases). A third of a tile
+// One copy in the binary (code footprint matters: the SM sub-partitions' instruction caches are the bottleneck of
+// the scalar phases). A third of a tile
 // (4 rows x 4 columns) at a time in registers, the three column groups in a rolled loop: column
 // 12J + 4g + b of a history vector sits at b*HP + 3J + g, so the group only shifts the address. Per
 // pending update the eight history words are loaded back to back, then 32 fma on 16 independent elements.
@@ -333,36 +217,27 @@ __device__ __noinline__ void dt_sweep_tile(double* __restrict__ Tt, const DSmem<
   }
 }
 
-// Record-only scalars of a step (kalmanfilter.cpp:17-37), one lane; evaluated while the front warp gates.
+// Record-only scalars of a step (kalmanfilter.cpp:17-37), one lane; evaluated one step ahead.
 template <int RB>
-__device__ __noinline__ void dt_helper_pre(DSmem<RB>& sm, const double* rec, const EkfConst& k) {
+__device__ __noinline__ void dt_helper_pre(DSmem<RB>& sm, const double* rec, int slot, const EkfConst& k) {
   PropSetup ps;
   ekf_build_prop_pre(ps, rec[0], rec[1], rec[2], k);
-  sm.pre = ps;
+  sm.pre[slot] = ps;
   const double RTV = rec[1] * k.deg2rad_pi / 180.0;
-  sm.pre_dphi = rec[2] * RTV;
+  sm.pre_dphi[slot] = rec[2] * RTV;
 }
 
 template <int RB>
 __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DRunArgs a) {
   using C = DCfg<RB>;
-  constexpr int NQ = C::NQ;
+  constexpr int NQ = C::NQ, HP = C::HP, PS = C::PS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DSmem<RB>& sm = *reinterpret_cast<DSmem<RB>*>(smem_raw);
   double* T = reinterpret_cast<double*>(smem_raw + ((sizeof(DSmem<RB>) + 15) & ~(size_t)15));
-  double* recbuf = T + ((C::TSIZE + 1) & ~1);                                                  // [2][Lp]
-  __shared__ int s_rot;
+  double* recbuf = T + ((C::TSIZE + 1) & ~1);                                                  // [3][Lp]: records of steps t, t+1, t+2
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    s_rot = (atomicAdd(&g_sm_slot[smid & 1023], 1) & 3) * DT_ROTATE;
-  }
-  __syncthreads();
-  const int rot = s_rot;
-  const bool front = warp == rot;                    // gating / decision warp
-  const bool front2 = warp == ((rot + 1) & 3);       // screens landmarks 32.. for the front warp
-  const bool helper = warp == ((rot + 2) & 3);       // scalar chains / P_RR warp
+  const bool helper = warp == 2;                     // scalar chains / P_RR / pose rows
+  const bool rows_warp = warp == 1 || warp == 3;     // gain phase: one landmark (two P_LL rows) per thread
   const bool is_tile = tid < C::NT;
   int I = 0, J = 0;
   if (is_tile) {                                     // inverse of dt_slot
@@ -371,14 +246,14 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
     I = 3 * J + 1 + s;
   }
   double* Tt = T + tid;                              // this thread's tile
-  const int q = tid;                                 // this thread's P_LL row (tid < NQ)
+  const int q = tid;                                 // this thread's P_LL row in the row-wise phases (tid < NQ)
   const int hq = dt_hidx<RB>(q < NQ ? q : 0);        // its slot in a history vector
-  constexpr int HP = C::HP, PS = C::PS;
-  // gain phase: one landmark (two P_LL rows) per thread on the two warps that are neither front nor helper
-  const bool rows_warp = front2 || warp == ((rot + 3) & 3);
-  const int lrow = (front2 ? 0 : 32) + lane;         // landmark of this thread in the gain phase
+  // gating: two lanes per landmark
+  const int gl = tid >> 1, gi = tid & 1;
+  // gain phase
+  const int lrow = (warp == 1 ? 0 : 32) + lane;      // landmark of this thread
   const int q0 = 2 * lrow < NQ ? 2 * lrow : 0;       // its first P_LL row
-  const int rt_l = dt_rowterm<RB>(q0), ct_l = dt_colterm<RB>(q0), sb_l = dt_slot<RB>(0, (q0 * 43) >> 9);
+  const int rt_l = dt_rowterm<RB>(q0), ct_l = dt_colterm<RB>(q0);
   const int hq0 = dt_hidx<RB>(q0);
   const int ld = a.st.ld, L = a.io.L, T_steps = a.io.T, M = a.io.M;
   const int Lp = (L + 1) & ~1;
@@ -397,7 +272,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
     double* gx = a.st.x + (size_t)f * a.st.xs;
     const double* grec = a.io.records + (size_t)f * T_steps * L;
     int n_lm = a.st.nlm[f];
-    int cnt = 0, ap_o = 0, ap_f = 0;   // history entries created; entries applied to the tiles of the non-front warps / the front warp
+    int cnt = 0, ap = 0;          // history entries created / applied to the tiles
     int dropped = 0;
     // ---- load: HBM (external layout, lower triangle, column by column) -> shared memory ------------
     {
@@ -426,24 +301,21 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
     }
     __syncthreads();
 
-    // ---- helper warp: everything of a step that does not depend on the landmarks -------------------
-    // Reads the pose / P_RR left by the previous update, applies the eager downdate of P_RR if that was
-    // an Old update (or compass), then doPropagation's scalars, the propagated pose and P_RR, and the
-    // landmark-independent part of the first measurement's update.
-    // Apply history entries [from, to) to this thread's tile.
-    auto sweep_own = [&](int from, int to) {
-      if (is_tile && 4 * I < 2 * n_lm && from < to) dt_sweep_tile<RB>(Tt, sm, I, J, from, to);
+    // Apply the pending history entries to this thread's tile; CTA-wide variant for the places that
+    // need the tiles current (New associations, a full history ring, end of run).
+    auto sweep_own = [&]() {
+      if (is_tile && 4 * I < 2 * n_lm && ap < cnt) dt_sweep_tile<RB>(Tt, sm, I, J, ap, cnt);
     };
-    // Every warp brings its tiles up to date (CTA-wide: New associations, a full history ring, end of run).
     auto flush_all = [&]() {
-      sweep_own(front ? ap_f : ap_o, cnt);
-      ap_f = ap_o = cnt;
+      sweep_own();
+      ap = cnt;
       __syncthreads();
     };
-    auto prr_eager = [&](int slot) {               // lanes 0..8: P_RR(i,j) += u_i . W_j of pending update `slot`
+    // lanes 0..8 of the helper warp: P_RR(i,j) += u_i . W_j of the history entry in `slot`
+    auto prr_eager = [&](int slot) {
       if (lane < 9) {
         const int i = lane % 3, j = lane / 3;
-        const double2 wi = sm.dec.WR[i], wj = sm.dec.WR[j];
+        const double2 wi = sm.WR[i], wj = sm.WR[j];
         double v = sm.PRR[i + 3 * j];
         if (sm.hrank[slot] == 2) v = fma(dt_flip(wi.y, sm.hs1[slot]), wj.y, v);
         v = fma(dt_flip(wi.x, sm.hs0[slot]), wj.x, v);
@@ -451,30 +323,43 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
       }
       __syncwarp();
     };
-    // Record-only scalars of a step (kalmanfilter.cpp:17-37): evaluated while the front warp gates.
-    auto helper_pre = [&](const double* rec) {
-      dt_cp_async_wait_all();
-      __syncwarp();
-      if (lane == 0) dt_helper_pre<RB>(sm, rec, k);
-      __syncwarp();
+    // Warp 0: records are fetched three steps ahead and their record-only scalars evaluated two steps
+    // ahead (in its idle time during the gain phase), so the helper chain never waits for either: the
+    // CTA barriers of the step in between order them.
+    auto fetch_record = [&](int step) {                   // -> ring slot step % 3
+      if (step < T_steps) {
+        const double* g = grec + (size_t)step * L;
+        double* dst = recbuf + (size_t)(step % 3) * Lp;
+        for (int i = lane; i < L; i += 32) dt_cp_async8(dst + i, g + i);
+      }
+      dt_cp_async_commit();
     };
-    auto helper_chain = [&](const double* rec) {
+    auto warp0_pre = [&](int step) {
+      if (step < T_steps) {
+        if (lane == 0) dt_helper_pre<RB>(sm, recbuf + (size_t)(step % 3) * Lp, step & 1, k);
+        __syncwarp();
+      }
+    };
+    // ---- helper warp: everything of a step that does not depend on the landmarks -------------------
+    // Reads the pose / P_RR left by the previous update; doPropagation's heading-dependent scalars, the
+    // propagated pose and P_RR, and the landmark-independent part of the first measurement's update.
+    auto helper_chain = [&](const double* rec, int tpar) {
       // operands that do not depend on the headings are loaded first
       const int e = lane % 9, i = e % 3, j = e / 3;
       double PRR[9], Q[4];
 #pragma unroll
       for (int w = 0; w < 9; ++w) PRR[w] = sm.PRR[w];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) Q[w] = sm.pre.Q[w];
+      for (int w = 0; w < 4; ++w) Q[w] = sm.pre[tpar].Q[w];
       double sn = 0.0, cs = 1.0;
       PropSetup ps;
       if (lane < 2) {
-        const double phi = lane == 0 ? sm.xr[2] : sm.xr[2] + sm.pre_dphi;   // same expression as the pose update
-        if (lane == 0) ps = sm.pre;
+        const double phi = lane == 0 ? sm.xr[2] : sm.xr[2] + sm.pre_dphi[tpar];   // same expression as the pose update
+        if (lane == 0) ps = sm.pre[tpar];
         sincos(phi, &sn, &cs);
         if (lane == 0) {
           ekf_build_prop_trig(ps, sn, cs);
-          sm.prop.phi02 = ps.phi02;                                        // all the strip threads need (Propagate.cpp:56)
+          sm.prop.phi02 = ps.phi02;                                        // all the strip propagation needs (Propagate.cpp:56)
           sm.prop.phi12 = ps.phi12;
           const double xm0 = ps.v * ps.c, xm1 = ps.v * ps.s, xm2 = ps.w;   // Propagate.cpp:33-37
           const double n0 = sm.xr[0] + ps.dt * xm0, n1 = sm.xr[1] + ps.dt * xm1, n2 = sm.xr[2] + ps.dt * xm2;
@@ -534,56 +419,64 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
         }
       }
     };
+
+    if (warp == 0) {                                     // records 1, 2 on their way; scalars of steps 0 and 1
+      fetch_record(1);
+      fetch_record(2);
+      warp0_pre(0);
+      dt_cp_async_wait_1();                              // record 1 has landed
+      __syncwarp();
+      warp0_pre(1);
+    }
+    __syncthreads();
     bool setup_valid = true;
-    bool pre_done = false;        // helper_pre already ran for the record of the coming step
     bool sync_first = false;      // the previous step ended on a New association: its row threads still read P_RR
 
     for (int t = 0; t < T_steps; ++t) {
-      const double* cur = recbuf + (size_t)(t & 1) * Lp;
+      const double* cur = recbuf + (size_t)(t % 3) * Lp;
       // ---- helper warp: landmark-independent part of this step (the one call site of helper_chain).
-      // After an Old update the helper warp gets here straight from B3 (it has no gain rows), so this
-      // runs beside the other warps' gain phase of the previous step.
+      // After an Old update the helper warp gets here straight from its pose rows, so this runs beside
+      // the gain phase of the previous step on warps 1 and 3.
       if (sync_first) __syncthreads();
       if (helper) {
-        if (!pre_done) helper_pre(cur);
         if (t > 0 && a.io.pose_trace && lane == 0) {     // slam.cpp:181 for the previous step, before the pose is propagated
           double* pt = a.io.pose_trace + ((size_t)f * T_steps + t - 1) * 3;
           pt[0] = sm.xr[0]; pt[1] = sm.xr[1]; pt[2] = sm.xr[2];
         }
         __syncwarp();
-        helper_chain(cur);
-        if (t + 1 < T_steps) {                           // the helper warp owns the record prefetch
-          const double* g = grec + (size_t)(t + 1) * L;
-          double* nxt = recbuf + (size_t)((t + 1) & 1) * Lp;
-          for (int i = lane; i < L; i += 32) dt_cp_async8(nxt + i, g + i);
-        }
+        helper_chain(cur, t & 1);
       }
-      pre_done = false;
       sync_first = false;
       setup_valid = true;
       DTILE_TS(0);
       __syncthreads();                                   // B1: helper results of this step (and its record) visible
+      DTILE_TS(1);
       const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
-      // ---- doPropagation, strip part (Propagate.cpp:56-60) ------------------------------------------
-      if (q < 2 * n_lm) {
-        double a0 = sm.SR[0][q], a1 = sm.SR[1][q], a2 = sm.SR[2][q];
-        ekf_prop_col(sm.prop, a0, a1, a2);
-        sm.SR[0][q] = a0; sm.SR[1][q] = a1; sm.SR[2][q] = a2;
+      // The strip propagation (Propagate.cpp:56-60) rides on the gating lanes' loads of the first measurement
+      // unless something else needs the propagated strip first (compass) or nothing gates (no measurement).
+      bool fold_prop = nz > 0 && cur[6] == 0.0;
+      if (!fold_prop) {
+        if (q < 2 * n_lm) {
+          double a0 = sm.SR[0][q], a1 = sm.SR[1][q], a2 = sm.SR[2][q];
+          ekf_prop_col(sm.prop, a0, a1, a2);
+          sm.SR[0][q] = a0; sm.SR[1][q] = a1; sm.SR[2][q] = a2;
+        }
+        if (nz > 0) __syncthreads();
       }
       // ---- doUpdateCompass (slam.cpp:144-147, kalmanfilter.cpp:96-130): a rank-1 pending update -----
       if (cur[6] != 0.0) {
-        if (cnt - min(ap_o, ap_f) > KH - 1) flush_all();   // no free history slot
+        if (cnt - ap > KH - 1) flush_all();              // no free history slot
         const int sl = cnt & (KH - 1);
         if (tid == 0) {
-          sm.dec.cres = ekf_compass_residual(sm.xr[2], cur[3], k);
-          sm.dec.cS = sm.PRR[8] + cur[4];
-          sm.hs0[sl] = sm.dec.cS < 0 ? 0u : 0x80000000u;
+          sm.cres = ekf_compass_residual(sm.xr[2], cur[3], k);
+          sm.cS = sm.PRR[8] + cur[4];
+          sm.hs0[sl] = sm.cS < 0 ? 0u : 0x80000000u;
           sm.hs1[sl] = 0u;
           sm.hrank[sl] = 1;
         }
         __syncthreads();
         {
-          const double res = sm.dec.cres, S = sm.dec.cS, invS = 1 / S, sq = sqrt(fabs(S));
+          const double res = sm.cres, S = sm.cS, invS = 1 / S, sq = sqrt(fabs(S));
           if (tid < NQ) {
             double2 w = make_double2(0.0, 0.0);
             if (q < 2 * n_lm) {
@@ -596,7 +489,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
             const int r = tid - NQ;
             const double Ki = invS * sm.PRR[r + 6];
             sm.xr[r] = sm.xr[r] + res * Ki;
-            sm.dec.WR[r] = make_double2(sq * Ki, 0.0);
+            sm.WR[r] = make_double2(sq * Ki, 0.0);
           }
         }
         __syncthreads();
@@ -605,7 +498,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
           const double2* Hc = sm.H[sl];
           const double u0 = dt_flip(Hc[hq].x, s0);
 #pragma unroll
-          for (int j = 0; j < 3; ++j) sm.SR[j][q] = fma(u0, sm.dec.WR[j].x, sm.SR[j][q]);
+          for (int j = 0; j < 3; ++j) sm.SR[j][q] = fma(u0, sm.WR[j].x, sm.SR[j][q]);
           const int aa = q & 3, l = q >> 1, m = q >> 2;
           if ((aa & 1) == 0) sm.Dd[0][l] = fma(u0, Hc[hq].x, sm.Dd[0][l]);
           else {
@@ -635,268 +528,176 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
           continue;
         }
         const double* zr = cur + 8 + 6 * m;
-        __syncthreads();                                 // B2: strip propagated / previous update complete
-        DTILE_TS(1);
-        const bool two_warps = n_lm > 32;                 // landmarks 32.. are screened by the second gating warp
-        const bool gate_warp = front || (front2 && two_warps);
         if (!setup_valid) {                                // pose / P_RR changed since the helper built sm.upd
-          if (front) {
-            if (lane == 0) {
-              UpdateSetup u;
-              double PRR[9];
-              for (int w = 0; w < 9; ++w) PRR[w] = sm.PRR[w];
-              ekf_build_setup(u, sm.xr[2], sm.xr[0], sm.xr[1], PRR, zr[0], zr[1], zr + 2);
-              sm.upd = u;
-            }
-            __syncwarp();
+          __syncthreads();                                 // the previous update (or the compass) is complete
+          if (tid == 0) {
+            UpdateSetup u;
+            double PRR[9];
+            for (int w = 0; w < 9; ++w) PRR[w] = sm.PRR[w];
+            ekf_build_setup(u, sm.xr[2], sm.xr[0], sm.xr[1], PRR, zr[0], zr[1], zr + 2);
+            sm.upd = u;
           }
-          if (gate_warp && two_warps) dt_bar_sync(1, 64);
+          __syncthreads();
         }
-        // ================= screen: one landmark per lane on the gating warps ==============================
-        double tl = INFINITY, th = INFINITY;
-        int st = 1;
-        if (gate_warp) {
+        // ---- every third update: bring the tiles up to date (nothing reads them before the gain phase)
+        if (cnt - ap >= KH - 1) {
+          sweep_own();
+          ap = cnt;
+        }
+        DTILE_TS(2);
+        // ================= gating: two lanes per landmark, reference operation order ===================
+        {
           const UpdateSetup& u = sm.upd;
-          ScreenU w;
-          dt_screen_setup(w, u, k.cond_max);
-          const int lm = lane + (front ? 0 : 32);
-          if (lm < n_lm) {
-            const double2 xy = *reinterpret_cast<const double2*>(&sm.xl[2 * lm]);
-            double sr[6], dd[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const double2 v = *reinterpret_cast<const double2*>(&sm.SR[j][2 * lm]);
-              sr[2 * j] = v.x; sr[2 * j + 1] = v.y;
+          const bool have = gl < n_lm;
+          double val = INFINITY;
+          int my_idx = INT_MAX;
+          GateResult g;
+          GatePre pre;
+          double ll = 0.0, sq0 = 0.0, sq1 = 0.0, d0 = 0.0, d1 = 0.0;
+          double Sa = 0.0, Sb = 0.0;
+          double pxa = 0.0, pxb = 0.0;
+          double2 pwa = make_double2(0.0, 0.0), pwb = pwa;
+          double2 s0 = make_double2(0.0, 0.0), s1 = s0, s2 = s0;
+          if (have) {
+            const double2 xy = *reinterpret_cast<const double2*>(&sm.xl[2 * gl]);
+            s0 = *reinterpret_cast<const double2*>(&sm.SR[0][2 * gl]);
+            s1 = *reinterpret_cast<const double2*>(&sm.SR[1][2 * gl]);
+            s2 = *reinterpret_cast<const double2*>(&sm.SR[2][2 * gl]);
+            const double p10 = sm.Dd[1][gl];
+            const double pll[4] = {sm.Dd[0][gl], p10, p10, sm.Dd[2][gl]};
+            if (fold_prop) {                               // P_RL <- Phi*P_RL for this landmark's two rows (Propagate.cpp:56-60)
+              ekf_prop_col(sm.prop, s0.x, s1.x, s2.x);
+              ekf_prop_col(sm.prop, s0.y, s1.y, s2.y);
             }
-#pragma unroll
-            for (int e = 0; e < 3; ++e) dd[e] = sm.Dd[e][lm];
-            dt_screen(w, xy.x, xy.y, sr, dd, tl, th, st);
+            const double p[6] = {s0.x, s0.y, s1.x, s1.y, s2.x, s2.y};
+            ekf_gate_prelude(u, xy.x, xy.y, pre);
+            // lane gi owns row gi of S: elements k = gi (column 0) and k = gi + 2 (column 1)
+            Sa = ekf_gate_S_element(u, pre, p, pll, gi);
+            Sb = ekf_gate_S_element(u, pre, p, pll, gi + 2);
           }
-        }
-        if (front2 && two_warps) {
-          sm.scr_tlo[lane] = tl; sm.scr_thi[lane] = th; sm.scr_state[lane] = st;
-          dt_bar_arrive(2, 64);
-        }
-        // While the front warp gates (it reads no tiles), the other warps bring their tiles up to date.
-        const bool osweep = cnt - ap_o >= KH - 1;
-        if (!front && osweep) sweep_own(ap_o, cnt);
-        if (osweep) ap_o = cnt;
-        if (front) {
-          // ================= front warp: candidates, exact evaluation, decision =========================
-          const UpdateSetup& u = sm.upd;
-          double tlo[2], thi[2];
-          int state[2];
-          tlo[0] = tl; thi[0] = th; state[0] = st;
-          tlo[1] = INFINITY; thi[1] = INFINITY; state[1] = 1;
-          if (two_warps) {
-            dt_bar_sync(2, 64);
-            tlo[1] = sm.scr_tlo[lane]; thi[1] = sm.scr_thi[lane]; state[1] = sm.scr_state[lane];
-          }
-          DTILE_TS(2);
-          // upper bound of the minimum over the landmarks that are kept for sure
-          const unsigned long long kmin = dt_warp_min_key(min(dt_key(thi[0]), dt_key(thi[1])));
-          bool flag[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int lm = lane + 32 * h;
-            // candidate unless skipped for sure or provably above the bound (NaN-safe: !(>))
-            flag[h] = lm < n_lm && state[h] != 1 && !(dt_key(tlo[h]) > kmin);
-          }
-          const unsigned mA = __ballot_sync(0xffffffffu, flag[0]), mB = __ballot_sync(0xffffffffu, flag[1]);
-          const int nA = __popc(mA), nTot = nA + __popc(mB);
-          const bool single = nTot == 1;                  // the normal case: one landmark survives the screen
-          if (nTot > 1) {
-            if (flag[0]) sm.list[__popc(mA & ((1u << lane) - 1))] = lane;
-            if (flag[1]) sm.list[nA + __popc(mB & ((1u << lane) - 1))] = lane + 32;
-            __syncwarp();
-          }
-          // winner of the exact evaluation (reference operation order, Update.cpp:108-147)
-          double bval = INFINITY;
-          int bidx = INT_MAX;
-          double bres0 = 0, bres1 = 0, bS0 = 0, bS1 = 0, bS2 = 0, bS3 = 0, bh0 = 0, bh1 = 0;
-          double bSi0 = 0, bSi1 = 0, bSi2 = 0, bSi3 = 0;
-          // L D L^T of the winning S and the pose rows of P H^T (lanes 0..2); with a single candidate they
-          // are evaluated next to the gate so their latencies overlap
-          double ll = 0, sq0 = 0, sq1 = 0, d0 = 0, d1 = 0, M0 = 0, M1 = 0;
-          auto ldl = [&](double S0, double S1, double S3) {
-            d0 = S0; ll = S1 / S0; d1 = S3 - ll * S1;
-            sq0 = sqrt(fabs(d0)); sq1 = sqrt(fabs(d1));
-          };
-          auto pose_rows = [&](int c0, double h0, double h1) {   // Update.cpp:186: row r of P at the five gain columns
-            if (lane < 3) {
-              const int r = lane;
-              const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = h0;
-              const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = h1;
-              const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
-              const double p0 = sm.PRR[r], p1 = sm.PRR[r + 3], p2 = sm.PRR[r + 6];
-              const double pa = sm.SR[r][c0], pb = sm.SR[r][c0 + 1];
-              const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
-              const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
-              const double B0 = pa * c00 + pb * c10;
-              const double B1 = pa * c01 + pb * c11;
-              M0 = A0 + B0; M1 = A1 + B1;
+          // the pair exchanges its rows of S (every lane takes part; the loads above are complete here)
+          const double Oa = __shfl_xor_sync(0xffffffffu, Sa, 1), Ob = __shfl_xor_sync(0xffffffffu, Sb, 1);
+          if (have) {
+            if (fold_prop) {                               // lane gi stores the propagated strip row gi
+              sm.SR[0][2 * gl + gi] = gi ? s0.y : s0.x;
+              sm.SR[1][2 * gl + gi] = gi ? s1.y : s1.x;
+              sm.SR[2][2 * gl + gi] = gi ? s2.y : s2.x;
             }
-          };
-          // four lanes per candidate, eight candidates per round; with a single candidate every quad
-          // evaluates it, so no reduction or broadcast is needed
-          for (int base = 0; base < nTot; base += 8) {
-            const int gi = base + (lane >> 2), e = lane & 3;
-            const bool have = single || gi < nTot;
-            const int lm = single ? (mA ? __ffs(mA) - 1 : 31 + __ffs(mB)) : (have ? sm.list[gi] : 0);
-            GatePre pre;
-            double p[6], pll[4];
-            {
-              const double2 xy = *reinterpret_cast<const double2*>(&sm.xl[2 * lm]);
-#pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                const double2 v = *reinterpret_cast<const double2*>(&sm.SR[j][2 * lm]);
-                p[2 * j] = v.x; p[2 * j + 1] = v.y;
-              }
-              const double p10 = sm.Dd[1][lm];
-              pll[0] = sm.Dd[0][lm]; pll[1] = p10; pll[2] = p10; pll[3] = sm.Dd[2][lm];
-              ekf_gate_prelude(u, xy.x, xy.y, pre);
-            }
-            if (single) pose_rows(2 * lm, pre.HR[4], pre.HR[5]);
-            const double Sk = ekf_gate_S_element(u, pre, p, pll, e);
-            double Sraw[4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) Sraw[kk] = __shfl_sync(0xffffffffu, Sk, (lane & ~3) + kk);
-            GateResult g;
+            const double Sraw[4] = {gi ? Oa : Sa, gi ? Sa : Oa, gi ? Ob : Sb, gi ? Sb : Ob};
             ekf_gate_from_S(pre, Sraw, k.cond_max, g);
-            const bool valid = have && !g.skip && (k.mahal_init > g.d2);   // Update.cpp:131,140
-            const double val = valid ? g.d2 : INFINITY;
-            const int my_idx = valid ? 3 + 2 * lm : INT_MAX;
-            if (single) {
-              ldl(g.S[0], g.S[1], g.S[3]);
-              bval = val; bidx = my_idx;
-              bres0 = g.res0; bres1 = g.res1; bS0 = g.S[0]; bS1 = g.S[1]; bS2 = g.S[2]; bS3 = g.S[3];
-              bh0 = g.h3_0; bh1 = g.h3_1;
-              bSi0 = g.Si[0]; bSi1 = g.Si[1]; bSi2 = g.Si[2]; bSi3 = g.Si[3];
-            } else {
-              int idx;
-              {   // warp argmin, lowest index wins ties (Update.cpp:140)
-                const unsigned long long key = dt_key(val + 0.0);
-                const unsigned long long mk = dt_warp_min_key(key);
-                idx = (int)__reduce_min_sync(0xffffffffu, key == mk ? (unsigned)my_idx : (unsigned)INT_MAX);
-              }
-              if (idx != INT_MAX) {
-                const int src = __ffs(__ballot_sync(0xffffffffu, my_idx == idx)) - 1;
-                const double cv = __shfl_sync(0xffffffffu, val, src);
-                if (cv < bval || (cv == bval && idx < bidx)) {
-                  bval = cv; bidx = idx;
-                  bres0 = __shfl_sync(0xffffffffu, g.res0, src); bres1 = __shfl_sync(0xffffffffu, g.res1, src);
-                  bS0 = __shfl_sync(0xffffffffu, g.S[0], src); bS1 = __shfl_sync(0xffffffffu, g.S[1], src);
-                  bS2 = __shfl_sync(0xffffffffu, g.S[2], src); bS3 = __shfl_sync(0xffffffffu, g.S[3], src);
-                  bh0 = __shfl_sync(0xffffffffu, g.h3_0, src); bh1 = __shfl_sync(0xffffffffu, g.h3_1, src);
-                  bSi0 = __shfl_sync(0xffffffffu, g.Si[0], src); bSi1 = __shfl_sync(0xffffffffu, g.Si[1], src);
-                  bSi2 = __shfl_sync(0xffffffffu, g.Si[2], src); bSi3 = __shfl_sync(0xffffffffu, g.Si[3], src);
-                }
+            // L D L^T of S (what the downdate needs if this landmark wins), beside the gate's own latencies
+            d0 = g.S[0]; ll = g.S[1] / g.S[0]; d1 = g.S[3] - ll * g.S[1];
+            sq0 = sqrt(fabs(d0)); sq1 = sqrt(fabs(d1));
+            const bool valid = !g.skip && (k.mahal_init > g.d2);   // Update.cpp:131,140
+            if (valid) { val = g.d2; my_idx = 3 + 2 * gl; }
+            // Pose rows of the gain, pose correction and their downdate vectors (Update.cpp:186-187) as if this
+            // landmark won: lane 0 of the pair takes rows 0 and 1, lane 1 row 2 (the heading the next step's
+            // scalar chain starts from), so nothing serial follows the argmin.
+            {
+              const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = g.h3_0;
+              const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = g.h3_1;
+              const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
+#pragma unroll
+              for (int rr = 0; rr < 2; ++rr) {
+                if (rr == 1 && gi == 1) break;
+                const int r = gi ? 2 : rr;
+                const double p0 = u.PRR[r], p1 = u.PRR[r + 3], p2 = u.PRR[r + 6];
+                const double pa = r == 0 ? s0.x : (r == 1 ? s1.x : s2.x);   // P(r, c0)   = SR[r][2 gl]
+                const double pb = r == 0 ? s0.y : (r == 1 ? s1.y : s2.y);   // P(r, c0+1) = SR[r][2 gl + 1]
+                const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
+                const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
+                const double B0 = pa * c00 + pb * c10;
+                const double B1 = pa * c01 + pb * c11;
+                const double M0 = A0 + B0, M1 = A1 + B1;
+                const double K0 = M0 * g.Si[0] + M1 * g.Si[1];
+                const double K1 = M0 * g.Si[2] + M1 * g.Si[3];
+                const double xn = sm.xr[r] + (K0 * g.res0 + K1 * g.res1);
+                const double2 wr = make_double2(sq0 * fma(ll, K1, K0), sq1 * K1);
+                if (rr == 0) { pxa = xn; pwa = wr; } else { pxb = xn; pwb = wr; }
               }
             }
           }
-          if (!single && bidx != INT_MAX) {
-            ldl(bS0, bS1, bS3);
-            pose_rows(bidx - 3, bh0, bh1);
+          int idx;
+          {   // warp argmin, lowest index wins ties (Update.cpp:140)
+            const unsigned long long key = dt_key(val + 0.0);
+            const unsigned long long mk = dt_warp_min_key(key);
+            idx = (int)__reduce_min_sync(0xffffffffu, key == mk ? (unsigned)my_idx : (unsigned)INT_MAX);
           }
-          DTILE_TS(3);
-          // ---- decision (Update.cpp:152,181,191) -----------------------------------------------------
-          const int opt_i = (bidx == INT_MAX) ? 0 : bidx;
-          const double mahal = (bidx == INT_MAX) ? k.mahal_init : bval;
-          int decision = ekf_decide(opt_i, mahal, k);
-          if (decision == EKF_DEC_NEW && n_lm >= cap_lm) decision = EKF_DEC_DROPPED;
-          int index = opt_i;
-          DDec& dc = sm.dec;
-          if (decision == EKF_DEC_OLD) {
-            const int c0 = opt_i - 3;
-            const unsigned s0m = d0 < 0 ? 0u : 0x80000000u, s1m = d1 < 0 ? 0u : 0x80000000u;
-            if (lane < 3) {
-              // pose rows of the gain, pose correction, downdate vector (Update.cpp:186-187)
-              const int r = lane;
-              const double K0 = M0 * bSi0 + M1 * bSi1;
-              const double K1 = M0 * bSi2 + M1 * bSi3;
-              sm.xr[r] = sm.xr[r] + (K0 * bres0 + K1 * bres1);
-              dc.WR[r] = make_double2(sq0 * fma(ll, K1, K0), sq1 * K1);
-            }
-            if (lane == 0) {
-              dc.c0 = c0;
-              dc.rt_c0 = dt_rowterm<RB>(c0);
-              dc.ct_c0 = dt_colterm<RB>(c0);
-              dc.sb_c0 = dt_slot<RB>(0, (c0 * 43) >> 9);
-              dc.h3[0] = bh0; dc.h3[1] = bh1;
-              dc.res[0] = bres0; dc.res[1] = bres1;
-              dc.Si[0] = bSi0; dc.Si[1] = bSi1; dc.Si[2] = bSi2; dc.Si[3] = bSi3;
-              dc.l = ll; dc.sq0 = sq0; dc.sq1 = sq1;
-              dc.sm0 = s0m; dc.sm1 = s1m;
-              { const int sl = cnt & (KH - 1); sm.hs0[sl] = s0m; sm.hs1[sl] = s1m; sm.hrank[sl] = 2; }
-            }
-          } else if (decision == EKF_DEC_NEW) {
-            index = 3 + 2 * n_lm;
-            if (lane == 0) {
-              // state augmentation blocks (Update.cpp:152-168)
-              const double c = u.c, s = u.s, z0 = zr[0], z1 = zr[1];
-              const double Cz0 = c * z0 + (-s) * z1, Cz1 = s * z0 + c * z1;   // Update.cpp:155
-              const double nl0 = u.x0 + Cz0, nl1 = u.x1 + Cz1;
-              const double dn0 = nl0 - u.x0, dn1 = nl1 - u.x1;
-              const double h30 = u.mCtJ[0] * dn0 + u.mCtJ[2] * dn1;
-              const double h31 = u.mCtJ[1] * dn0 + u.mCtJ[3] * dn1;
-              const double HR[6] = {u.mCt[0], u.mCt[1], u.mCt[2], u.mCt[3], h30, h31};
-              double a1[6], t1[4], in[4], b1[4];
-              for (int j = 0; j < 3; ++j) {
-                a1[0 + 2 * j] = u.q[0 + 2 * j] + h30 * u.PRR[2 + 3 * j];
-                a1[1 + 2 * j] = u.q[1 + 2 * j] + h31 * u.PRR[2 + 3 * j];
-              }
-              for (int j = 0; j < 2; ++j)
-                for (int i = 0; i < 2; ++i)
-                  t1[i + 2 * j] = (a1[i] * HR[j] + a1[i + 2] * HR[j + 2]) + a1[i + 4] * HR[j + 4];
-              for (int w2 = 0; w2 < 4; ++w2) in[w2] = t1[w2] + u.R[w2];
-              const double Cm[4] = {u.Ct[0], u.Ct[2], u.Ct[1], u.Ct[3]};
-              for (int j = 0; j < 2; ++j)
-                for (int i = 0; i < 2; ++i) b1[i + 2 * j] = Cm[i] * in[0 + 2 * j] + Cm[i + 2] * in[1 + 2 * j];
-              for (int j = 0; j < 2; ++j)       // Update.cpp:168
-                for (int i = 0; i < 2; ++i)
-                  dc.PLL[i + 2 * j] = b1[i] * u.Ct[0 + 2 * j] + b1[i + 2] * u.Ct[1 + 2 * j];
-              dc.nl[0] = nl0; dc.nl[1] = nl1;
-              dc.h3n[0] = h30; dc.h3n[1] = h31;
-            }
-          } else if (decision == EKF_DEC_DROPPED) {
-            index = -1;
-          }
-          if (lane < 4) { dc.Ct[lane] = u.Ct[lane]; dc.mCt[lane] = u.mCt[lane]; }
-          if (lane == 0) {
-            dc.decision = decision;
-            const size_t oi = ((size_t)f * T_steps + t) * M + m;
-            if (a.io.decision) a.io.decision[oi] = decision;
-            if (a.io.index) a.io.index[oi] = index;
-            if (a.io.mahal) a.io.mahal[oi] = mahal;
+          DCand& cd = sm.cand[warp];
+          if (idx == INT_MAX) {
+            if (lane == 0) { cd.val = INFINITY; cd.idx = INT_MAX; }
+          } else if (my_idx == idx && gi == 1) {
+            cd.xr[2] = pxa; cd.WR[2] = pwa;
+          } else if (my_idx == idx) {
+            cd.xr[0] = pxa; cd.WR[0] = pwa; cd.xr[1] = pxb; cd.WR[1] = pwb;
+            const int c0 = 2 * gl;
+            cd.val = val; cd.idx = idx; cd.c0 = c0;
+            cd.rt_c0 = dt_rowterm<RB>(c0); cd.ct_c0 = dt_colterm<RB>(c0);
+            cd.res[0] = g.res0; cd.res[1] = g.res1;
+            cd.S[0] = g.S[0]; cd.S[1] = g.S[1]; cd.S[2] = g.S[2]; cd.S[3] = g.S[3];
+            cd.Si[0] = g.Si[0]; cd.Si[1] = g.Si[1]; cd.Si[2] = g.Si[2]; cd.Si[3] = g.Si[3];
+            cd.h3[0] = g.h3_0; cd.h3[1] = g.h3_1;
+            cd.l = ll; cd.sq0 = sq0; cd.sq1 = sq1;
+            cd.sm0 = d0 < 0 ? 0u : 0x80000000u; cd.sm1 = d1 < 0 ? 0u : 0x80000000u;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { cd.Ct[w] = u.Ct[w]; cd.mCt[w] = u.mCt[w]; }
           }
         }
+        fold_prop = false;
+        DTILE_TS(3);
+        __syncthreads();                                 // B2: candidates published
         DTILE_TS(4);
-        const bool last_meas = m == nz - 1;
-        if (helper && last_meas && t + 1 < T_steps) helper_pre(recbuf + (size_t)((t + 1) & 1) * Lp);   // idle window of the helper warp
-        if (last_meas && t + 1 < T_steps) pre_done = true;
-        __syncthreads();                                 // B3: decision published (and the next record visible)
-        DTILE_TS(5);
-        const int decision = sm.dec.decision;
+        // ---- decision (Update.cpp:152,181,191), uniform over the CTA ----------------------------------
+        int wsel = 0;
+        int decision, index;
+        double mahal;
+        {
+          double val = sm.cand[0].val;
+          int idx = sm.cand[0].idx;
+#pragma unroll
+          for (int w = 1; w < 4; ++w) {
+            const double ov = sm.cand[w].val;
+            const int oi = sm.cand[w].idx;
+            if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; wsel = w; }
+          }
+          const int opt_i = (idx == INT_MAX) ? 0 : idx;
+          mahal = (idx == INT_MAX) ? k.mahal_init : val;
+          decision = ekf_decide(opt_i, mahal, k);
+          if (decision == EKF_DEC_NEW && n_lm >= cap_lm) decision = EKF_DEC_DROPPED;
+          index = opt_i;
+          if (decision == EKF_DEC_NEW) index = 3 + 2 * n_lm;
+          if (decision == EKF_DEC_DROPPED) index = -1;
+        }
+        const DCand& dc = sm.cand[wsel];
+        if (tid == 0) {
+          const size_t oi = ((size_t)f * T_steps + t) * M + m;
+          if (a.io.decision) a.io.decision[oi] = decision;
+          if (a.io.index) a.io.index[oi] = index;
+          if (a.io.mahal) a.io.mahal[oi] = mahal;
+        }
         setup_valid = false;
         if (decision == EKF_DEC_OLD) {
-          if (cnt - min(ap_o, ap_f) > KH - 1) flush_all();   // no free history slot (compass / several measurements per step)
+          if (cnt - ap > KH - 1) flush_all();              // no free history slot (compass / several measurements per step)
           const int sl = cnt & (KH - 1);
-          const bool fsweep = cnt - ap_f >= KH - 1;          // the front warp sweeps its tiles behind the row threads' reads
-          const DDec& dc = sm.dec;
           if (helper) {
-            // ---- P_RR downdate ----------------------------------------------------------------------------
-            prr_eager(sl);                               // then straight on to the next step's chain (top of the loop)
+            // ---- the winner's pose, the history entry's signs, P_RR downdate; then straight on to the next
+            // step's chain (top of the loop)
+            if (lane < 3) { sm.xr[lane] = dc.xr[lane]; sm.WR[lane] = dc.WR[lane]; }
+            if (lane == 0) { sm.hs0[sl] = dc.sm0; sm.hs1[sl] = dc.sm1; sm.hrank[sl] = 2; }
+            __syncwarp();
+            prr_eager(sl);
           }
           if (rows_warp) {
             // ---- gain rows, state, downdate vectors (Update.cpp:186-187): one landmark (two rows) per thread
             const bool live = lrow < n_lm;
             double2 wA = make_double2(0.0, 0.0), wB = make_double2(0.0, 0.0);
             double uA0 = 0.0, uA1 = 0.0, uB0 = 0.0, uB1 = 0.0;
+            double2 s0 = make_double2(0.0, 0.0), s1 = s0, s2 = s0;
             if (live) {
               const int c0 = dc.c0, hc0 = dt_hidx<RB>(c0);
-              const double2 s0 = *reinterpret_cast<const double2*>(&sm.SR[0][q0]);
-              const double2 s1 = *reinterpret_cast<const double2*>(&sm.SR[1][q0]);
-              const double2 s2 = *reinterpret_cast<const double2*>(&sm.SR[2][q0]);
+              s0 = *reinterpret_cast<const double2*>(&sm.SR[0][q0]);
+              s1 = *reinterpret_cast<const double2*>(&sm.SR[1][q0]);
+              s2 = *reinterpret_cast<const double2*>(&sm.SR[2][q0]);
               double paA, pbA, paB, pbB;                 // P(q0, c0), P(q0, c0+1), P(q0+1, c0), P(q0+1, c0+1)
               if ((q0 >> 2) == (c0 >> 2)) {              // same aligned pair: eager entries, already current
                 if (q0 == c0) {
@@ -909,19 +710,15 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
                   else { paA = e0; pbA = e2; paB = e1; pbB = e3; }          // this landmark is the second: P(4m+2+i, 4m+j) = Do[i+2j]
                 }
               } else {
-                // stored tile entries + the pending downdates of that tile, in order (the deferred sweep's fma sequence)
-                int tslot;
+                // stored tile entries + the pending downdates, in order (the deferred sweep's fma sequence)
                 if (q0 > c0) {
                   const int ad = rt_l + dc.ct_c0;        // (q0, c0)
                   paA = T[ad]; pbA = T[ad + 4 * PS + 1]; paB = T[ad + PS]; pbB = T[ad + 5 * PS + 1];
-                  tslot = dc.sb_c0 + (q0 >> 2);
                 } else {
                   const int ad = dc.rt_c0 + ct_l;        // (c0, q0)
                   paA = T[ad]; pbA = T[ad + PS]; paB = T[ad + 4 * PS + 1]; pbB = T[ad + 5 * PS + 1];
-                  tslot = sb_l + (c0 >> 2);
                 }
-                const int efrom = (tslot >> 5) == rot ? ap_f : ap_o;   // what the tile's owner has applied so far
-                for (int en = efrom; en < cnt; ++en) {
+                for (int en = ap; en < cnt; ++en) {
                   const int p = en & (KH - 1);
                   const double2 wqa = sm.H[p][hq0], wqb = sm.H[p][hq0 + HP], wa = sm.H[p][hc0], wb = sm.H[p][hc0 + HP];
                   const unsigned m0 = sm.hs0[p], m1 = sm.hs1[p];
@@ -938,7 +735,6 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
               const double h00 = dc.mCt[0], h01 = dc.mCt[2], h02 = dc.h3[0];
               const double h10 = dc.mCt[1], h11 = dc.mCt[3], h12 = dc.h3[1];
               const double c00 = dc.Ct[0], c10 = dc.Ct[2], c01 = dc.Ct[1], c11 = dc.Ct[3];
-              const double2 w0 = dc.WR[0], w1 = dc.WR[1], w2 = dc.WR[2];
               {   // row q0
                 const double A0 = (s0.x * h00 + s1.x * h01) + s2.x * h02;
                 const double A1 = (s0.x * h10 + s1.x * h11) + s2.x * h12;
@@ -963,10 +759,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
                 wB = make_double2(dc.sq0 * fma(dc.l, K1, K0), dc.sq1 * K1);
                 uB0 = dt_flip(wB.x, dc.sm0); uB1 = dt_flip(wB.y, dc.sm1);
               }
-              // eager downdate of the strip rows and of the landmark's own 2x2 block (Update.cpp:188,193-194)
-              *reinterpret_cast<double2*>(&sm.SR[0][q0]) = make_double2(fma(uA0, w0.x, fma(uA1, w0.y, s0.x)), fma(uB0, w0.x, fma(uB1, w0.y, s0.y)));
-              *reinterpret_cast<double2*>(&sm.SR[1][q0]) = make_double2(fma(uA0, w1.x, fma(uA1, w1.y, s1.x)), fma(uB0, w1.x, fma(uB1, w1.y, s1.y)));
-              *reinterpret_cast<double2*>(&sm.SR[2][q0]) = make_double2(fma(uA0, w2.x, fma(uA1, w2.y, s2.x)), fma(uB0, w2.x, fma(uB1, w2.y, s2.y)));
+              // eager downdate of the landmark's own 2x2 block (Update.cpp:188,193-194)
               sm.Dd[0][lrow] = fma(uA0, wA.x, fma(uA1, wA.y, sm.Dd[0][lrow]));
               sm.Dd[1][lrow] = fma(uB0, wA.x, fma(uB1, wA.y, sm.Dd[1][lrow]));
               sm.Dd[2][lrow] = fma(uB0, wB.x, fma(uB1, wB.y, sm.Dd[2][lrow]));
@@ -975,7 +768,6 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
               sm.H[sl][hq0] = wA;
               sm.H[sl][hq0 + HP] = wB;
             }
-            if (fsweep) dt_bar_arrive(3, 96);            // this warp's tile reads are done
             {   // 2x2 block between the two landmarks of an aligned pair: rows of the odd one, columns of the even one
               const double pAx = __shfl_up_sync(0xffffffffu, wA.x, 1), pAy = __shfl_up_sync(0xffffffffu, wA.y, 1);
               const double pBx = __shfl_up_sync(0xffffffffu, wB.x, 1), pBy = __shfl_up_sync(0xffffffffu, wB.y, 1);
@@ -987,24 +779,52 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
                 sm.Do[3][m2] = fma(uB0, pBx, fma(uB1, pBy, sm.Do[3][m2]));   // (4m+3, 4m+1)
               }
             }
+            if (live) {                                  // eager downdate of the strip rows
+              const double2 w0 = dc.WR[0], w1 = dc.WR[1], w2 = dc.WR[2];
+              *reinterpret_cast<double2*>(&sm.SR[0][q0]) = make_double2(fma(uA0, w0.x, fma(uA1, w0.y, s0.x)), fma(uB0, w0.x, fma(uB1, w0.y, s0.y)));
+              *reinterpret_cast<double2*>(&sm.SR[1][q0]) = make_double2(fma(uA0, w1.x, fma(uA1, w1.y, s1.x)), fma(uB0, w1.x, fma(uB1, w1.y, s1.y)));
+              *reinterpret_cast<double2*>(&sm.SR[2][q0]) = make_double2(fma(uA0, w2.x, fma(uA1, w2.y, s2.x)), fma(uB0, w2.x, fma(uB1, w2.y, s2.y)));
+            }
           }
-          if (front && fsweep) {
-            dt_bar_sync(3, 96);                          // both row warps have read the tiles
-            sweep_own(ap_f, cnt);
-          }
-          if (fsweep) ap_f = cnt;
           DTILE_TS(6);
           cnt += 1;
         } else if (decision == EKF_DEC_NEW) {
           // ---- state augmentation (Update.cpp:152-178); pending downdates are applied first ----------
-          if (cnt > min(ap_o, ap_f)) flush_all();
-          const DDec& dc = sm.dec;
+          if (tid == 0) {
+            const UpdateSetup& u = sm.upd;
+            const double c = u.c, s = u.s, z0 = zr[0], z1 = zr[1];
+            const double Cz0 = c * z0 + (-s) * z1, Cz1 = s * z0 + c * z1;   // Update.cpp:155
+            const double nl0 = u.x0 + Cz0, nl1 = u.x1 + Cz1;
+            const double dn0 = nl0 - u.x0, dn1 = nl1 - u.x1;
+            const double h30 = u.mCtJ[0] * dn0 + u.mCtJ[2] * dn1;
+            const double h31 = u.mCtJ[1] * dn0 + u.mCtJ[3] * dn1;
+            const double HR[6] = {u.mCt[0], u.mCt[1], u.mCt[2], u.mCt[3], h30, h31};
+            double a1[6], t1[4], in[4], b1[4];
+            for (int j = 0; j < 3; ++j) {
+              a1[0 + 2 * j] = u.q[0 + 2 * j] + h30 * u.PRR[2 + 3 * j];
+              a1[1 + 2 * j] = u.q[1 + 2 * j] + h31 * u.PRR[2 + 3 * j];
+            }
+            for (int j = 0; j < 2; ++j)
+              for (int i = 0; i < 2; ++i)
+                t1[i + 2 * j] = (a1[i] * HR[j] + a1[i + 2] * HR[j + 2]) + a1[i + 4] * HR[j + 4];
+            for (int w2 = 0; w2 < 4; ++w2) in[w2] = t1[w2] + u.R[w2];
+            const double Cm[4] = {u.Ct[0], u.Ct[2], u.Ct[1], u.Ct[3]};
+            for (int j = 0; j < 2; ++j)
+              for (int i = 0; i < 2; ++i) b1[i + 2 * j] = Cm[i] * in[0 + 2 * j] + Cm[i + 2] * in[1 + 2 * j];
+            for (int j = 0; j < 2; ++j)       // Update.cpp:168
+              for (int i = 0; i < 2; ++i)
+                sm.PLL[i + 2 * j] = b1[i] * u.Ct[0 + 2 * j] + b1[i + 2] * u.Ct[1 + 2 * j];
+            sm.nl[0] = nl0; sm.nl[1] = nl1;
+            sm.h3n[0] = h30; sm.h3n[1] = h31;
+          }
+          flush_all();                                   // tiles current; the New blocks visible
+          const UpdateSetup& u = sm.upd;
           const int qn = 2 * n_lm;                       // P_LL rows of the new landmark
           const bool pose_row = tid >= NQ && tid < NQ + 3;
           if (q < qn || pose_row) {                      // P_xL = -P[:,0:3]*H_R^T*H_Li (:169), existing row
-            const double h00 = dc.mCt[0], h01 = dc.mCt[2], h02 = dc.h3n[0];
-            const double h10 = dc.mCt[1], h11 = dc.mCt[3], h12 = dc.h3n[1];
-            const double ct00 = dc.Ct[0], ct10 = dc.Ct[1], ct01 = dc.Ct[2], ct11 = dc.Ct[3];
+            const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = sm.h3n[0];
+            const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = sm.h3n[1];
+            const double ct00 = u.Ct[0], ct10 = u.Ct[1], ct01 = u.Ct[2], ct11 = u.Ct[3];
             double e0, e1, e2;
             if (pose_row) { const int r = tid - NQ; e0 = sm.PRR[r]; e1 = sm.PRR[r + 3]; e2 = sm.PRR[r + 6]; }
             else { e0 = sm.SR[0][q]; e1 = sm.SR[1][q]; e2 = sm.SR[2][q]; }
@@ -1016,18 +836,25 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
             else { *pll_ref(qn, q) = v0; *pll_ref(qn + 1, q) = v1; }
           }
           if (tid == 0) {
-            const double off = 0.5 * (dc.PLL[2] + dc.PLL[1]);   // :193-194 on the new 2x2 block
-            sm.Dd[0][n_lm] = dc.PLL[0];
+            const double off = 0.5 * (sm.PLL[2] + sm.PLL[1]);   // :193-194 on the new 2x2 block
+            sm.Dd[0][n_lm] = sm.PLL[0];
             sm.Dd[1][n_lm] = off;
-            sm.Dd[2][n_lm] = dc.PLL[3];
-            sm.xl[qn] = dc.nl[0];
-            sm.xl[qn + 1] = dc.nl[1];
+            sm.Dd[2][n_lm] = sm.PLL[3];
+            sm.xl[qn] = sm.nl[0];
+            sm.xl[qn + 1] = sm.nl[1];
           }
           n_lm += 1;
           sync_first = true;
         } else if (decision == EKF_DEC_DROPPED) {
           dropped = 1;
         }
+      }
+      // ---- warp 0 (idle during the gain phase): record-only scalars of the next step -----------------
+      if (warp == 0) {
+        fetch_record(t + 3);                             // into the slot of this step's record (not read any more)
+        dt_cp_async_wait_1();                            // record t+2 has landed
+        __syncwarp();
+        warp0_pre(t + 2);
       }
       DTILE_TS(8);
     }
@@ -1066,7 +893,7 @@ __global__ void __launch_bounds__(DT_THREADS, 4) ekf_batch_dtile_kernel(const DR
 template <int RB>
 size_t dtile_smem_bytes(int L) {
   return ((sizeof(DSmem<RB>) + 15) & ~(size_t)15) + (size_t)((DCfg<RB>::TSIZE + 1) & ~1) * sizeof(double) +
-         (size_t)2 * ((L + 1) & ~1) * sizeof(double);
+         (size_t)3 * ((L + 1) & ~1) * sizeof(double);
 }
 
 template <int RB>

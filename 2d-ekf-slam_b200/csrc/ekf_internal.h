@@ -64,7 +64,7 @@ cudaError_t ekf_stile_timestamps(long long* out128);
 cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
 
 // Deferred-downdate variant (ekf_dtile.cu): eager strip / diagonal blocks, P_LL tiles swept once per
-// four updates, gating on one warp with exact re-evaluation on demand; four filters per SM, <= 50 landmarks.
+// three updates, exact gating with two lanes per landmark; four filters per SM, <= 50 landmarks.
 int ekf_dtile_max_landmarks();
 int ekf_dtile_ctas_per_sm();
 cudaError_t ekf_dtile_timestamps(long long* out64);

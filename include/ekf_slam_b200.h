@@ -53,13 +53,13 @@ extern "C" {
 #define EKF_REGIME_LARGE 2      /* whole grid per filter; covariance streamed from HBM          */
 
 /* ---- fused-kernel variants of the batch regime (same arithmetic, bit-identical results) ------- */
-#define EKF_BATCH_KERNEL_AUTO 0   /* DTILE when max_landmarks <= 50, STILE when <= 62, else SMEM   */
+#define EKF_BATCH_KERNEL_AUTO 0   /* STILE when max_landmarks <= 62 (measured fastest), else SMEM  */
 #define EKF_BATCH_KERNEL_SMEM 1   /* covariance resident in shared memory                         */
 #define EKF_BATCH_KERNEL_TILE 2   /* covariance's lower block triangle resident in registers      */
 #define EKF_BATCH_KERNEL_STILE 3  /* lower block triangle tiled in shared memory, 4 filters per SM */
-#define EKF_BATCH_KERNEL_DTILE 4  /* as STILE with the O(n^2) downdate deferred: tiles swept once per
-                                     four updates, gating on one warp with exact re-evaluation on
-                                     demand; max_landmarks <= 50                                    */
+#define EKF_BATCH_KERNEL_DTILE 4  /* as STILE with the O(n^2) downdate deferred (tiles swept once per
+                                     three updates, strip / diagonal blocks updated eagerly), exact
+                                     gating with two lanes per landmark; max_landmarks <= 50         */
 
 typedef struct ekf_handle_s* ekf_handle;
 

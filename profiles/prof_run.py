@@ -64,9 +64,9 @@ def batch(F=592, T=1000, cap=50):
             prev = mx
     if os.environ.get("EKF_DTILE_TS"):      # -DEKF_DTILE_TIMING builds (make timing; EKF_B200_LIB=.../libekf_slam_b200_timing.so)
         ts = ekf.debug_dtile_timestamps()
-        names = ["step start (before B1)", "after B2 (strip propagated)", "front: screen done", "front: exact pass done",
-                 "before B3 (front: decision published)", "after B3", "rows / helper chain done", "-", "step end",
-                 "sweep start (a step of 498..501)", "sweep end"]
+        names = ["step start (before B1; warp 2 = helper chain done)", "after B1", "before gating (after the sweep, if any)",
+                 "gating done (candidate written)", "after B2", "-", "gain phase / pose rows done", "-", "step end (warp 0: record scalars done)",
+                 "-", "-"]
         t0 = ts[:, 0][ts[:, 0] > 0].min()
         print("stamps of CTA 0, first filter, step 501 (cycles since the first warp entered the step); front warp = the one with stamps 2,3:")
         print("  %-40s %s" % ("", " ".join("    w%d" % w for w in range(4))))
