@@ -63,6 +63,7 @@ struct ekf_handle_s {
   DevBuf<double> records;
   DevBuf<int> t_dec, t_idx;
   DevBuf<double> t_mah, t_pose;
+  DevBuf<int> resume;         // [F] park codes of the two-launch growth path (launch_batch_kernel)
   int rec_T = 0, rec_M = 0, rec_L = 0;
   bool have_trace = false, have_pose_trace = false;
   std::vector<uint8_t> flag_compass, flag_nz;   // host mirror [F][T] of record flags (regime B)
@@ -115,6 +116,24 @@ int pick_batch_kernel(ekf_handle h) {
 
 cudaError_t launch_batch_kernel(ekf_handle h, int kern, const EkfState& st, const EkfRunIO& io) {
   if (kern == 4) return ekf_dtile_run(st, io, h->k, h->sm_count, h->stream);
+  if (kern == 3 && h->cfg.batch_kernel == EKF_BATCH_KERNEL_AUTO && st.cap_lm > ekf_stile_fast_landmarks()) {
+    // Capacity beyond the four-filters-per-SM tile size (Update.cpp:158-177 grows the map without bound):
+    // every filter starts in the fast small-tile instance; the few whose map outgrows it are written
+    // back ("parked") and finished, from the measurement where they stopped, by the instance sized for
+    // the handle's capacity. Same arithmetic in both, so the result does not depend on where a filter ran.
+    cudaError_t e = h->resume.reserve((size_t)h->st.F);
+    if (e != cudaSuccess) return e;
+    EkfRunIO io2 = io;
+    io2.resume = h->resume.p + (st.nlm - h->st.nlm);
+    e = cudaMemsetAsync(io2.resume, 0, (size_t)st.F * sizeof(int), h->stream);
+    if (e != cudaSuccess) return e;
+    io2.continuation = 0;
+    e = ekf_stile_run(st, io2, h->k, h->sm_count, h->stream, ekf_stile_fast_landmarks());
+    if (e != cudaSuccess) return e;
+    io2.continuation = 1;
+    h->launches += 1;
+    return ekf_stile_run(st, io2, h->k, h->sm_count, h->stream, 0);
+  }
   if (kern == 3) return ekf_stile_run(st, io, h->k, h->sm_count, h->stream);
   if (kern == 2) return ekf_tile_run(st, io, h->k, h->sm_count, h->stream);
   return ekf_batch_run(st, io, h->k, h->grid_cap, h->stream);
@@ -323,6 +342,7 @@ int ekf_destroy(ekf_handle h) {
   cudaFree(h->st.x); cudaFree(h->st.P); cudaFree(h->st.nlm); cudaFree(h->st.status);
   cudaFree(h->wk.W); cudaFree(h->wk.cand_val); cudaFree(h->wk.cand_idx); cudaFree(h->wk.small);
   h->in.release(); h->o_dec.release(); h->o_idx.release(); h->o_mah.release(); h->in_valid.release();
+  h->resume.release();
   h->records.release(); h->t_dec.release(); h->t_idx.release(); h->t_mah.release(); h->t_pose.release();
   if (h->ev0) {
     cudaEventDestroy(h->ev0);
@@ -583,7 +603,7 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
     return fail(h, EKF_ERR_UNSUPPORTED, "the requested fused kernel does not support max_landmarks = " + std::to_string(h->st.cap_lm) + " (TILE / STILE: <= " + std::to_string(ekf_tile_max_landmarks()) + ", DTILE: <= " + std::to_string(ekf_dtile_max_landmarks()) + ")");
   // chunk = a multiple of the co-resident CTA count (2 filters per CTA), at most kMaxChunks chunks
   const size_t wave = (size_t)(kern == 4 ? ekf_dtile_ctas_per_sm() * h->sm_count
-                               : kern == 3 ? ekf_stile_ctas_per_sm(st.cap_lm) * h->sm_count
+                               : kern == 3 ? ekf_stile_ctas_per_sm(h->cfg.batch_kernel == EKF_BATCH_KERNEL_AUTO ? 1 : st.cap_lm) * h->sm_count
                                            : (kern == 2 ? 2 * h->sm_count : h->grid_cap));
   size_t chunk = 2 * wave;
   while ((F + chunk - 1) / chunk > (size_t)kMaxChunks) chunk += wave;
@@ -649,6 +669,19 @@ int ekf_sync(ekf_handle h) {
   cudaSetDevice(h->device);
   EKF_CK(h, cudaStreamSynchronize(h->stream));
   return check_status(h);
+}
+
+int ekf_capacity_flags(ekf_handle h, int* n_flagged, int clear) {
+  if (!h || !n_flagged) return EKF_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  std::vector<int> s(h->st.F);
+  EKF_CK(h, cudaMemcpyAsync(s.data(), h->st.status, sizeof(int) * h->st.F, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  int n = 0;
+  for (int f = 0; f < h->st.F; ++f) n += (s[f] & 1);
+  *n_flagged = n;
+  if (clear) EKF_CK(h, cudaMemsetAsync(h->st.status, 0, sizeof(int) * h->st.F, h->stream));
+  return EKF_OK;
 }
 
 const char* ekf_last_error(ekf_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }

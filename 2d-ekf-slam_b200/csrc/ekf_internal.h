@@ -27,6 +27,13 @@ struct EkfRunIO {
   int* index;              // [F][T][M] or null
   double* mahal;           // [F][T][M] or null
   double* pose_trace;      // [F][T][3] or null
+  // Growth beyond a kernel's tile capacity (ekf_stile.cu): a filter whose map outgrows the kernel that
+  // runs it is written back and "parked"; resume[f] = 1 + t*(M+1) + m says where (step t propagated,
+  // next measurement m; -1 = before step 0). A continuation launch (continuation = 1) of a kernel with
+  // larger tiles visits only the parked filters and picks up there. null = no parking (New at capacity
+  // is dropped and flagged).
+  int* resume;             // [F] or null
+  int continuation;
 };
 
 struct EkfPercallIO {
@@ -61,7 +68,9 @@ cudaError_t ekf_tile_run(const EkfState& st, const EkfRunIO& io, const EkfConst&
 int ekf_stile_max_landmarks();
 int ekf_stile_ctas_per_sm(int cap_lm);
 cudaError_t ekf_stile_timestamps(long long* out128);
-cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream);
+cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream,
+                          int tile_cap = 0);
+int ekf_stile_fast_landmarks();   // capacity of the four-filters-per-SM instance
 
 // Deferred-downdate variant (ekf_dtile.cu): eager strip / diagonal blocks, P_LL tiles swept once per
 // three updates, exact gating with two lanes per landmark; four filters per SM, <= 50 landmarks.

@@ -158,9 +158,15 @@ __device__ __forceinline__ void tile_downdate(double* __restrict__ Tt, const dou
   }
 }
 
-template <int NB>
+// MODE 0: plain (a New association at capacity is dropped and flagged). MODE 1: the fast small-tile
+// instance of the growth path - a filter whose map outgrows the tiles is written back and parked
+// (io.resume). MODE 2: the continuation - visits only the parked filters and resumes them at the
+// measurement where they stopped. Separate instantiations, so the plain and the parking kernels do
+// not carry the resume logic.
+template <int NB, int MODE>
 __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf_batch_stile_kernel(const RunArgs a) {
   using C = STileCfg<NB>;
+  constexpr bool CAN_PARK = MODE == 1, CAN_RESUME = MODE == 2;
   constexpr int NT = C::PS, SP0 = C::SP0;   // NT: plane stride of the tile storage
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* T = reinterpret_cast<double*>(smem_raw);                               // [32][NT]
@@ -191,6 +197,17 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
     const double* grec = a.io.records + (size_t)f * T_steps * L;
     int n_lm = a.st.nlm[f];
     int dropped = 0;
+    int t_begin = 0, m_begin = 0, parked = 0;
+    bool resumed = false;
+    if (CAN_RESUME) {
+      const int code = a.io.resume[f];
+      if (code == 0) continue;                           // finished by the primary launch
+      if (code > 0) { t_begin = (code - 1) / (M + 1); m_begin = (code - 1) % (M + 1); resumed = true; }
+    }
+    if (CAN_PARK && n_lm > C::MAX_LM) {                  // the map does not fit this kernel's tiles: leave it to the continuation
+      if (tid == 0) a.io.resume[f] = -1;
+      continue;
+    }
     {
       const int n_int = 4 + 2 * n_lm;
       // Column by column (a warp per column, a lane per row): the HBM reads are contiguous runs and
@@ -224,7 +241,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
         }
       }
       for (int r = tid; r < C::NI; r += C::THREADS) sm.xs[r] = (r != 3 && r < n_int) ? gx[ext_index(r)] : 0.0;
-      for (int i = tid; i < L; i += C::THREADS) cp_async8(recbuf + i, grec + i);
+      for (int i = tid; i < L; i += C::THREADS) cp_async8(recbuf + (size_t)(t_begin & 1) * Lp + i, grec + (size_t)t_begin * L + i);   // t_begin = 0 unless resumed
       cp_async_wait_all();
     }
     __syncthreads();
@@ -263,8 +280,9 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
     };
     bool scalar_done = false;
 
-    for (int t = 0; t < T_steps; ++t) {
+    for (int t = CAN_RESUME ? t_begin : 0; t < T_steps && !(CAN_PARK && parked); ++t) {
       const double* cur = recbuf + (size_t)(t & 1) * Lp;
+      const bool skip_front = CAN_RESUME && resumed && t == t_begin;   // a resumed filter: this step is already propagated
       if (t + 1 < T_steps) {
         const double* g = grec + (size_t)(t + 1) * L;
         double* nxt = recbuf + (size_t)((t + 1) & 1) * Lp;
@@ -273,6 +291,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
       const int nz = min((int)cur[5], (L - 8) / 6);   // never read past the record's measurement slots
       bool rec_ready = false;
       STILE_TS(0);
+      if (!skip_front) {
       // ---- doPropagation (slam.cpp:136) ------------------------------------------------------------
       if (!scalar_done) {
         scalar_chains(cur);
@@ -311,10 +330,11 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
       }
       STILE_TS(1);
       __syncthreads();
+      }   // !skip_front
 
-      bool setup_valid = true;
+      bool setup_valid = !skip_front;
       // ---- doUpdateCompass (slam.cpp:144-147, kalmanfilter.cpp:96-130) ---------------------------
-      if (cur[6] != 0.0) {
+      if (!skip_front && cur[6] != 0.0) {
         if (tid == 0) {
           sm.cres = ekf_compass_residual(sm.xs[2], cur[3], k);
           sm.cS = T[(2 + 4 * 2) * NT] + cur[4];
@@ -333,7 +353,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
       }
 
       // ---- doUpdate per measurement (slam.cpp:150-171, Update.cpp:80-195) -----------------------
-      for (int m = 0; m < M; ++m) {
+      for (int m = (CAN_RESUME && skip_front) ? m_begin : 0; m < M; ++m) {
         int decision = EKF_DEC_NONE, index = -1;
         double mahal = 0.0;
         if (m < nz) {
@@ -429,9 +449,12 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
             const int opt_i = (idx == INT_MAX) ? 0 : idx;
             mahal = (idx == INT_MAX) ? k.mahal_init : val;
             decision = ekf_decide(opt_i, mahal, k);
-            if (decision == EKF_DEC_NEW && n_lm >= a.st.cap_lm) decision = EKF_DEC_DROPPED;
+            if (decision == EKF_DEC_NEW && n_lm >= a.st.cap_lm) decision = EKF_DEC_DROPPED;   // (tiles are sized for >= cap_lm unless CAN_PARK)
+            if (CAN_PARK && decision == EKF_DEC_NEW && n_lm >= C::MAX_LM)
+              parked = 1 + t * (M + 1) + m;   // the map outgrows this kernel's tiles: a kernel with larger tiles continues here
             index = opt_i ? opt_i - 1 : 0;   // external state index
           }
+          if (CAN_PARK && parked) break;     // nothing of this measurement has been applied (the decision is CTA-uniform)
           const Candidate& cd = sm.cand[wsel];
           STILE_TS(9);
 
@@ -566,7 +589,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
           if (a.io.mahal) a.io.mahal[oi] = mahal;
         }
       }
-      if (a.io.pose_trace && sc_prop) {   // slam.cpp:181; by the lane that overwrites the pose at the next step start
+      if (a.io.pose_trace && sc_prop && !(CAN_PARK && parked)) {   // slam.cpp:181; by the lane that overwrites the pose at the next step start
         double* pt = a.io.pose_trace + ((size_t)f * T_steps + t) * 3;
         pt[0] = sm.xs[0]; pt[1] = sm.xs[1]; pt[2] = sm.xs[2];
       }
@@ -599,6 +622,7 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
       if (tid == 0) {
         a.st.nlm[f] = n_lm;
         if (dropped) a.st.status[f] |= 1;
+        if (MODE != 0) a.io.resume[f] = parked;
       }
     }
     __syncthreads();
@@ -611,7 +635,7 @@ size_t stile_smem_bytes(int L) {
          (size_t)2 * ((L + 1) & ~1) * sizeof(double);
 }
 
-template <int NB>
+template <int NB, int MODE>
 cudaError_t launch_stile(const RunArgs& a, int sm_count, cudaStream_t stream) {
   using C = STileCfg<NB>;
   const size_t bytes = stile_smem_bytes<NB>(a.io.L);
@@ -624,19 +648,19 @@ cudaError_t launch_stile(const RunArgs& a, int sm_count, cudaStream_t stream) {
   size_t& configured = configured_dev[dev];
   int& grid_cap = grid_cap_dev[dev];
   if (bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(ekf_batch_stile_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(ekf_batch_stile_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ekf_batch_stile_kernel<NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    e = cudaFuncSetAttribute(ekf_batch_stile_kernel<NB, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_batch_stile_kernel<NB>, C::THREADS, bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_batch_stile_kernel<NB, MODE>, C::THREADS, bytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     grid_cap = per_sm * sm_count;
     configured = bytes;
   }
   const int grid = a.st.F < grid_cap ? a.st.F : grid_cap;
-  ekf_batch_stile_kernel<NB><<<grid, C::THREADS, bytes, stream>>>(a);
+  ekf_batch_stile_kernel<NB, MODE><<<grid, C::THREADS, bytes, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -657,11 +681,27 @@ int ekf_stile_max_landmarks() { return STileCfg<16>::MAX_LM; }
 // CTAs that run at once per SM for a given capacity (the filter chunking of the pipelined path uses it)
 int ekf_stile_ctas_per_sm(int cap_lm) { return cap_lm <= STileCfg<13>::MAX_LM ? 4 : (cap_lm <= STileCfg<14>::MAX_LM ? 3 : 2); }
 
-cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream) {
+// tile_cap: the landmark count the tiles are sized for (0 = the handle's capacity). A smaller value
+// runs the faster small-tile instance; with io.resume set, filters that outgrow it are parked for a
+// continuation launch with tile_cap = 0.
+cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream,
+                          int tile_cap) {
   RunArgs a{st, io, k};
-  if (st.cap_lm <= STileCfg<13>::MAX_LM) return launch_stile<13>(a, sm_count, stream);
-  if (st.cap_lm <= STileCfg<14>::MAX_LM) return launch_stile<14>(a, sm_count, stream);
-  if (st.cap_lm <= STileCfg<15>::MAX_LM) return launch_stile<15>(a, sm_count, stream);
-  if (st.cap_lm <= STileCfg<16>::MAX_LM) return launch_stile<16>(a, sm_count, stream);
+  const int cap = tile_cap > 0 ? tile_cap : st.cap_lm;
+  if (io.resume && !io.continuation) {                  // primary launch of the growth path: the fast instance, parking
+    if (cap <= STileCfg<13>::MAX_LM) return launch_stile<13, 1>(a, sm_count, stream);
+    return cudaErrorInvalidValue;
+  }
+  if (io.resume) {                                       // continuation: tiles for the handle's capacity
+    if (cap <= STileCfg<14>::MAX_LM) return launch_stile<14, 2>(a, sm_count, stream);
+    if (cap <= STileCfg<15>::MAX_LM) return launch_stile<15, 2>(a, sm_count, stream);
+    if (cap <= STileCfg<16>::MAX_LM) return launch_stile<16, 2>(a, sm_count, stream);
+    return cudaErrorInvalidValue;
+  }
+  if (cap <= STileCfg<13>::MAX_LM) return launch_stile<13, 0>(a, sm_count, stream);
+  if (cap <= STileCfg<14>::MAX_LM) return launch_stile<14, 0>(a, sm_count, stream);
+  if (cap <= STileCfg<15>::MAX_LM) return launch_stile<15, 0>(a, sm_count, stream);
+  if (cap <= STileCfg<16>::MAX_LM) return launch_stile<16, 0>(a, sm_count, stream);
   return cudaErrorInvalidValue;
 }
+int ekf_stile_fast_landmarks() { return STileCfg<13>::MAX_LM; }

@@ -98,6 +98,8 @@ def core_lib():
         L.ekf_max_landmarks.argtypes = [H]
         L.ekf_regime.argtypes = [H]
         L.ekf_set_batch_kernel.argtypes = [H, C.c_int]
+        if hasattr(L, "ekf_capacity_flags"):        # absent from older profiling builds (EKF_B200_LIB)
+            L.ekf_capacity_flags.argtypes = [H, C.POINTER(C.c_int), C.c_int]
         L.ekf_set_state.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, C.c_int]
         L.ekf_get_state.argtypes = [H, C.c_int, C.POINTER(C.c_int), c_dp, c_dp, C.c_int]
         L.ekf_get_pose.argtypes = [H, c_dp, c_ip]
@@ -283,6 +285,12 @@ class FilterBatch:
         if not (allow_capacity and rc == ERR_CAPACITY):
             self._chk(rc)
         return rc
+
+    def capacity_flags(self, clear=False):
+        """Filters that dropped a New association at capacity since the flags were last cleared."""
+        n = C.c_int()
+        self._chk(self.L.ekf_capacity_flags(self.h, C.byref(n), 1 if clear else 0))
+        return n.value
 
     def set_state(self, filt, x, P, symmetric=False):
         """x (n), P (n x n, numpy row-major). symmetric=True skips the transpose copy to column-major

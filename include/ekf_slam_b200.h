@@ -155,6 +155,9 @@ int ekf_download_outputs(ekf_handle h, const ekf_run_outputs* out);      /* sync
 
 /* ---- plumbing -------------------------------------------------------------------------------- */
 int ekf_sync(ekf_handle h);                         /* waits; returns sticky EKF_ERR_CAPACITY etc. */
+/* Waits, then counts the filters whose sticky capacity flag is set (a New association was dropped since
+ * the last ekf_reset / ekf_set_state / clear) and, if `clear`, clears the flags. */
+int ekf_capacity_flags(ekf_handle h, int* n_flagged, int clear);
 const char* ekf_last_error(ekf_handle h);           /* h may be NULL: last create() failure        */
 void* ekf_host_alloc(size_t bytes);                 /* pinned host memory (cudaMallocHost)         */
 void ekf_host_free(void* p);

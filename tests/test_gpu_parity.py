@@ -367,3 +367,36 @@ def test_randomised_configuration_sweep(ekf, oracle, kernel):
             assert_state_close(x, P, xr, Pr, what + " filter %d" % f)
         fb.close()
     assert done >= 8
+
+
+@pytest.mark.parametrize("N,cap", [(53, 56), (58, 62), (51, 51)])
+def test_maps_that_outgrow_the_fast_tiles_are_finished_by_the_larger_instance(ekf, oracle, N, cap):
+    """Update.cpp:158-177 grows the map without bound. With the default kernel choice every filter starts
+    in the four-filters-per-SM instance (tiles for 50 landmarks); a filter whose map outgrows it is parked
+    and finished by the instance sized for the handle's capacity, from the measurement where it stopped.
+    Decisions, indices and state must equal the oracle's and what the large instance alone produces, in
+    the lap where the maps grow past 50 and in the later laps that start beyond 50."""
+    T, F = 500, 5
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=2, compass_every=9)
+    lap = syn.generate(F, T)
+    rec = np.ascontiguousarray(np.concatenate([lap] * 3, axis=1))
+    want = oracle.run_batch(rec, 2, cap, pose_trace=True, final_state=True)
+    assert not want["bad"] and int(want["final_nlm"].max()) > 50
+    res = []
+    for kern in (0, 3):                       # AUTO (fast tiles + continuation) and the large instance alone
+        fb = ekf.FilterBatch(F, cap, batch_kernel=kern)
+        got = fb.run(rec, 2, trace=True, pose_trace=True)
+        assert_trace_equal(got, want, "kernel %d" % kern)
+        assert np.array_equal(got["final_nlm"], want["final_nlm"])
+        assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL
+        sts = _final_states(fb, F)
+        for f, ((x, P), (xr, Pr)) in enumerate(zip(sts, _oracle_states(want, F))):
+            assert_state_close(x, P, xr, Pr, "kernel %d filter %d" % (kern, f))
+        got2 = fb.run(lap, 2, trace=True, pose_trace=True)      # a later call starts beyond the fast tiles
+        res.append((got, sts, got2, _final_states(fb, F)))
+        fb.close()
+    (a, sa, a2, sa2), (b, sb, b2, sb2) = res
+    for k in ("decision", "index", "mahal", "pose_trace", "final_pose", "final_nlm"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a2[k], b2[k]), k
+    for (xa, Pa), (xb, Pb) in zip(sa + sa2, sb + sb2):
+        assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
