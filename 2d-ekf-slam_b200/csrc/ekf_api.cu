@@ -64,6 +64,14 @@ struct ekf_handle_s {
   DevBuf<int> t_dec, t_idx;
   DevBuf<double> t_mah, t_pose;
   DevBuf<int> resume;         // [F] park codes of the two-launch growth path (launch_batch_kernel)
+  // per-call surface of the batch regime: a doPropagation call is held back until the next call shows
+  // whether it can ride in one launch with the doUpdate that follows it (slam.cpp:136,170)
+  bool prop_pending = false;
+  std::vector<double> pend;   // [3][F]: vel, rotvel, dt of the held-back call
+  DevBuf<double> pc_rec;      // [F][14] step records of the fused propagate+update launch
+  double* stage[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned staging ring for those records
+  cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int stage_i = 0;
   int rec_T = 0, rec_M = 0, rec_L = 0;
   bool have_trace = false, have_pose_trace = false;
   std::vector<uint8_t> flag_compass, flag_nz;   // host mirror [F][T] of record flags (regime B)
@@ -205,6 +213,26 @@ int download(ekf_handle h, const ekf_run_outputs* out) {
   return check_status(h);
 }
 
+// Runs a held-back doPropagation call on its own (the per-call propagate kernel).
+int flush_pending(ekf_handle h) {
+  if (!h->prop_pending) return EKF_OK;
+  h->prop_pending = false;
+  const size_t F = h->st.F;
+  EKF_CK(h, h->in.reserve(3 * F));
+  EKF_CK(h, cudaMemcpyAsync(h->in.p, h->pend.data(), 3 * F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EkfPercallIO io{};
+  io.vel = h->in.p; io.rotvel = h->in.p + F; io.dt = h->in.p + 2 * F; io.dt_stride = 1;
+  EKF_CK(h, ekf_batch_percall(h->st, io, EKF_OP_PROPAGATE, h->k, h->stream));
+  h->launches += 1;
+  EKF_CK(h, cudaStreamSynchronize(h->stream));   // h->pend / the staging buffer are reusable
+  return EKF_OK;
+}
+#define EKF_FLUSH(h)                              \
+  do {                                            \
+    const int rc__ = flush_pending(h);            \
+    if (rc__ != EKF_OK) return rc__;              \
+  } while (0)
+
 }  // namespace
 
 extern "C" {
@@ -308,7 +336,9 @@ int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, co
     if ((e = cudaMalloc(&h->wk.small, ekf_large_small_doubles() * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
     cudaMemset(h->wk.W, 0, w_count * sizeof(double2));
     {
-      // TMA-staged downdate: on unless EKF_LARGE_TMA=0 (the plain double2 sweep stays available)
+      // TMA-staged downdate: on unless EKF_LARGE_TMA=0 selects the plain double2 sweep. No silent
+      // fallback: if the tensor maps cannot be encoded the handle is not created (ekf_large_downdate_kernel()
+      // reports which sweep a handle runs).
       const char* env = getenv("EKF_LARGE_TMA");
       h->wk.use_tma = env ? atoi(env) : 1;
       if (h->wk.use_tma) {
@@ -317,7 +347,9 @@ int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, co
         bool ok = ekf_large_tma_prepare(sms, &h->wk.tma_grid) == cudaSuccess;
         for (int f = 0; ok && f < n_filters; ++f)
           ok = ekf_large_tma_encode(h->tmaps.data() + (size_t)f * mb, st.P + (size_t)f * st.slab, st.cap_n, st.ld) == cudaSuccess;
-        if (!ok) { h->wk.use_tma = 0; cudaGetLastError(); }
+        if (!ok)
+          return bail(EKF_ERR_CUDA, "the tensor maps of the TMA-staged covariance sweep could not be encoded "
+                                    "(set EKF_LARGE_TMA=0 to run the plain double2 sweep instead)");
         h->wk.tmaps = h->tmaps.data();
       }
     }
@@ -342,7 +374,11 @@ int ekf_destroy(ekf_handle h) {
   cudaFree(h->st.x); cudaFree(h->st.P); cudaFree(h->st.nlm); cudaFree(h->st.status);
   cudaFree(h->wk.W); cudaFree(h->wk.cand_val); cudaFree(h->wk.cand_idx); cudaFree(h->wk.small);
   h->in.release(); h->o_dec.release(); h->o_idx.release(); h->o_mah.release(); h->in_valid.release();
-  h->resume.release();
+  h->resume.release(); h->pc_rec.release();
+  for (int i = 0; i < 4; ++i) {
+    if (h->stage[i]) cudaFreeHost(h->stage[i]);
+    if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+  }
   h->records.release(); h->t_dec.release(); h->t_idx.release(); h->t_mah.release(); h->t_pose.release();
   if (h->ev0) {
     cudaEventDestroy(h->ev0);
@@ -367,6 +403,7 @@ int ekf_destroy(ekf_handle h) {
 int ekf_reset(ekf_handle h) {
   if (!h) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  h->prop_pending = false;                       // a held-back propagate of the old state is moot
   const EkfState& st = h->st;
   EKF_CK(h, cudaMemsetAsync(st.x, 0, (size_t)st.F * st.xs * sizeof(double), h->stream));
   EKF_CK(h, cudaMemsetAsync(st.P, 0, (size_t)st.F * st.slab * sizeof(double), h->stream));
@@ -379,6 +416,10 @@ int ekf_reset(ekf_handle h) {
 int ekf_n_filters(ekf_handle h) { return h ? h->st.F : 0; }
 int ekf_max_landmarks(ekf_handle h) { return h ? h->st.cap_lm : 0; }
 int ekf_regime(ekf_handle h) { return h ? h->regime : 0; }
+int ekf_large_downdate_kernel(ekf_handle h) {
+  if (!h || h->regime != EKF_REGIME_LARGE) return -1;
+  return h->wk.use_tma ? 1 : 0;
+}
 int ekf_set_batch_kernel(ekf_handle h, int batch_kernel) {
   if (!h || batch_kernel < EKF_BATCH_KERNEL_AUTO || batch_kernel > EKF_BATCH_KERNEL_DTILE) return EKF_ERR_BAD_ARG;
   h->cfg.batch_kernel = batch_kernel;
@@ -398,6 +439,7 @@ int ekf_set_state(ekf_handle h, int filter, int n_landmarks, const double* x, co
         return fail(h, EKF_ERR_BAD_ARG, "ekf_set_state: P must be bit-symmetric (the reference symmetrises after every operation)");
     }
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   EKF_CK(h, cudaMemcpyAsync(st.x + (size_t)filter * st.xs, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   EKF_CK(h, cudaMemcpy2DAsync(st.P + (size_t)filter * st.slab, (size_t)st.ld * sizeof(double), P, (size_t)ld * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
@@ -413,6 +455,7 @@ int ekf_get_state(ekf_handle h, int filter, int* n_landmarks, double* x, double*
   const EkfState& st = h->st;
   if (filter < 0 || filter >= st.F) return fail(h, EKF_ERR_BAD_ARG, "ekf_get_state: bad filter");
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   int nl = 0;
   EKF_CK(h, cudaMemcpyAsync(&nl, st.nlm + filter, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EKF_CK(h, cudaStreamSynchronize(h->stream));
@@ -435,6 +478,7 @@ int ekf_get_cov_block(ekf_handle h, int filter, int r0, int c0, int nr, int nc, 
       ld_out < nr)
     return fail(h, EKF_ERR_BAD_ARG, "ekf_get_cov_block: bad block");
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   EKF_CK(h, cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(double),
                               st.P + (size_t)filter * st.slab + r0 + (size_t)c0 * st.ld, (size_t)st.ld * sizeof(double),
                               (size_t)nr * sizeof(double), nc, cudaMemcpyDeviceToHost, h->stream));
@@ -446,6 +490,7 @@ int ekf_get_pose(ekf_handle h, double* xyphi, int32_t* n_landmarks) {
   if (!h) return EKF_ERR_BAD_ARG;
   const EkfState& st = h->st;
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   if (xyphi)
     EKF_CK(h, cudaMemcpy2DAsync(xyphi, 3 * sizeof(double), st.x, st.xs * sizeof(double), 3 * sizeof(double), st.F,
                                 cudaMemcpyDeviceToHost, h->stream));
@@ -458,6 +503,18 @@ int ekf_propagate(ekf_handle h, const double* vel_mm_s, const double* rotvel_deg
   if (!h || !vel_mm_s || !rotvel_deg_s || !dt) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   const size_t F = h->st.F;
+  if (h->regime == EKF_REGIME_BATCH) {
+    // Held back: if the next call is doUpdate with one measurement (slam.cpp:136 -> :170) both ride in ONE
+    // launch of the fused kernel (covariance on chip for the pair, read and written once); any other call
+    // runs this propagate on its own first (flush_pending).
+    EKF_FLUSH(h);
+    h->pend.resize(3 * F);
+    memcpy(h->pend.data(), vel_mm_s, F * sizeof(double));
+    memcpy(h->pend.data() + F, rotvel_deg_s, F * sizeof(double));
+    for (size_t f = 0; f < F; ++f) h->pend[2 * F + f] = dt[dt_stride ? f : 0];
+    h->prop_pending = true;
+    return EKF_OK;
+  }
   EKF_CK(h, h->in.reserve(3 * F));
   EKF_CK(h, cudaMemcpyAsync(h->in.p, vel_mm_s, F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   EKF_CK(h, cudaMemcpyAsync(h->in.p + F, rotvel_deg_s, F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -483,6 +540,53 @@ int ekf_update(ekf_handle h, int n_z, const double* z, const double* R, int32_t*
   if (n_z == 0) return EKF_OK;
   cudaSetDevice(h->device);
   const size_t F = h->st.F, FZ = F * n_z;
+  if (h->prop_pending && n_z == 1 && h->regime == EKF_REGIME_BATCH && pick_batch_kernel(h) > 0) {
+    // doPropagation + doUpdate of one loop iteration in one fused launch (T = 1 step records)
+    h->prop_pending = false;
+    const int L = EKF_RECORD_LEN(1);
+    const int si = h->stage_i;
+    h->stage_i = (si + 1) & 3;
+    if (!h->stage[si]) {
+      EKF_CK(h, cudaMallocHost(&h->stage[si], F * L * sizeof(double)));
+      EKF_CK(h, cudaEventCreateWithFlags(&h->stage_ev[si], cudaEventDisableTiming));
+    } else {
+      EKF_CK(h, cudaEventSynchronize(h->stage_ev[si]));   // the copy that last read this staging buffer is done
+    }
+    double* rec = h->stage[si];
+    for (size_t f = 0; f < F; ++f) {
+      double* r = rec + f * L;
+      r[0] = h->pend[f]; r[1] = h->pend[F + f]; r[2] = h->pend[2 * F + f];
+      r[3] = 0.0; r[4] = 0.0; r[5] = 1.0; r[6] = 0.0; r[7] = 0.0;
+      r[8] = z[2 * f]; r[9] = z[2 * f + 1];
+      for (int c = 0; c < 4; ++c) r[10 + c] = R[4 * f + c];
+    }
+    EKF_CK(h, h->pc_rec.reserve(F * L));
+    EKF_CK(h, cudaMemcpyAsync(h->pc_rec.p, rec, F * L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    EKF_CK(h, cudaEventRecord(h->stage_ev[si], h->stream));
+    EkfRunIO io{};
+    io.records = h->pc_rec.p; io.T = 1; io.M = 1; io.L = L;
+    const bool want = decision || lm_index || mahal;
+    if (want) {
+      EKF_CK(h, h->o_dec.reserve(F));
+      EKF_CK(h, h->o_idx.reserve(F));
+      EKF_CK(h, h->o_mah.reserve(F));
+      io.decision = h->o_dec.p; io.index = h->o_idx.p; io.mahal = h->o_mah.p;
+    }
+    kernel_event_begin(h);
+    EKF_CK(h, launch_batch_kernel(h, pick_batch_kernel(h), h->st, io));
+    kernel_event_end(h);
+    h->launches += 1;
+    if (!want) return EKF_OK;                        // fully asynchronous: no host round trip
+    if (decision) EKF_CK(h, cudaMemcpyAsync(decision, h->o_dec.p, F * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (lm_index) EKF_CK(h, cudaMemcpyAsync(lm_index, h->o_idx.p, F * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (mahal) EKF_CK(h, cudaMemcpyAsync(mahal, h->o_mah.p, F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EKF_CK(h, cudaStreamSynchronize(h->stream));
+    if (decision)
+      for (size_t q = 0; q < F; ++q)
+        if (decision[q] == EKF_DECISION_DROPPED) return fail(h, EKF_ERR_CAPACITY, "landmark capacity exceeded, a New association was dropped");
+    return EKF_OK;
+  }
+  EKF_FLUSH(h);
   std::vector<double> zr(FZ * 6);
   for (size_t q = 0; q < FZ; ++q) {
     zr[6 * q + 0] = z[2 * q + 0];
@@ -519,6 +623,7 @@ int ekf_update(ekf_handle h, int n_z, const double* z, const double* R, int32_t*
 int ekf_update_compass(ekf_handle h, const double* z, const double* R, const uint8_t* valid) {
   if (!h || !z || !R) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   const size_t F = h->st.F;
   EKF_CK(h, h->in.reserve(2 * F));
   EKF_CK(h, cudaMemcpyAsync(h->in.p, z, F * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -570,6 +675,7 @@ int ekf_upload_records(ekf_handle h, int n_steps, int max_meas, const double* re
 int ekf_run_resident(ekf_handle h, int want_trace, int want_pose_trace) {
   if (!h) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   return launch_run(h, want_trace != 0, want_pose_trace != 0);
 }
 
@@ -651,6 +757,10 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
 }
 
 int ekf_run(ekf_handle h, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out) {
+  if (h) {
+    cudaSetDevice(h->device);
+    EKF_FLUSH(h);
+  }
   if (h && records && h->regime == EKF_REGIME_BATCH && n_steps >= 1 && max_meas >= 0 && max_meas <= EKF_MAX_MEAS) {
     cudaSetDevice(h->device);
     return run_pipelined(h, n_steps, max_meas, records, out);
@@ -667,6 +777,7 @@ int ekf_run(ekf_handle h, int n_steps, int max_meas, const double* records, cons
 int ekf_sync(ekf_handle h) {
   if (!h) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   EKF_CK(h, cudaStreamSynchronize(h->stream));
   return check_status(h);
 }
@@ -674,6 +785,7 @@ int ekf_sync(ekf_handle h) {
 int ekf_capacity_flags(ekf_handle h, int* n_flagged, int clear) {
   if (!h || !n_flagged) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   std::vector<int> s(h->st.F);
   EKF_CK(h, cudaMemcpyAsync(s.data(), h->st.status, sizeof(int) * h->st.F, cudaMemcpyDeviceToHost, h->stream));
   EKF_CK(h, cudaStreamSynchronize(h->stream));
@@ -704,6 +816,7 @@ int ekf_timer_start(ekf_handle h) {
 int ekf_timer_stop(ekf_handle h, float* ms) {
   if (!h || !ms) return EKF_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  EKF_FLUSH(h);
   EKF_CK(h, cudaEventRecord(h->ev1, h->stream));
   EKF_CK(h, cudaEventSynchronize(h->ev1));
   EKF_CK(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));

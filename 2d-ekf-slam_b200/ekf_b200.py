@@ -98,6 +98,8 @@ def core_lib():
         L.ekf_max_landmarks.argtypes = [H]
         L.ekf_regime.argtypes = [H]
         L.ekf_set_batch_kernel.argtypes = [H, C.c_int]
+        if hasattr(L, "ekf_large_downdate_kernel"):
+            L.ekf_large_downdate_kernel.argtypes = [H]
         if hasattr(L, "ekf_capacity_flags"):        # absent from older profiling builds (EKF_B200_LIB)
             L.ekf_capacity_flags.argtypes = [H, C.POINTER(C.c_int), C.c_int]
         L.ekf_set_state.argtypes = [H, C.c_int, C.c_int, c_dp, c_dp, C.c_int]
@@ -285,6 +287,11 @@ class FilterBatch:
         if not (allow_capacity and rc == ERR_CAPACITY):
             self._chk(rc)
         return rc
+
+    def large_downdate_kernel(self):
+        """'large_downdate_tma' / 'large_downdate' (the plain double2 sweep) / None for the batch regime."""
+        v = self.L.ekf_large_downdate_kernel(self.h)
+        return {1: "large_downdate_tma", 0: "large_downdate"}.get(v)
 
     def capacity_flags(self, clear=False):
         """Filters that dropped a New association at capacity since the flags were last cleared."""

@@ -236,7 +236,36 @@ def profile_facts():
         return {}
 
 
-def large_map_leg(ekf, n_lm, steps, hbm_peak, device):
+def verify_large_map(fb, rec, x0, P0, k):
+    """The first k update steps of the large-map leg against the CPU oracle (checker only): decisions and
+    indices exact, state and covariance (diagonal + 64 sampled columns) within 1e-9 norm-wise."""
+    from oracle_lib import Oracle
+    from parity import TOL
+    n = len(x0)
+    of = Oracle().new_filter((n - 3) // 2).set_state(x0, P0)
+    got = fb.run(np.ascontiguousarray(rec[:, :k]), 1, trace=True)
+    n_old = 0
+    for t in range(k):
+        r = rec[0, t]
+        of.propagate(r[0], r[1], r[2])
+        n_before = of.n
+        tr = of.update(r[8:10], r[10:14])
+        assert got["decision"][0, t, 0] == tr.decision, "large-map decision differs from the oracle at step %d" % t
+        assert got["index"][0, t, 0] == (n_before if tr.decision == 0 else tr.opt_i), "large-map index differs at step %d" % t
+        n_old += tr.decision == 1
+    x, P = fb.get_state(0)
+    xr, Pr = of.get_state()
+    cols = np.unique(np.concatenate([np.random.default_rng(1).integers(0, n, 64), [0, 1, 2, n - 2, n - 1]]))
+    scale = float(np.abs(np.diagonal(Pr)).max())
+    err = max(float(np.abs(P[:, cols] - Pr[:, cols]).max()), float(np.abs(np.diagonal(P) - np.diagonal(Pr)).max()))
+    ex = float(np.abs(x - xr).max() / np.abs(xr).max())
+    assert err <= TOL * scale and ex <= TOL, "large-map state differs from the oracle: P %g of %g, x %g" % (err, scale, ex)
+    return {"steps": k, "old_updates": int(n_old), "decisions_and_indices": "exact",
+            "cov_max_abs_err_over_scale": err / scale, "state_rel_err": ex,
+            "compared": "diagonal + %d sampled columns of P, full x" % len(cols)}
+
+
+def large_map_leg(ekf, n_lm, steps, hbm_peak, device, verify_steps=0):
     """BASELINE configs[3]/[4]: one large map, covariance in HBM, Old-updates from an injected state."""
     from parity import injected_state
     # a (nearly) stationary robot: the same few visible landmarks are re-observed, every update is
@@ -246,6 +275,11 @@ def large_map_leg(ekf, n_lm, steps, hbm_peak, device):
     x0, P0 = injected_state(syn.world(), seed=n_lm)
     fb = ekf.FilterBatch(1, n_lm + 2, device=device)
     fb.set_state(0, x0, P0, symmetric=True)
+    verified = None
+    if verify_steps > 0:                       # parity at size, before anything is timed
+        verified = verify_large_map(fb, rec, x0, P0, verify_steps)
+        fb.set_state(0, x0, P0, symmetric=True)
+    sweep = fb.large_downdate_kernel()
     fb.upload_records(rec, 1)
     fb.run_resident(trace=True)            # warm-up pass
     fb.sync()
@@ -266,9 +300,10 @@ def large_map_leg(ekf, n_lm, steps, hbm_peak, device):
                        (n_lm, 3 + 2 * n_lm, 8.0 * (3 + 2 * n_lm) ** 2 / 1e9, steps),
            "old_updates": n_old, "steps": steps, "ms_per_step": ms / steps,
            "update_steps_per_s": steps / (ms * 1e-3), "gpu_launches": int(l1 - l0),
-           "roofline": {"bound": "hbm", "kernel": "large_downdate<2>", "achieved": alg / (kms * 1e-3) / 1e9 if kn else None,
+           "verified_against_oracle": verified,
+           "roofline": {"bound": "hbm", "kernel": sweep + "<2,0>", "achieved": alg / (kms * 1e-3) / 1e9 if kn else None,
                         "peak": hbm_peak, "unit": "GB/s", "frac": (alg / (kms * 1e-3) / 1e9) / hbm_peak if kn else None,
-                        "traffic": profile_facts().get("large_traffic_bytes_per_launch", {}).get(str(n_lm)),
+                        "traffic": profile_facts().get("large_traffic_bytes_per_launch", {}).get(sweep, {}).get(str(n_lm)),
                         "algorithmic_bytes_per_launch": alg, "avg_kernel_ms": kms,
                         "launches_timed": kn},
            "step_gbs": alg * n_old / (ms * 1e-3) / 1e9}
@@ -402,7 +437,9 @@ def main():
     ap.add_argument("--weak-filters-per-gpu", type=int, default=4096,
                     help="filters per GPU of the weak-scaling side run reported under 'weak' (0 = skip; BASELINE configs[1])")
     ap.add_argument("--large-map", default="2000,10000", help="comma list of landmark counts for the regime-B leg ('' = skip)")
-    ap.add_argument("--sharded-map", default="", help="landmark count for the multi-GPU sharded single-map leg ('' = skip)")
+    ap.add_argument("--sharded-map", default="auto",
+                    help="landmark count for the multi-GPU sharded single-map leg; 'auto' = 10000 over the job's GPUs "
+                         "when --gpus > 1 (run by rank 0 after the batch measurement), skipped on one GPU; '' = skip")
     ap.add_argument("--shard-devices", default="", help="comma list of device ordinals for --sharded-map (default: all visible)")
     ap.add_argument("--hough", type=int, default=4096, help="scans in the Hough front-end leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -531,7 +568,7 @@ def main():
     roofline = {"bound": "fp64", "kernel": "ekf_batch_stile_kernel<13> (+ a continuation launch of <14> for maps beyond 50 landmarks)",
                 "achieved": achieved / 1e12 if achieved else None, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
-                "traffic": prof.get("batch_traffic_bytes_per_launch"),
+                "traffic": (prof.get("batch_traffic_bytes_per_filter_lap") or 0) * F or None,
                 "algorithmic_flops_per_launch": flops_per_launch, "avg_kernel_ms": kms, "launches_timed": kn,
                 "peak_source": "measured live: DFMA-chain microbenchmark (ekf_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
@@ -559,8 +596,8 @@ def main():
         legs = []
         for tok in args.large_map.split(","):
             n_lm = int(tok)
-            steps = 400 if n_lm <= 2000 else 30
-            legs.append(large_map_leg(ekf, n_lm, steps, hbm_peak, local))
+            steps = 10000 if n_lm <= 2000 else 30      # BASELINE configs[3]: 10,000 update steps
+            legs.append(large_map_leg(ekf, n_lm, steps, hbm_peak, local, verify_steps=4 if n_lm <= 2000 else 2))
         line["large_map"] = legs
         line["roofline_hbm"] = dict(legs[-1]["roofline"], peak_source=hbm_src)
     if world == 1 and args.hough > 0:
@@ -568,10 +605,22 @@ def main():
             line["hough"] = hough_leg(ekf, args.hough, hbm_peak, local, with_cpu=not args.no_cpu_baseline)
         except Exception as e:                 # noqa: BLE001
             line["hough"] = {"error": "%s: %s" % (type(e).__name__, e)}
-    if world == 1 and args.sharded_map:
-        devs = [int(t) for t in args.shard_devices.split(",") if t.strip()] or list(range(ekf.device_count()))
-        steps = 400 if int(args.sharded_map) <= 4000 else 60
-        line["sharded_map"] = [sharded_map_leg(ekf, int(args.sharded_map), steps, hbm_peak, devs)]
+    sh = args.sharded_map
+    if sh == "auto":
+        sh = "10000" if world > 1 else ""
+    if sh:
+        # one process (rank 0) drives every GPU of the job: the covariance of ONE map column-sharded over
+        # them, gain rows exchanged by peer stores over NVLink; the other ranks are done
+        devs = [int(t) for t in args.shard_devices.split(",") if t.strip()] or list(range(min(max(world, 1), ekf.device_count()) if world > 1 else ekf.device_count()))
+        steps = 400 if int(sh) <= 4000 else 60
+        try:
+            legs = [sharded_map_leg(ekf, int(sh), steps, hbm_peak, devs)]
+            if len(devs) > 1:                  # the same map on one GPU, for the speed-up
+                legs.append(sharded_map_leg(ekf, int(sh), steps, hbm_peak, devs[:1]))
+                legs[0]["speedup_vs_one_gpu"] = legs[1]["ms_per_step"] / legs[0]["ms_per_step"]
+            line["sharded_map"] = legs
+        except Exception as e:                 # noqa: BLE001  an auxiliary leg must never cost the headline line
+            line["sharded_map"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(rec)
         line["cpu_baseline"] = cb

@@ -102,6 +102,10 @@ int ekf_n_filters(ekf_handle h);
 int ekf_max_landmarks(ekf_handle h);
 int ekf_regime(ekf_handle h);                      /* the regime actually selected */
 int ekf_set_batch_kernel(ekf_handle h, int batch_kernel);   /* EKF_BATCH_KERNEL_*, for later fused runs */
+/* Which O(n^2) covariance sweep a large-regime handle runs: 1 = large_downdate_tma (TMA-staged tiles,
+ * the default), 0 = large_downdate (plain double2 sweep, EKF_LARGE_TMA=0 at creation), -1 = not a
+ * large-regime handle. */
+int ekf_large_downdate_kernel(ekf_handle h);
 
 /* ---- state access (also checkpoint / state injection) -------------------------------------- */
 /* The reference keeps state/covariance private (kalmanfilter.h:37-38); these are the harness
@@ -115,9 +119,14 @@ int ekf_get_cov_block(ekf_handle h, int filter, int r0, int c0, int nr, int nc, 
  * xyphi[n_filters][3], n_landmarks[n_filters] (either may be NULL). Synchronises. */
 int ekf_get_pose(ekf_handle h, double* xyphi, int32_t* n_landmarks);
 
-/* ---- per-call surface (one launch per reference call, P goes through HBM) -------------------- */
+/* ---- per-call surface (P goes through HBM once per loop iteration) ----------------------------- */
 /* KalmanFilter::doPropagation (kalmanfilter.cpp:15-62 -> Propagate.cpp:15-75), minus the two
- * ofstream side effects. Arrays of n_filters; dt may be a single value when dt_stride == 0. */
+ * ofstream side effects. Arrays of n_filters; dt may be a single value when dt_stride == 0.
+ * Batch regime: the inputs are copied and the call is HELD BACK - if the next call on the handle is
+ * ekf_update with n_z = 1 (the slam.cpp:136 -> :170 sequence) both run in ONE launch of the fused
+ * kernel (covariance read and written once for the pair, no host round trip unless outputs are
+ * requested); any other call first runs the propagation on its own. Results do not depend on which
+ * way a call was executed. */
 int ekf_propagate(ekf_handle h, const double* vel_mm_s, const double* rotvel_deg_s, const double* dt,
                   int dt_stride);
 /* KalmanFilter::doUpdate (kalmanfilter.cpp:64-90 -> Update.cpp:22-204) with n_z measurements per

@@ -400,3 +400,46 @@ def test_maps_that_outgrow_the_fast_tiles_are_finished_by_the_larger_instance(ek
         assert np.array_equal(a[k], b[k]) and np.array_equal(a2[k], b2[k]), k
     for (xa, Pa), (xb, Pb) in zip(sa + sa2, sb + sb2):
         assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
+
+
+@pytest.mark.parametrize("tma", [1, 0], ids=["tma", "plain"])
+def test_large_map_at_bench_size(ekf, oracle, tma, monkeypatch):
+    """BASELINE config 5 at its full size: 10,000 landmarks (n = 20,003, P = 3.2 GB, byte offsets beyond
+    32 bits, boundary tiles of the TMA sweep), three updates from an injected state through the fused
+    large-regime path, against the C oracle: decisions / indices exact, state and the FULL covariance
+    within 1e-9 (norm-wise), both sweeps (TMA-staged and plain)."""
+    N, steps = 10000, 3
+    monkeypatch.setenv("EKF_LARGE_TMA", str(tma))
+    syn = ekf.Synth(N, steps_per_lap=10 ** 7, max_meas=1)
+    rec = syn.generate(1, steps)
+    x0, P0 = injected_state(syn.world(), seed=N)
+    fb = ekf.FilterBatch(1, N + 2)
+    assert fb.regime == 2 and fb.large_downdate_kernel() == ("large_downdate_tma" if tma else "large_downdate")
+    fb.set_state(0, x0, P0, symmetric=True)
+    got = fb.run(rec, 1, trace=True, pose_trace=True)
+    of = oracle.new_filter(N + 2).set_state(x0, P0)
+    del P0
+    n_old = 0
+    for t in range(steps):
+        r = rec[0, t]
+        of.propagate(r[0], r[1], r[2])
+        n_before = of.n
+        tr = of.update(r[8:10], r[10:14])
+        assert got["decision"][0, t, 0] == tr.decision
+        assert got["index"][0, t, 0] == (n_before if tr.decision == 0 else tr.opt_i)
+        assert abs(got["mahal"][0, t, 0] - tr.mahal) <= TOL * max(1.0, abs(tr.mahal))
+        n_old += tr.decision == 1
+    assert n_old >= 3, "three Old updates over the full 3.2 GB covariance"
+    x, P = fb.get_state(0)
+    fb.close()
+    xr, Pr = of.get_state()
+    assert rel_state(x, xr) <= TOL
+    # norm-wise over the full matrix, in column blocks (no 3.2 GB temporaries)
+    worst, scale = 0.0, 0.0
+    for j0 in range(0, P.shape[1], 1024):
+        a, b = P[:, j0:j0 + 1024], Pr[:, j0:j0 + 1024]
+        worst = max(worst, float(np.abs(a - b).max()))
+        scale = max(scale, float(np.abs(b).max()))
+    assert worst <= TOL * scale, "covariance differs: %g of %g" % (worst, scale)
+    idx = np.random.default_rng(0).integers(0, P.shape[0], 4096)
+    assert np.array_equal(P[idx[:2048], idx[2048:]], P[idx[2048:], idx[:2048]]), "covariance must stay bit-symmetric"
