@@ -250,6 +250,14 @@ void ekf_default_config(ekf_config* cfg) {
   cfg->batch_kernel = EKF_BATCH_KERNEL_AUTO;
 }
 
+int ekf_device_count(int* n_devices) {
+  if (!n_devices) return EKF_ERR_BAD_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return EKF_ERR_NO_DEVICE;
+  *n_devices = n;
+  return EKF_OK;
+}
+
 int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin, size_t* total_mem) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return EKF_ERR_NO_DEVICE;
@@ -410,6 +418,40 @@ int ekf_reset(ekf_handle h) {
   EKF_CK(h, cudaMemsetAsync(st.nlm, 0, (size_t)st.F * sizeof(int), h->stream));
   EKF_CK(h, cudaMemsetAsync(st.status, 0, (size_t)st.F * sizeof(int), h->stream));
   if (h->wk.W) EKF_CK(h, cudaMemsetAsync(h->wk.W, 0, ((size_t)st.cap_n + 512) * sizeof(double2), h->stream));
+  return EKF_OK;
+}
+
+int ekf_resize(ekf_handle* hp, int new_max_landmarks) {
+  if (!hp || !*hp) return EKF_ERR_BAD_ARG;
+  ekf_handle h = *hp;
+  cudaSetDevice(h->device);
+  EKF_FLUSH(h);
+  const EkfState& so = h->st;
+  std::vector<int> nl(so.F);
+  EKF_CK(h, cudaMemcpyAsync(nl.data(), so.nlm, sizeof(int) * so.F, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CK(h, cudaStreamSynchronize(h->stream));
+  int need = 0;
+  for (int f = 0; f < so.F; ++f) need = nl[f] > need ? nl[f] : need;
+  if (new_max_landmarks < need || new_max_landmarks < 1)
+    return fail(h, EKF_ERR_BAD_ARG, "ekf_resize: new capacity " + std::to_string(new_max_landmarks) + " is below the largest map (" + std::to_string(need) + " landmarks)");
+  ekf_config cfg = h->cfg;
+  cfg.regime = EKF_REGIME_AUTO;                  // the regime follows the capacity
+  ekf_handle g = nullptr;
+  const int rc = ekf_create(&g, h->device, so.F, new_max_landmarks, &cfg);
+  if (rc != EKF_OK) return fail(h, rc, "ekf_resize: " + g_create_error);
+  const EkfState& sn = g->st;
+  for (int f = 0; f < so.F; ++f) {
+    const size_t n = 3 + 2 * (size_t)nl[f];
+    EKF_CK(h, cudaMemcpyAsync(sn.x + (size_t)f * sn.xs, so.x + (size_t)f * so.xs, n * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
+    EKF_CK(h, cudaMemcpy2DAsync(sn.P + (size_t)f * sn.slab, (size_t)sn.ld * sizeof(double), so.P + (size_t)f * so.slab,
+                                (size_t)so.ld * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToDevice, g->stream));
+  }
+  EKF_CK(h, cudaMemcpyAsync(sn.nlm, so.nlm, sizeof(int) * so.F, cudaMemcpyDeviceToDevice, g->stream));
+  EKF_CK(h, cudaMemcpyAsync(sn.status, so.status, sizeof(int) * so.F, cudaMemcpyDeviceToDevice, g->stream));
+  EKF_CK(h, cudaStreamSynchronize(g->stream));
+  g->launches = h->launches;
+  ekf_destroy(h);
+  *hp = g;
   return EKF_OK;
 }
 

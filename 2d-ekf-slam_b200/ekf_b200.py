@@ -192,6 +192,17 @@ class Synth:
         synth_lib().ekf_synth_true_pose(C.byref(self.cfg), t, _dp(p))
         return p
 
+    def scan(self, t):
+        """Synthetic LMS-200 scan at the true pose of step t -> (local x [181] mm, local y [181] mm, range [181] mm)."""
+        x = np.zeros(181)
+        y = np.zeros(181)
+        r = np.zeros(181, np.uint32)
+        L = synth_lib()
+        L.ekf_synth_scan.argtypes = [C.c_void_p, C.c_long, c_dp, c_dp, C.POINTER(C.c_uint32)]
+        n = L.ekf_synth_scan(C.byref(self.cfg), t, _dp(x), _dp(y), r.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert n == 181
+        return x, y, r
+
     def generate(self, n_filters, n_steps, f0=0, t0=0, out=None, want_ids=False, n_threads=0):
         L = self.record_len
         if out is None:

@@ -177,6 +177,45 @@ void ekf_synth_true_pose(const ekf_synth_config* cfg, long t, double* xyphi) {
   true_pose(*cfg, wd, t, xyphi);
 }
 
+int ekf_synth_scan(const ekf_synth_config* cfg, long t, double* local_x_mm, double* local_y_mm, uint32_t* range_mm) {
+  if (!config_ok(cfg) || !local_x_mm || !local_y_mm || !range_mm) return 0;
+  const World wd = make_world(*cfg);
+  double pose[3];
+  true_pose(*cfg, wd, t, pose);
+  const double half = 0.15, max_m = 8.191;
+  for (int b = 0; b < EKF_SYNTH_SCAN_BEAMS; ++b) {
+    const double ang = (b - 90) * kPi / 180.0;
+    const double dx = std::cos(pose[2] + ang), dy = std::sin(pose[2] + ang);
+    double best = max_m;
+    for (int k = 0; k < cfg->n_landmarks; ++k) {
+      // slab test of the ray against the axis-aligned square around landmark k
+      const double ox = wd.lx[k] - pose[0], oy = wd.ly[k] - pose[1];
+      if (ox * ox + oy * oy > (max_m + 1.0) * (max_m + 1.0)) continue;
+      double t0 = 0.0, t1 = best;
+      bool hit = true;
+      const double o[2] = {ox, oy}, d[2] = {dx, dy};
+      for (int a = 0; a < 2 && hit; ++a) {
+        if (std::fabs(d[a]) < 1e-12) {
+          hit = std::fabs(o[a]) <= half;
+        } else {
+          double ta = (o[a] - half) / d[a], tb = (o[a] + half) / d[a];
+          if (ta > tb) std::swap(ta, tb);
+          t0 = std::max(t0, ta);
+          t1 = std::min(t1, tb);
+          hit = t0 <= t1;
+        }
+      }
+      if (hit && t0 > 1e-9 && t0 < best) best = t0;
+    }
+    const double r_mm = std::floor(best * 1000.0 + 0.5);
+    const uint32_t r = best >= max_m ? 8191u : static_cast<uint32_t>(r_mm);
+    range_mm[b] = r;
+    local_x_mm[b] = r * std::cos(ang);
+    local_y_mm[b] = r * std::sin(ang);
+  }
+  return EKF_SYNTH_SCAN_BEAMS;
+}
+
 // slam.cpp:158-167. Evaluated in the reference's order: R_chunk = (G*R)*G^T with sequential
 // two-term inner sums seeded by the first product.
 void ekf_synth_measurement_from_feature(double fx_mm, double fy_mm, double* z, double* R) {

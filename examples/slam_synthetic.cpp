@@ -12,8 +12,9 @@
 //   stdout: "Update: <tokens><Num_Landmarks>" lines as slam.cpp:169-171 prints, then "odom X Y Phi".
 //   With log_dir the reference's log files are written there in its own text formats
 //   (odomRun.txt slam.cpp:181, featuresRun.txt slam.cpp:172-177, covRun.txt and knownfeaturesRun.txt
-//   kalmanfilter.cpp:51-61), so plot.py / RealTimePlotting.m read a synthetic run unchanged;
-//   scanRun.txt needs laser readings and is not produced.
+//   kalmanfilter.cpp:51-61, scanRun.txt slam.cpp:184-203 from synthetic LMS-200 scans of the landmark
+//   world), so plot.py / RealTimePlotting.m read a synthetic run unchanged.
+//   A fifth argument "shards=<k>" runs the filter as ONE map column-sharded over k shards (devices 0..).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -40,9 +41,10 @@ int main(int argc, char** argv) {
   ekf_synth_generate(&cfg, 0, 1, 0, n_steps, rec.data(), nullptr, 1);
 
   ArRobot robot;
-  std::ofstream odomFile, featuresFile, covFile, knownfeaturesFile;   // closed unless log_dir is given
-  if (argc > 4) {
+  std::ofstream odomFile, featuresFile, covFile, knownfeaturesFile, scanFile;   // closed unless log_dir is given
+  if (argc > 4 && std::string(argv[4]) != "-") {
     const std::string dir(argv[4]);
+    scanFile.open((dir + "/scanRun.txt").c_str());
     odomFile.open((dir + "/odomRun.txt").c_str());
     featuresFile.open((dir + "/featuresRun.txt").c_str());
     covFile.open((dir + "/covRun.txt").c_str());
@@ -51,7 +53,18 @@ int main(int argc, char** argv) {
   std::cout.precision(17);
 
   // Initialize the kalman filter (slam.cpp:127)
-  KalmanFilter* ekf = new KalmanFilter(&robot, max_landmarks, 0);
+  KalmanFilter* ekf;
+  if (argc > 5 && std::string(argv[5]).rfind("shards=", 0) == 0) {
+    const int k = std::atoi(argv[5] + 7);
+    int n_dev = 1;
+    ekf_device_count(&n_dev);
+    std::vector<int> devices;
+    for (int s = 0; s < k; ++s) devices.push_back(s % (n_dev > 0 ? n_dev : 1));
+    ekf = new KalmanFilter(&robot, max_landmarks, devices);
+  } else {
+    ekf = new KalmanFilter(&robot, max_landmarks, 0);
+  }
+  double loopTime = 0.0;
 
   // Enter SLAM loop (slam.cpp:130)
   for (int t = 0; t < n_steps; ++t) {
@@ -82,6 +95,25 @@ int main(int argc, char** argv) {
     }
     if (odomFile.is_open()) odomFile << ekf->X << " " << ekf->Y << std::endl;          // slam.cpp:181
     std::cout << "odom " << ekf->X << " " << ekf->Y << " " << ekf->Phi << std::endl;   // slam.cpp:181
+
+    // If haven't saved laser scan in over a second, save the laser scan (slam.cpp:184-203)
+    loopTime += dt;
+    if (loopTime > 1.0) {
+      if (scanFile.is_open()) {
+        double lx[EKF_SYNTH_SCAN_BEAMS], ly[EKF_SYNTH_SCAN_BEAMS];
+        uint32_t range[EKF_SYNTH_SCAN_BEAMS];
+        const int nb = ekf_synth_scan(&cfg, t + 1, lx, ly, range);   // the robot has made t+1 moves
+        for (int i = 0; i < nb; i++) {
+          if (range[i] > 7000) continue;
+          double fx = lx[i] / 1000.0;
+          double fy = ly[i] / 1000.0;
+          double newX = fx * cos(ekf->Phi) - fy * sin(ekf->Phi);
+          double newY = fx * sin(ekf->Phi) + fy * cos(ekf->Phi);
+          scanFile << newX + ekf->X << " " << newY + ekf->Y << std::endl;
+        }
+      }
+      loopTime = 0.0;
+    }
   }
   delete ekf;
   return 0;

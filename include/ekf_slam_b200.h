@@ -98,6 +98,13 @@ void ekf_default_config(ekf_config* cfg);
 int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, const ekf_config* cfg);
 int ekf_destroy(ekf_handle h);
 int ekf_reset(ekf_handle h);                       /* back to kalmanfilter.cpp:7-11 */
+/* The reference grows its state without bound (Update.cpp:158-177, kalmanfilter.cpp:76-84: state and
+ * covariance are re-allocated after every update). Here capacity is fixed per handle; ekf_resize
+ * replaces *h by a handle of capacity new_max_landmarks (>= every filter's current landmark count) on
+ * the same device with the same configuration and the same state (device-to-device copy), and destroys
+ * the old one. The regime is chosen again for the new capacity. The drop-in class calls it before an
+ * update that could overflow, which restores the reference's behaviour up to device memory. */
+int ekf_resize(ekf_handle* h, int new_max_landmarks);
 int ekf_n_filters(ekf_handle h);
 int ekf_max_landmarks(ekf_handle h);
 int ekf_regime(ekf_handle h);                      /* the regime actually selected */
@@ -176,6 +183,7 @@ long long ekf_kernel_launches(ekf_handle h);        /* kernels this handle has l
 /* Average device time of the dominant kernel since the last call (ms) and how many launches that
  * covers; measured with CUDA events around each launch on the handle's stream. */
 int ekf_kernel_time(ekf_handle h, float* avg_ms, int* n_launches);
+int ekf_device_count(int* n_devices);                /* CUDA devices visible to the process */
 int ekf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin,
                     size_t* total_mem);
 /* DFMA-chain microbenchmark on `device`: achieved FP64 FLOP/s (2 flop per DFMA). Used as the

@@ -59,6 +59,14 @@ void ekf_synth_true_pose(const ekf_synth_config* cfg, long t, double* xyphi);
  * Returns 0, or non-zero on bad arguments. n_threads <= 0 = all hardware threads. */
 int ekf_synth_generate(const ekf_synth_config* cfg, long f0, int nf, long t0, int nt, double* out, int32_t* lm_ids,
                        int n_threads);
+/* What the LMS-200 would return at the TRUE pose of global step t (slam.cpp:90: 181 beams over the
+ * front 180 degrees in 1-degree steps, beam 0 at -90 degrees): every landmark is a square pillar of
+ * side 0.3 m centred on it, a beam returns the distance to the nearest pillar face, or 8191 mm when
+ * nothing is within 8.191 m. local_x_mm / local_y_mm are ArSensorReading::getLocalX/Y (x forward, y
+ * left), range_mm is getRange (integer millimetres). Arrays of EKF_SYNTH_SCAN_BEAMS. Deterministic.
+ * Used for the scanRun.txt log (slam.cpp:184-203). Returns the number of beams written. */
+#define EKF_SYNTH_SCAN_BEAMS 181
+int ekf_synth_scan(const ekf_synth_config* cfg, long t, double* local_x_mm, double* local_y_mm, uint32_t* range_mm);
 /* slam.cpp:158-167: corner feature (mm, robot frame) -> z (m), R (column-major 2x2). */
 void ekf_synth_measurement_from_feature(double fx_mm, double fy_mm, double* z, double* R);
 

@@ -277,9 +277,20 @@ void ref_measurement_from_feature(double fx_mm, double fy_mm, double* z_out, dou
 // kalmanfilter.cpp:51-61, with OPEN streams this time) and with slam.cpp's expressions restated here
 // for the two files main() writes (featuresRun: slam.cpp:172-177, odomRun: slam.cpp:181). scanRun
 // needs laser readings and is not produced. Returns 0, or -1 if a file cannot be opened.
+// scan_x / scan_y / scan_r (optional): [n_steps][n_beams] laser readings (getLocalX/Y in mm, getRange) of
+// every step, for the scanRun.txt dump of slam.cpp:184-203.
+int ref_run_logged_scans(int n_steps, int max_meas, const double* inputs, const char* dir, const double* scan_x,
+                         const double* scan_y, const uint32_t* scan_r, int n_beams);
 int ref_run_logged(int n_steps, int max_meas, const double* inputs, const char* dir) {
+  return ref_run_logged_scans(n_steps, max_meas, inputs, dir, nullptr, nullptr, nullptr, 0);
+}
+int ref_run_logged_scans(int n_steps, int max_meas, const double* inputs, const char* dir, const double* scan_x,
+                         const double* scan_y, const uint32_t* scan_r, int n_beams) {
   const int L = 8 + 6 * max_meas;
   const std::string d(dir);
+  std::ofstream scanFile;
+  if (scan_r) scanFile.open((d + "/scanRun.txt").c_str());
+  double loopTime = 0.0;
   std::ofstream odomFile((d + "/odomRun.txt").c_str()), featuresFile((d + "/featuresRun.txt").c_str());
   std::ofstream covFile((d + "/covRun.txt").c_str()), knownfeaturesFile((d + "/knownfeaturesRun.txt").c_str());
   if (!odomFile.is_open() || !featuresFile.is_open() || !covFile.is_open() || !knownfeaturesFile.is_open()) return -1;
@@ -309,6 +320,20 @@ int ref_run_logged(int n_steps, int max_meas, const double* inputs, const char* 
       featuresFile << newX + ekf->X << " " << newY + ekf->Y << std::endl;
     }
     odomFile << ekf->X << " " << ekf->Y << std::endl;
+    // slam.cpp:184-203: at most one laser scan per second, in the world frame of the filter's pose
+    loopTime += rec[2];
+    if (scan_r && loopTime > 1.0) {
+      for (int i = 0; i < n_beams; i++) {
+        const size_t q = static_cast<size_t>(t) * n_beams + i;
+        if (scan_r[q] > 7000) continue;
+        double fx = scan_x[q] / 1000.0;
+        double fy = scan_y[q] / 1000.0;
+        double newX = fx * cos(ekf->Phi) - fy * sin(ekf->Phi);
+        double newY = fx * sin(ekf->Phi) + fy * cos(ekf->Phi);
+        scanFile << newX + ekf->X << " " << newY + ekf->Y << std::endl;
+      }
+      loopTime = 0.0;
+    }
   }
   delete ekf->state;         // the reference has no destructor (kalmanfilter.h:21-43)
   delete ekf->covariance;

@@ -213,13 +213,24 @@ class Ref:
         self.lib.ref_measurement_from_feature(fx_mm, fy_mm, _dp(z), _dp(R))
         return z, R
 
-    def run_logged(self, records, max_meas, directory):
-        """The reference's odomRun / featuresRun / covRun / knownfeaturesRun text files for one filter."""
+    def run_logged(self, records, max_meas, directory, scans=None):
+        """The reference's odomRun / featuresRun / covRun / knownfeaturesRun text files for one filter;
+        with scans = (x [T][B], y [T][B], range [T][B]) also scanRun.txt (slam.cpp:184-203)."""
         records = np.ascontiguousarray(records, np.float64)
         T, L = records.shape
         assert L == record_len(max_meas)
-        self.lib.ref_run_logged.argtypes = [C.c_int, C.c_int, c_dp, C.c_char_p]
-        rc = self.lib.ref_run_logged(T, max_meas, _dp(records), str(directory).encode())
+        if scans is None:
+            self.lib.ref_run_logged.argtypes = [C.c_int, C.c_int, c_dp, C.c_char_p]
+            rc = self.lib.ref_run_logged(T, max_meas, _dp(records), str(directory).encode())
+        else:
+            sx = np.ascontiguousarray(scans[0], np.float64)
+            sy = np.ascontiguousarray(scans[1], np.float64)
+            sr = np.ascontiguousarray(scans[2], np.uint32)
+            assert sx.shape == sy.shape == sr.shape and sx.shape[0] == T
+            self.lib.ref_run_logged_scans.argtypes = [C.c_int, C.c_int, c_dp, C.c_char_p, c_dp, c_dp,
+                                                      C.POINTER(C.c_uint32), C.c_int]
+            rc = self.lib.ref_run_logged_scans(T, max_meas, _dp(records), str(directory).encode(), _dp(sx), _dp(sy),
+                                               sr.ctypes.data_as(C.POINTER(C.c_uint32)), sx.shape[1])
         assert rc == 0
 
     def call_update(self, x, P, z_chunk, R_chunk, gamma_max=50, gamma_min=10):

@@ -45,9 +45,10 @@ def test_slam_loop_through_the_dropin_class(ekf, oracle, tmp_path):
 
 
 def test_log_files_match_the_reference_formats(ekf, ref, tmp_path):
-    """odomRun / featuresRun / covRun / knownfeaturesRun written through the
+    """odomRun / featuresRun / covRun / knownfeaturesRun / scanRun written through the
     drop-in class are the reference's text, line for line (default ostream formatting, the
-    reference's own knownfeatures index stride), so plot.py / RealTimePlotting.m work unchanged."""
+    reference's own knownfeatures index stride, one laser scan per second of loop time as
+    slam.cpp:184-203), so plot.py / RealTimePlotting.m work unchanged."""
     exe = str(tmp_path / "slam_synthetic")
     lib = os.path.join(ROOT, "2d-ekf-slam_b200", "lib")
     subprocess.run(["/usr/bin/g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "oracle", "shim"),
@@ -60,8 +61,10 @@ def test_log_files_match_the_reference_formats(ekf, ref, tmp_path):
     theirs.mkdir()
     subprocess.run([exe, str(N), str(T), "16", str(ours)], stdout=subprocess.DEVNULL, check=True)
     syn = ekf.Synth(N, steps_per_lap=T, max_meas=2, compass_every=10)
-    ref.run_logged(syn.generate(1, T)[0], 2, theirs)
-    for name, min_lines in (("odomRun.txt", T), ("featuresRun.txt", T), ("covRun.txt", T), ("knownfeaturesRun.txt", T)):
+    scans = [np.stack(v) for v in zip(*[syn.scan(t + 1) for t in range(T)])]     # the robot has made t+1 moves
+    ref.run_logged(syn.generate(1, T)[0], 2, theirs, scans=scans)
+    for name, min_lines in (("odomRun.txt", T), ("featuresRun.txt", T), ("covRun.txt", T), ("knownfeaturesRun.txt", T),
+                            ("scanRun.txt", 200)):
         a = (ours / name).read_text().split("\n")
         b = (theirs / name).read_text().split("\n")
         assert len(a) == len(b) and len(b) > min_lines, name
@@ -100,3 +103,35 @@ def test_hough_example_through_the_c_header(tmp_path):
         if np.hypot(fx - cx, fy - cy) < 60:
             found += 1
     assert found >= 3, out
+
+
+def _build_example(tmp_path):
+    exe = str(tmp_path / "slam_synthetic")
+    lib = os.path.join(ROOT, "2d-ekf-slam_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "oracle", "shim"),
+                    "-I" + os.path.join(ROOT, "2d-ekf-slam_b200", "host"), "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "slam_synthetic.cpp"), "-L" + lib, "-lekf_slam_b200",
+                    "-lekf_synth", "-Wl,-rpath," + lib, "-o", exe], check=True)
+    return exe
+
+
+def test_dropin_class_grows_like_the_reference_and_runs_sharded(tmp_path):
+    """Update.cpp:158-177 never refuses a New association. (i) The drop-in class started with room for 4
+    landmarks in a 20-landmark world must print exactly what it prints with room for 24 (ekf_resize doubles
+    the capacity before an update that could overflow: 4 -> 8 -> 16 -> 32, crossing nothing but memory);
+    (ii) the same loop with the filter as ONE map column-sharded over three shards prints the same tokens
+    and the same odometry to 1e-9."""
+    exe = _build_example(tmp_path)
+    run = lambda *a: subprocess.run([exe] + [str(v) for v in a], stdout=subprocess.PIPE, check=True, text=True).stdout
+    big = run(20, 300, 24)
+    small = run(20, 300, 4)
+    assert "Full" not in small and small == big
+    sharded = run(20, 300, 24, "-", "shards=3")
+    la, lb = big.split("\n"), sharded.split("\n")
+    assert len(la) == len(lb)
+    for a, b in zip(la, lb):
+        if a.startswith("odom"):
+            for va, vb in zip(a.split()[1:], b.split()[1:]):
+                assert abs(float(va) - float(vb)) <= 1e-9 * max(1.0, abs(float(va)))
+        else:
+            assert a == b
