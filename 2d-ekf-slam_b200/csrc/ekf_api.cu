@@ -48,6 +48,8 @@ struct ekf_handle_s {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy engines of the pipelined end-to-end path
+  cudaStream_t s_grow = nullptr;                  // continuation launches of the growth path, beside the primary launch
+  cudaEvent_t ev_grow0 = nullptr, ev_grow1 = nullptr;
   cudaEvent_t ev_in[kMaxChunks], ev_k[kMaxChunks], ev_done = nullptr;
   EkfConst k{};
   ekf_config cfg{};
@@ -129,17 +131,32 @@ cudaError_t launch_batch_kernel(ekf_handle h, int kern, const EkfState& st, cons
     // every filter starts in the fast small-tile instance; the few whose map outgrows it are written
     // back ("parked") and finished, from the measurement where they stopped, by the instance sized for
     // the handle's capacity. Same arithmetic in both, so the result does not depend on where a filter ran.
+    // Maps that are already beyond the fast tiles when the run starts (they grew in an earlier run) are
+    // marked and run by a continuation launch on a second stream BESIDE the primary launch, so their lap
+    // (one CTA per filter for the whole lap) is not a serial tail; only a filter that outgrows the tiles
+    // during this run waits for the primary launch to finish.
     cudaError_t e = h->resume.reserve((size_t)h->st.F);
     if (e != cudaSuccess) return e;
+    if (!h->s_grow) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if ((e = cudaStreamCreateWithPriority(&h->s_grow, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+      cudaEventCreateWithFlags(&h->ev_grow0, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->ev_grow1, cudaEventDisableTiming);
+    }
     EkfRunIO io2 = io;
     io2.resume = h->resume.p + (st.nlm - h->st.nlm);
-    e = cudaMemsetAsync(io2.resume, 0, (size_t)st.F * sizeof(int), h->stream);
-    if (e != cudaSuccess) return e;
+    if ((e = ekf_stile_mark_grown(st.nlm, io2.resume, st.F, h->stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(h->ev_grow0, h->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(h->s_grow, h->ev_grow0, 0)) != cudaSuccess) return e;
+    io2.continuation = 2;
+    if ((e = ekf_stile_run(st, io2, h->k, h->sm_count, h->s_grow, 0)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(h->ev_grow1, h->s_grow)) != cudaSuccess) return e;
     io2.continuation = 0;
-    e = ekf_stile_run(st, io2, h->k, h->sm_count, h->stream, ekf_stile_fast_landmarks());
-    if (e != cudaSuccess) return e;
+    if ((e = ekf_stile_run(st, io2, h->k, h->sm_count, h->stream, ekf_stile_fast_landmarks())) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(h->stream, h->ev_grow1, 0)) != cudaSuccess) return e;
     io2.continuation = 1;
-    h->launches += 1;
+    h->launches += 3;
     return ekf_stile_run(st, io2, h->k, h->sm_count, h->stream, 0);
   }
   if (kern == 3) return ekf_stile_run(st, io, h->k, h->sm_count, h->stream);
@@ -383,6 +400,11 @@ int ekf_destroy(ekf_handle h) {
   cudaFree(h->wk.W); cudaFree(h->wk.cand_val); cudaFree(h->wk.cand_idx); cudaFree(h->wk.small);
   h->in.release(); h->o_dec.release(); h->o_idx.release(); h->o_mah.release(); h->in_valid.release();
   h->resume.release(); h->pc_rec.release();
+  if (h->s_grow) {
+    cudaStreamDestroy(h->s_grow);
+    cudaEventDestroy(h->ev_grow0);
+    cudaEventDestroy(h->ev_grow1);
+  }
   for (int i = 0; i < 4; ++i) {
     if (h->stage[i]) cudaFreeHost(h->stage[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);

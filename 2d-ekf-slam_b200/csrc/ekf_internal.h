@@ -33,7 +33,7 @@ struct EkfRunIO {
   // larger tiles visits only the parked filters and picks up there. null = no parking (New at capacity
   // is dropped and flagged).
   int* resume;             // [F] or null
-  int continuation;
+  int continuation;        // 0: primary (parks); 1: resumes the parked filters; 2: runs the filters marked -2 from the start
 };
 
 struct EkfPercallIO {
@@ -71,6 +71,7 @@ cudaError_t ekf_stile_timestamps(long long* out128);
 cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst& k, int sm_count, cudaStream_t stream,
                           int tile_cap = 0);
 int ekf_stile_fast_landmarks();   // capacity of the four-filters-per-SM instance
+cudaError_t ekf_stile_mark_grown(const int* nlm, int* resume, int F, cudaStream_t stream);
 
 // Deferred-downdate variant (ekf_dtile.cu): eager strip / diagonal blocks, P_LL tiles swept once per
 // three updates, exact gating with two lanes per landmark; four filters per SM, <= 50 landmarks.

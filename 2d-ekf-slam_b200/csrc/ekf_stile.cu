@@ -201,13 +201,11 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
     bool resumed = false;
     if (CAN_RESUME) {
       const int code = a.io.resume[f];
-      if (code == 0) continue;                           // finished by the primary launch
+      if (code == 0) continue;                           // finished (or being run) by the primary launch
+      if (a.io.continuation == 2 ? code > 0 : code < 0) continue;   // 2: only maps that were too large at launch; 1: only parked ones
       if (code > 0) { t_begin = (code - 1) / (M + 1); m_begin = (code - 1) % (M + 1); resumed = true; }
     }
-    if (CAN_PARK && n_lm > C::MAX_LM) {                  // the map does not fit this kernel's tiles: leave it to the continuation
-      if (tid == 0) a.io.resume[f] = -1;
-      continue;
-    }
+    if (CAN_PARK && n_lm > C::MAX_LM) continue;          // too large for these tiles at launch: marked, the concurrent continuation runs it
     {
       const int n_int = 4 + 2 * n_lm;
       // Column by column (a warp per column, a lane per row): the HBM reads are contiguous runs and
@@ -705,3 +703,16 @@ cudaError_t ekf_stile_run(const EkfState& st, const EkfRunIO& io, const EkfConst
   return cudaErrorInvalidValue;
 }
 int ekf_stile_fast_landmarks() { return STileCfg<13>::MAX_LM; }
+
+namespace {
+__global__ void stile_mark_grown(const int* __restrict__ nlm, int* __restrict__ resume, int F, int fast_cap) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < F) resume[f] = nlm[f] > fast_cap ? -2 : 0;
+}
+}  // namespace
+// resume[f] = -2 for the filters whose map is already beyond the fast tiles (they are run, from the start
+// of the lap, by a continuation launch with io.continuation = 2 beside the primary launch), else 0.
+cudaError_t ekf_stile_mark_grown(const int* nlm, int* resume, int F, cudaStream_t stream) {
+  stile_mark_grown<<<(F + 255) / 256, 256, 0, stream>>>(nlm, resume, F, STileCfg<13>::MAX_LM);
+  return cudaGetLastError();
+}
