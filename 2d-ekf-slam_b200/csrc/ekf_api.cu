@@ -56,6 +56,7 @@ struct ekf_handle_s {
   EkfState st{};
   int grid_cap = 0;           // regime A: co-resident CTAs
   EkfLargeWork wk{};          // regime B scratch
+  unsigned sweep_seq = 0;
   // staging
   DevBuf<double> in;          // per-call inputs
   DevBuf<int> o_dec, o_idx;
@@ -361,6 +362,22 @@ int ekf_create(ekf_handle* out, int device, int n_filters, int max_landmarks, co
     if ((e = cudaMalloc(&h->wk.small, ekf_large_small_doubles() * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
     cudaMemset(h->wk.W, 0, w_count * sizeof(double2));
     {
+      // look-ahead runs (ekf_large.cu): on unless EKF_LARGE_LOOKAHEAD=0 keeps every kernel on one stream
+      const char* env = getenv("EKF_LARGE_LOOKAHEAD");
+      h->wk.la = env ? (atoi(env) != 0) : 1;
+      env = getenv("EKF_LARGE_SNAKE");         // consecutive sweeps in opposite directions (L2 reuse)
+      h->wk.snake = env ? (atoi(env) != 0) : 1;
+      h->wk.sweep_seq = &h->sweep_seq;
+      h->wk.lds = (st.cap_n + 2 + 7) & ~7;
+      if ((e = cudaMalloc(&h->wk.strip, 3 * (size_t)h->wk.lds * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+      if ((e = cudaMalloc(&h->wk.diag, 4 * ((size_t)st.cap_lm + 1) * sizeof(double))) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+      int lo = 0, hi = 0;                      // the side chain's small grids go in front of the sweep's CTAs
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if ((e = cudaStreamCreateWithPriority(&h->wk.s_side, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+      cudaEventCreateWithFlags(&h->wk.ev_a, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->wk.ev_b, cudaEventDisableTiming);
+    }
+    {
       // TMA-staged downdate: on unless EKF_LARGE_TMA=0 selects the plain double2 sweep. No silent
       // fallback: if the tensor maps cannot be encoded the handle is not created (ekf_large_downdate_kernel()
       // reports which sweep a handle runs).
@@ -398,6 +415,10 @@ int ekf_destroy(ekf_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->st.x); cudaFree(h->st.P); cudaFree(h->st.nlm); cudaFree(h->st.status);
   cudaFree(h->wk.W); cudaFree(h->wk.cand_val); cudaFree(h->wk.cand_idx); cudaFree(h->wk.small);
+  cudaFree(h->wk.strip); cudaFree(h->wk.diag);
+  if (h->wk.s_side) cudaStreamDestroy(h->wk.s_side);
+  if (h->wk.ev_a) cudaEventDestroy(h->wk.ev_a);
+  if (h->wk.ev_b) cudaEventDestroy(h->wk.ev_b);
   h->in.release(); h->o_dec.release(); h->o_idx.release(); h->o_mah.release(); h->in_valid.release();
   h->resume.release(); h->pc_rec.release();
   if (h->s_grow) {

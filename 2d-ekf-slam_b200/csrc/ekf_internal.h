@@ -91,6 +91,16 @@ struct EkfLargeWork {      // device scratch owned by the handle
   const unsigned char* tmaps;   // [F][ekf_large_tma_map_bytes()] or null
   int tma_grid;
   int use_tma;
+  // look-ahead runs (ekf_large.cu header): O(n) cache of what the next operation's gating reads, a side
+  // stream for the chain that works on the cache alone, and the two events that join the streams
+  double* strip;           // [3][lds]
+  double* diag;            // [cap_lm][4]
+  int lds;
+  unsigned* sweep_seq;     // host counter of sweeps launched (direction of the next one)
+  int snake;
+  int la;                  // 1: ekf_large_run overlaps gating / decision with the previous sweep
+  cudaStream_t s_side;
+  cudaEvent_t ev_a, ev_b;
 };
 
 // Device addresses the TMA downdate reads its control state from (fields of LargeSmall).
@@ -102,6 +112,9 @@ struct EkfLargeTmaArgs {
   const double2* W;
   int* nlm_out;
   const int* n_lm;
+  // Consecutive sweeps walk the tiles in opposite directions: what one sweep touched last is what the next
+  // touches first, so a covariance of about the size of the 126 MB L2 is largely served from it.
+  int reverse;
 };
 size_t ekf_large_tma_map_bytes();
 cudaError_t ekf_large_tma_encode(void* map_out, double* P, int cap_n, int ld);

@@ -18,6 +18,17 @@
 // The arithmetic is the same code the batch regime uses (ekf_small.cuh), so decisions follow
 // the reference's operation order; the downdate uses the bit-symmetric two-fma form described
 // in ekf_cta.cuh.
+//
+// Look-ahead (the LA = true instantiations, used by ekf_large_run): of everything the dense sweep
+// of operation k writes, the gating / decision chain of operation k+1 reads only O(n) entries - the
+// three robot columns and the 2x2 diagonal blocks. Those are kept in a small cache (strip[3][lds],
+// diag[lm][4]) that the gain kernel itself brings up to date with the same two-fma expression the
+// sweep applies to P, so propagate, gating and the decision of operation k+1 run on a second stream
+// WHILE the sweep of operation k is still streaming P; only the gain kernel (which needs two full,
+// swept columns of P) stays between two consecutive sweeps. P's own robot rows / columns are stale
+// during such a run and are written back from the cache when it ends (la_store); the diagonal blocks in
+// P always equal the cache (same operations, same bits). The control block is double-buffered so the
+// decision of operation k+1 never overwrites what the sweep of operation k is reading.
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
 #include "ekf_pdl.cuh"
@@ -36,6 +47,7 @@ struct LargeSmall {
   double l, sq0, sq1, m0, m1;
   double nl[2], PLL[4], h3n[2];
   double cres, cS, csq, cm0;
+  double2 Wp[3];  // look-ahead: downdate vectors of the pose rows (computed with the decision)
 };
 
 struct LargeArgs {
@@ -47,18 +59,29 @@ struct LargeArgs {
   double* cand_val;
   int* cand_idx;
   int n_cand;
+  double* strip;  // look-ahead cache: strip[r*lds + i] = P(i, r), r = 0..2 (includes the 3x3 robot block)
+  double* diag;   // look-ahead cache: diag[4*lm + q] = the 2x2 block of landmark lm, column-major
+  int lds;
+  int la;         // 1: look-ahead run (the sweep leaves the landmark count alone)
+  int reverse;    // plain sweep: walk the tiles back to front
 };
 
 __device__ __forceinline__ double* filt_P(const LargeArgs& a) { return a.st.P + (size_t)a.f * a.st.slab; }
 __device__ __forceinline__ double* filt_x(const LargeArgs& a) { return a.st.x + (size_t)a.f * a.st.xs; }
 
 // ---- propagate ---------------------------------------------------------------------------------
+// The 3x3 robot block lives in P (element (i,j) at P[i + j*ld]) or, in a look-ahead run, in the cache.
+template <bool LA>
+__device__ __forceinline__ double* prr_elem(const LargeArgs& a, double* P, int i, int j) {
+  return LA ? a.strip + (size_t)j * a.lds + i : P + i + (size_t)j * a.st.ld;
+}
+
+template <bool LA>
 __global__ void large_prop_setup(const LargeArgs a, const double* vel, const double* rot, const double* dt) {
   ekf_pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double* P = filt_P(a);
   double* x = filt_x(a);
-  const int ld = a.st.ld;
   PropSetup p;
   ekf_build_prop(p, *vel, *rot, *dt, x[2], a.k);
   a.sm->prop = p;
@@ -68,12 +91,13 @@ __global__ void large_prop_setup(const LargeArgs a, const double* vel, const dou
   x[2] = x[2] + p.dt * xm2;
   double PRR[9];
   for (int j = 0; j < 3; ++j)
-    for (int i = 0; i < 3; ++i) PRR[i + 3 * j] = P[i + (size_t)j * ld];
+    for (int i = 0; i < 3; ++i) PRR[i + 3 * j] = *prr_elem<LA>(a, P, i, j);
   ekf_prop_prr(p, PRR);
   for (int j = 0; j < 3; ++j)
-    for (int i = 0; i < 3; ++i) P[i + (size_t)j * ld] = PRR[i + 3 * j];
+    for (int i = 0; i < 3; ++i) *prr_elem<LA>(a, P, i, j) = PRR[i + 3 * j];
 }
 
+template <bool LA>
 __global__ void __launch_bounds__(kThreads) large_prop_strip(const LargeArgs a) {
   __shared__ PropSetup ps;
   ekf_pdl_entry();
@@ -83,6 +107,13 @@ __global__ void __launch_bounds__(kThreads) large_prop_strip(const LargeArgs a) 
   const int ld = a.st.ld;
   const int n = 3 + 2 * a.st.nlm[a.f];
   for (int j = 3 + blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
+    if (LA) {                                   // the cache is the strip; P's copy is written back by la_store
+      double* c = a.strip + j;
+      double a0 = c[0], a1 = c[a.lds], a2 = c[2 * (size_t)a.lds];
+      ekf_prop_col(ps, a0, a1, a2);
+      c[0] = a0; c[a.lds] = a1; c[2 * (size_t)a.lds] = a2;
+      continue;
+    }
     double a0 = P[j], a1 = P[j + (size_t)ld], a2 = P[j + (size_t)2 * ld];   // mirror rows: coalesced
     ekf_prop_col(ps, a0, a1, a2);
     P[j] = a0;
@@ -94,21 +125,34 @@ __global__ void __launch_bounds__(kThreads) large_prop_strip(const LargeArgs a) 
 }
 
 // ---- update: gating ------------------------------------------------------------------------------
-__device__ __forceinline__ void load_gate_inputs(const double* P, int ld, int Li, double* p, double* pll) {
+template <bool LA>
+__device__ __forceinline__ void load_gate_inputs(const LargeArgs& a, const double* P, int ld, int Li, double* p, double* pll) {
+  if constexpr (LA) {
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    p[0 + 2 * j] = P[Li + (size_t)j * ld];
-    p[1 + 2 * j] = P[Li + 1 + (size_t)j * ld];
+    for (int j = 0; j < 3; ++j) {
+      p[0 + 2 * j] = a.strip[(size_t)j * a.lds + Li];
+      p[1 + 2 * j] = a.strip[(size_t)j * a.lds + Li + 1];
+    }
+    const double2* d = reinterpret_cast<const double2*>(a.diag + 2 * (Li - 3));   // 4 doubles per landmark
+    const double2 d0 = d[0], d1 = d[1];
+    pll[0] = d0.x; pll[1] = d0.y; pll[2] = d1.x; pll[3] = d1.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      p[0 + 2 * j] = P[Li + (size_t)j * ld];
+      p[1 + 2 * j] = P[Li + 1 + (size_t)j * ld];
+    }
+    pll[0] = P[Li + (size_t)Li * ld];
+    pll[1] = P[Li + 1 + (size_t)Li * ld];
+    pll[2] = P[Li + (size_t)(Li + 1) * ld];
+    pll[3] = P[Li + 1 + (size_t)(Li + 1) * ld];
   }
-  pll[0] = P[Li + (size_t)Li * ld];
-  pll[1] = P[Li + 1 + (size_t)Li * ld];
-  pll[2] = P[Li + (size_t)(Li + 1) * ld];
-  pll[3] = P[Li + 1 + (size_t)(Li + 1) * ld];
 }
 
 // chunk_pos: 0 = a doUpdate call of its own (gating bound = live landmark count); 1 = first
 // measurement of an n_z > 1 call (same bound, and block 0 records it); 2 = later measurement of that
 // call: Update.cpp:26 read n_lm once, so landmarks added since the call began are not candidates.
+template <bool LA>
 __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const double* zr, int chunk_pos) {
   __shared__ CtaScratch sc;
   ekf_pdl_entry();
@@ -120,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const 
   if (threadIdx.x == 0) {
     double PRR[9];
     for (int j = 0; j < 3; ++j)
-      for (int i = 0; i < 3; ++i) PRR[i + 3 * j] = P[i + (size_t)j * ld];
+      for (int i = 0; i < 3; ++i) PRR[i + 3 * j] = *prr_elem<LA>(a, const_cast<double*>(P), i, j);
     UpdateSetup u;
     ekf_build_setup(u, x[2], x[0], x[1], PRR, zr[0], zr[1], zr + 2);
     sc.upd = u;
@@ -132,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const 
   for (int lm = blockIdx.x * kThreads + threadIdx.x; lm < n_lm; lm += gridDim.x * kThreads) {
     const int Li = 3 + 2 * lm;
     double p[6], pll[4];
-    load_gate_inputs(P, ld, Li, p, pll);
+    load_gate_inputs<LA>(a, P, ld, Li, p, pll);
     GateResult g;
     ekf_gate_landmark(sc.upd, x[Li], x[Li + 1], p, pll, a.k.cond_max, g);
     const bool valid = !g.skip && (a.k.mahal_init > g.d2);
@@ -146,6 +190,10 @@ __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const 
 }
 
 // ---- update: decision ------------------------------------------------------------------------------
+// Look-ahead runs: the decision thread also finishes the three pose rows of the operation (gain, state,
+// downdate vectors, the 3x3 block of the cache) - it has every input in the cache, and it keeps the
+// gain kernel, the only kernel left between two sweeps, free of any cross-CTA dependence.
+template <bool LA>
 __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, const double* zr, int* out_decision,
                                                         int* out_index, double* out_mahal) {
   __shared__ CtaScratch sc;
@@ -161,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
   if (threadIdx.x != 0) return;
   LargeSmall* sm = a.sm;
   const double* P = filt_P(a);
-  const double* x = filt_x(a);
+  double* x = filt_x(a);
   const int ld = a.st.ld;
   const int n_lm = a.st.nlm[a.f];
   const int n = 3 + 2 * n_lm;
@@ -172,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
   const UpdateSetup& u = sm->upd;
   if (decision == EKF_DEC_OLD) {
     double p[6], pll[4];
-    load_gate_inputs(P, ld, opt_i, p, pll);
+    load_gate_inputs<LA>(a, P, ld, opt_i, p, pll);
     GateResult g;
     ekf_gate_landmark(u, x[opt_i], x[opt_i + 1], p, pll, a.k.cond_max, g);   // same bits as the gating pass
     sm->res[0] = g.res0; sm->res[1] = g.res1;
@@ -185,6 +233,37 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
     sm->sq1 = sqrt(fabs(d1));
     sm->m0 = d0 < 0 ? 1.0 : -1.0;
     sm->m1 = d1 < 0 ? 1.0 : -1.0;
+    if (LA) {
+      // pose rows i = 0..2 of large_gain's Old branch (same expressions), then the 3x3 block of the cache
+      // in the sweep's element form v <- fma(u_i1, w_j.y, v); v <- fma(u_i0, w_j.x, v)
+      const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = g.h3_0;
+      const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = g.h3_1;
+      const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
+      const double s00 = sm->Si[0], s10 = sm->Si[1], s01 = sm->Si[2], s11 = sm->Si[3];
+      double2 w[3];
+      for (int i = 0; i < 3; ++i) {
+        const double p0 = a.strip[i], p1 = a.strip[a.lds + i], p2 = a.strip[2 * (size_t)a.lds + i];
+        const double pa = a.strip[(size_t)i * a.lds + opt_i], pb = a.strip[(size_t)i * a.lds + opt_i + 1];
+        const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
+        const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
+        const double B0 = pa * c00 + pb * c10;
+        const double B1 = pa * c01 + pb * c11;
+        const double M0 = A0 + B0, M1 = A1 + B1;
+        const double K0 = M0 * s00 + M1 * s10;
+        const double K1 = M0 * s01 + M1 * s11;
+        x[i] = x[i] + (K0 * g.res0 + K1 * g.res1);
+        w[i] = make_double2(sm->sq0 * fma(l, K1, K0), sm->sq1 * K1);
+        sm->Wp[i] = w[i];
+      }
+      for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) {
+          double* e = prr_elem<true>(a, nullptr, i, j);
+          double v = *e;
+          v = fma(sm->m1 * w[i].y, w[j].y, v);
+          v = fma(sm->m0 * w[i].x, w[j].x, v);
+          *e = v;
+        }
+    }
   } else if (decision == EKF_DEC_NEW) {
     if (n_lm >= a.st.cap_lm) {
       decision = EKF_DEC_DROPPED;
@@ -214,6 +293,24 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
       sm->nl[0] = nl0; sm->nl[1] = nl1;
       sm->h3n[0] = h30; sm->h3n[1] = h31;
       index = n;
+      if (LA) {
+        // pose rows of large_gain's New branch, the new diagonal block, the new state entries and the
+        // landmark count - all cache / vector writes, nothing the running sweep touches
+        const double ct00 = u.Ct[0], ct10 = u.Ct[1], ct01 = u.Ct[2], ct11 = u.Ct[3];
+        for (int i = 0; i < 3; ++i) {
+          const double q0 = -a.strip[i], q1 = -a.strip[a.lds + i], q2 = -a.strip[2 * (size_t)a.lds + i];
+          const double t0 = (q0 * HR[0] + q1 * HR[2]) + q2 * h30;
+          const double t1 = (q0 * HR[1] + q1 * HR[3]) + q2 * h31;
+          a.strip[(size_t)i * a.lds + n] = t0 * ct00 + t1 * ct10;
+          a.strip[(size_t)i * a.lds + n + 1] = t0 * ct01 + t1 * ct11;
+        }
+        const double off = 0.5 * (sm->PLL[2] + sm->PLL[1]);
+        double* d = a.diag + 4 * (size_t)n_lm;
+        d[0] = sm->PLL[0]; d[1] = off; d[2] = off; d[3] = sm->PLL[3];
+        x[n] = nl0;
+        x[n + 1] = nl1;
+        a.st.nlm[a.f] = n_lm + 1;
+      }
     }
   }
   sm->decision = decision;
@@ -286,6 +383,94 @@ __global__ void __launch_bounds__(kThreads) large_gain(const LargeArgs a) {
   }
 }
 
+// Look-ahead form of large_gain: one landmark (two rows) per thread, pose rows already done by
+// large_decide<true>. Besides what large_gain does, the thread brings the landmark's cache entries (its
+// three strip columns' worth of robot-row elements and its 2x2 diagonal block) up to date with exactly
+// the fma pair the sweep applies to the same elements of P.
+__global__ void __launch_bounds__(kThreads) large_gain_la(const LargeArgs a) {
+  ekf_pdl_entry();
+  const LargeSmall* sm = a.sm;
+  const int decision = sm->decision;
+  if (decision != EKF_DEC_OLD && decision != EKF_DEC_NEW) return;
+  double* P = filt_P(a);
+  double* x = filt_x(a);
+  const int ld = a.st.ld, n = sm->n, n_lm = sm->n_lm, lds = a.lds;
+  const UpdateSetup& u = sm->upd;
+  const int lm0 = blockIdx.x * kThreads + threadIdx.x, stride = gridDim.x * kThreads;
+  if (decision == EKF_DEC_OLD) {
+    const int opt_i = sm->opt_i;
+    const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = sm->h3[0];
+    const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = sm->h3[1];
+    const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
+    const double s00 = sm->Si[0], s10 = sm->Si[1], s01 = sm->Si[2], s11 = sm->Si[3];
+    const double r0 = sm->res[0], r1 = sm->res[1], l = sm->l, sq0 = sm->sq0, sq1 = sm->sq1;
+    const double m0 = sm->m0, m1 = sm->m1;
+    const double2 wp0 = sm->Wp[0], wp1 = sm->Wp[1], wp2 = sm->Wp[2];
+    if (lm0 == 0) {
+      a.W[0] = wp0; a.W[1] = wp1; a.W[2] = wp2;
+      a.W[n] = make_double2(0.0, 0.0);            // pad row of the double2 sweep (n is odd)
+    }
+    for (int lm = lm0; lm < n_lm; lm += stride) {
+      const int Li = 3 + 2 * lm;
+      double2 w[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = Li + e;
+        const double p0 = a.strip[i], p1 = a.strip[lds + i], p2 = a.strip[2 * (size_t)lds + i];
+        const double pa = P[i + (size_t)opt_i * ld], pb = P[i + (size_t)(opt_i + 1) * ld];
+        const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
+        const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
+        const double B0 = pa * c00 + pb * c10;
+        const double B1 = pa * c01 + pb * c11;
+        const double M0 = A0 + B0, M1 = A1 + B1;
+        const double K0 = M0 * s00 + M1 * s10;      // Update.cpp:186
+        const double K1 = M0 * s01 + M1 * s11;
+        x[i] = x[i] + (K0 * r0 + K1 * r1);          // :187
+        w[e] = make_double2(sq0 * fma(l, K1, K0), sq1 * K1);
+        a.W[i] = w[e];
+        const double u0 = m0 * w[e].x, u1 = m1 * w[e].y;
+        a.strip[i] = fma(u0, wp0.x, fma(u1, wp0.y, p0));
+        a.strip[lds + i] = fma(u0, wp1.x, fma(u1, wp1.y, p1));
+        a.strip[2 * (size_t)lds + i] = fma(u0, wp2.x, fma(u1, wp2.y, p2));
+      }
+      double2* d = reinterpret_cast<double2*>(a.diag + 4 * (size_t)lm);
+      double2 d0 = d[0], d1 = d[1];               // (Li,Li) (Li+1,Li) | (Li,Li+1) (Li+1,Li+1)
+      const double ua0 = m0 * w[0].x, ua1 = m1 * w[0].y, ub0 = m0 * w[1].x, ub1 = m1 * w[1].y;
+      d0.x = fma(ua0, w[0].x, fma(ua1, w[0].y, d0.x));
+      d0.y = fma(ub0, w[0].x, fma(ub1, w[0].y, d0.y));
+      d1.x = fma(ua0, w[1].x, fma(ua1, w[1].y, d1.x));
+      d1.y = fma(ub0, w[1].x, fma(ub1, w[1].y, d1.y));
+      d[0] = d0; d[1] = d1;
+    }
+  } else {
+    const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = sm->h3n[0];
+    const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = sm->h3n[1];
+    const double ct00 = u.Ct[0], ct10 = u.Ct[1], ct01 = u.Ct[2], ct11 = u.Ct[3];
+    for (int lm = lm0; lm < n_lm; lm += stride) {   // Update.cpp:169,175-176 (rows 0..2: large_decide<true>)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 3 + 2 * lm + e;
+        const double q0 = -a.strip[i], q1 = -a.strip[lds + i], q2 = -a.strip[2 * (size_t)lds + i];
+        const double t0 = (q0 * h00 + q1 * h01) + q2 * h02;
+        const double t1 = (q0 * h10 + q1 * h11) + q2 * h12;
+        const double o0 = t0 * ct00 + t1 * ct10;
+        const double o1 = t0 * ct01 + t1 * ct11;
+        P[i + (size_t)n * ld] = o0;
+        P[i + (size_t)(n + 1) * ld] = o1;
+        P[n + (size_t)i * ld] = o0;
+        P[n + 1 + (size_t)i * ld] = o1;
+      }
+    }
+    if (lm0 == 0) {
+      const double off = 0.5 * (sm->PLL[2] + sm->PLL[1]);
+      P[n + (size_t)n * ld] = sm->PLL[0];
+      P[n + 1 + (size_t)n * ld] = off;
+      P[n + (size_t)(n + 1) * ld] = off;
+      P[n + 1 + (size_t)(n + 1) * ld] = sm->PLL[3];
+    }
+  }
+}
+
 // ---- the HBM-bound kernel: dense symmetric rank-RANK downdate --------------------------------------
 // P_ij <- P_ij + u_i0*W_j0 + u_i1*W_j1,  u = (m0*W_0, m1*W_1). Column-major P: each thread owns
 // two consecutive rows (one 16-byte double2) of a 512-row panel and walks CB columns with all
@@ -297,13 +482,13 @@ __global__ void __launch_bounds__(kThreads) large_downdate(const LargeArgs a) {
   const LargeSmall* sm = a.sm;
   if (!COMPASS) {
     if (sm->decision != EKF_DEC_OLD) {
-      if (sm->decision == EKF_DEC_NEW && blockIdx.x == 0 && threadIdx.x == 0) a.st.nlm[a.f] = sm->n_lm + 1;
+      if (sm->decision == EKF_DEC_NEW && !a.la && blockIdx.x == 0 && threadIdx.x == 0) a.st.nlm[a.f] = sm->n_lm + 1;
       return;
     }
   }
   double* P = filt_P(a);
   const int ld = a.st.ld;
-  const int n = COMPASS ? 3 + 2 * a.st.nlm[a.f] : sm->n;
+  const int n = sm->n;      // set by large_decide / large_compass_setup
   const double m0 = COMPASS ? sm->cm0 : sm->m0, m1 = COMPASS ? 0.0 : sm->m1;
   const int n_even = (n + 1) & ~1;
   const int rows_per_panel = 2 * kThreads;
@@ -311,7 +496,8 @@ __global__ void __launch_bounds__(kThreads) large_downdate(const LargeArgs a) {
   const int n_cb = (n + kCB - 1) / kCB;
   const long n_tiles = (long)n_panels * n_cb;
   const double2* __restrict__ W = a.W;
-  for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (long tk = blockIdx.x; tk < n_tiles; tk += gridDim.x) {
+    const long tile = a.reverse ? n_tiles - 1 - tk : tk;
     const int panel = (int)(tile % n_panels), cb = (int)(tile / n_panels);
     const int i = panel * rows_per_panel + 2 * threadIdx.x;
     if (i >= n_even) continue;
@@ -347,18 +533,34 @@ __global__ void __launch_bounds__(kThreads) large_downdate(const LargeArgs a) {
 }
 
 // ---- compass ---------------------------------------------------------------------------------------
+template <bool LA>
 __global__ void large_compass_setup(const LargeArgs a, const double* z, const double* R) {
   ekf_pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double* P = filt_P(a);
-  const double* x = filt_x(a);
+  double* P = filt_P(a);
+  double* x = filt_x(a);
   LargeSmall* sm = a.sm;
   sm->cres = ekf_compass_residual(x[2], *z, a.k);
-  const double S = P[2 + (size_t)2 * a.st.ld] + *R;
+  const double S = *prr_elem<LA>(a, P, 2, 2) + *R;
   sm->cS = S;
   sm->csq = sqrt(fabs(S));
   sm->cm0 = S < 0 ? 1.0 : -1.0;
   sm->n = 3 + 2 * a.st.nlm[a.f];
+  if (LA) {   // pose rows of large_compass_gain and the 3x3 block of the cache (rank-1 sweep form)
+    const double res = sm->cres, invS = 1 / sm->cS, sq = sm->csq;
+    double2 w[3];
+    for (int i = 0; i < 3; ++i) {
+      const double Ki = invS * a.strip[2 * (size_t)a.lds + i];
+      x[i] = x[i] + res * Ki;
+      w[i] = make_double2(sq * Ki, 0.0);
+      sm->Wp[i] = w[i];
+    }
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) {
+        double* e = prr_elem<true>(a, nullptr, i, j);
+        *e = fma(sm->cm0 * w[i].x, w[j].x, *e);
+      }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) large_compass_gain(const LargeArgs a) {
@@ -377,6 +579,76 @@ __global__ void __launch_bounds__(kThreads) large_compass_gain(const LargeArgs a
   }
 }
 
+// Look-ahead form of large_compass_gain: landmark rows only, cache kept current (rank 1).
+__global__ void __launch_bounds__(kThreads) large_compass_gain_la(const LargeArgs a) {
+  ekf_pdl_entry();
+  const LargeSmall* sm = a.sm;
+  double* x = filt_x(a);
+  const int n = sm->n, n_lm = (n - 3) / 2, lds = a.lds;
+  const double res = sm->cres, invS = 1 / sm->cS, sq = sm->csq, m0 = sm->cm0;
+  const double w0 = sm->Wp[0].x, w1 = sm->Wp[1].x, w2 = sm->Wp[2].x;
+  const int lm0 = blockIdx.x * kThreads + threadIdx.x;
+  if (lm0 == 0) {
+    a.W[0] = sm->Wp[0]; a.W[1] = sm->Wp[1]; a.W[2] = sm->Wp[2];
+    a.W[n] = make_double2(0.0, 0.0);
+  }
+  for (int lm = lm0; lm < n_lm; lm += gridDim.x * kThreads) {
+    double wv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 3 + 2 * lm + e;
+      const double p0 = a.strip[i], p1 = a.strip[lds + i], p2 = a.strip[2 * (size_t)lds + i];
+      const double Ki = invS * p2;
+      x[i] = x[i] + res * Ki;
+      wv[e] = sq * Ki;
+      a.W[i] = make_double2(wv[e], 0.0);
+      const double u0 = m0 * wv[e];
+      a.strip[i] = fma(u0, w0, p0);
+      a.strip[lds + i] = fma(u0, w1, p1);
+      a.strip[2 * (size_t)lds + i] = fma(u0, w2, p2);
+    }
+    double2* d = reinterpret_cast<double2*>(a.diag + 4 * (size_t)lm);
+    double2 d0 = d[0], d1 = d[1];
+    const double ua = m0 * wv[0], ub = m0 * wv[1];
+    d0.x = fma(ua, wv[0], d0.x);
+    d0.y = fma(ub, wv[0], d0.y);
+    d1.x = fma(ua, wv[1], d1.x);
+    d1.y = fma(ub, wv[1], d1.y);
+    d[0] = d0; d[1] = d1;
+  }
+}
+
+// ---- look-ahead cache <-> P -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) large_la_load(const LargeArgs a) {
+  const double* P = filt_P(a);
+  const int ld = a.st.ld, n = 3 + 2 * a.st.nlm[a.f];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    a.strip[i] = P[i];
+    a.strip[a.lds + i] = P[i + (size_t)ld];
+    a.strip[2 * (size_t)a.lds + i] = P[i + (size_t)2 * ld];
+    if (i >= 3) {                                   // i = Li + e: column e of the landmark's 2x2 block
+      const int Li = 3 + 2 * ((i - 3) >> 1), e = (i - 3) & 1;
+      a.diag[2 * (size_t)(Li - 3) + 2 * e + 0] = P[Li + (size_t)i * ld];
+      a.diag[2 * (size_t)(Li - 3) + 2 * e + 1] = P[Li + 1 + (size_t)i * ld];
+    }
+  }
+}
+// Robot rows and columns of P from the cache (the diagonal blocks of P are current, see the header).
+__global__ void __launch_bounds__(kThreads) large_la_store(const LargeArgs a) {
+  double* P = filt_P(a);
+  const int ld = a.st.ld, n = 3 + 2 * a.st.nlm[a.f];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const double v0 = a.strip[i], v1 = a.strip[a.lds + i], v2 = a.strip[2 * (size_t)a.lds + i];
+    P[i] = v0;
+    P[i + (size_t)ld] = v1;
+    P[i + (size_t)2 * ld] = v2;
+    if (i >= 3) {
+      double* c = P + (size_t)i * ld;
+      c[0] = v0; c[1] = v1; c[2] = v2;
+    }
+  }
+}
+
 LargeArgs make_args(const EkfState& st, int f, const EkfConst& k, const EkfLargeWork& wk, int n_cand) {
   LargeArgs a;
   a.st = st;
@@ -387,6 +659,11 @@ LargeArgs make_args(const EkfState& st, int f, const EkfConst& k, const EkfLarge
   a.cand_val = wk.cand_val;
   a.cand_idx = wk.cand_idx;
   a.n_cand = n_cand;
+  a.strip = wk.strip;
+  a.diag = wk.diag;
+  a.lds = wk.lds;
+  a.la = 0;
+  a.reverse = 0;
   return a;
 }
 
@@ -401,43 +678,49 @@ int row_grid(const EkfState& st, const EkfLargeWork& wk) {
   return g < 1 ? 1 : g;
 }
 
-void launch_propagate(const LargeArgs& a, const EkfState& st, const EkfLargeWork& wk, const double* vel,
-                      const double* rot, const double* dt, cudaStream_t s) {
-  ekf_launch_pdl(large_prop_setup, 1, 32, 0, s, a, vel, rot, dt);
-  ekf_launch_pdl(large_prop_strip, row_grid(st, wk), kThreads, 0, s, a);
-}
-void launch_update(LargeArgs a, const EkfState& st, const EkfLargeWork& wk, const double* zr, int chunk_pos, int* dec,
-                   int* idx, double* mah, EkfLargeTiming* tm, cudaStream_t s) {
-  const int gg = gate_grid(st, wk);
-  a.n_cand = gg;
-  ekf_launch_pdl(large_gate, gg, kThreads, 0, s, a, zr, chunk_pos);
-  ekf_launch_pdl(large_decide, 1, kThreads, 0, s, a, zr, dec, idx, mah);
-  ekf_launch_pdl(large_gain, row_grid(st, wk), kThreads, 0, s, a);
-  const bool sample = tm && tm->used < tm->cap && (tm->seen++ % tm->every) == 0;
+// The dense sweep of one operation (rank 2 after a landmark update, rank 1 after a compass update).
+void launch_sweep(LargeArgs a, const EkfLargeWork& wk, bool compass, EkfLargeTiming* tm, cudaStream_t s) {
+  const bool sample = !compass && tm && tm->used < tm->cap && (tm->seen++ % tm->every) == 0;
   if (sample) cudaEventRecord(tm->ev0[tm->used], s);
+  const int reverse = wk.snake ? (int)((*wk.sweep_seq)++ & 1) : 0;
+  a.reverse = reverse;
   if (wk.use_tma) {
-    EkfLargeTmaArgs t{&a.sm->decision, &a.sm->n, &a.sm->m0, &a.sm->m1, a.W, a.st.nlm + a.f, &a.sm->n_lm};
-    ekf_large_tma_downdate(t, wk.tmaps + (size_t)a.f * ekf_large_tma_map_bytes(), wk.tma_grid, false, s);
+    EkfLargeTmaArgs t{&a.sm->decision, &a.sm->n, &a.sm->m0, &a.sm->m1, a.W, a.la ? nullptr : a.st.nlm + a.f, &a.sm->n_lm, reverse};
+    if (compass) t = EkfLargeTmaArgs{nullptr, &a.sm->n, &a.sm->cm0, &a.sm->cm0, a.W, nullptr, nullptr, reverse};
+    ekf_large_tma_downdate(t, wk.tmaps + (size_t)a.f * ekf_large_tma_map_bytes(), wk.tma_grid, compass, s);
+  } else if (compass) {
+    ekf_launch_pdl(large_downdate<1, true>, wk.grid, kThreads, 0, s, a);
   } else {
     ekf_launch_pdl(large_downdate<2, false>, wk.grid, kThreads, 0, s, a);
   }
   if (sample) cudaEventRecord(tm->ev1[tm->used++], s);
 }
+
+void launch_propagate(const LargeArgs& a, const EkfState& st, const EkfLargeWork& wk, const double* vel,
+                      const double* rot, const double* dt, cudaStream_t s) {
+  ekf_launch_pdl(large_prop_setup<false>, 1, 32, 0, s, a, vel, rot, dt);
+  ekf_launch_pdl(large_prop_strip<false>, row_grid(st, wk), kThreads, 0, s, a);
+}
+void launch_update(LargeArgs a, const EkfState& st, const EkfLargeWork& wk, const double* zr, int chunk_pos, int* dec,
+                   int* idx, double* mah, EkfLargeTiming* tm, cudaStream_t s) {
+  const int gg = gate_grid(st, wk);
+  a.n_cand = gg;
+  ekf_launch_pdl(large_gate<false>, gg, kThreads, 0, s, a, zr, chunk_pos);
+  ekf_launch_pdl(large_decide<false>, 1, kThreads, 0, s, a, zr, dec, idx, mah);
+  ekf_launch_pdl(large_gain, row_grid(st, wk), kThreads, 0, s, a);
+  launch_sweep(a, wk, false, tm, s);
+}
 void launch_compass(const LargeArgs& a, const EkfState& st, const EkfLargeWork& wk, const double* z, const double* R,
                     cudaStream_t s) {
-  ekf_launch_pdl(large_compass_setup, 1, 32, 0, s, a, z, R);
+  ekf_launch_pdl(large_compass_setup<false>, 1, 32, 0, s, a, z, R);
   ekf_launch_pdl(large_compass_gain, row_grid(st, wk), kThreads, 0, s, a);
-  if (wk.use_tma) {
-    EkfLargeTmaArgs t{nullptr, &a.sm->n, &a.sm->cm0, &a.sm->cm0, a.W, nullptr, nullptr};
-    ekf_large_tma_downdate(t, wk.tmaps + (size_t)a.f * ekf_large_tma_map_bytes(), wk.tma_grid, true, s);
-  } else {
-    ekf_launch_pdl(large_downdate<1, true>, wk.grid, kThreads, 0, s, a);
-  }
+  launch_sweep(a, wk, true, nullptr, s);
 }
 
 }  // namespace
 
-size_t ekf_large_small_doubles() { return (sizeof(LargeSmall) + 7) / 8; }
+constexpr size_t kSmallStride = (sizeof(LargeSmall) + 15) / 16 * 16;   // two control blocks (look-ahead)
+size_t ekf_large_small_doubles() { return 2 * kSmallStride / 8; }
 
 cudaError_t ekf_large_prepare(int sm_count, int* grid) {
   int per_sm = 0;
@@ -470,9 +753,81 @@ cudaError_t ekf_large_percall(const EkfState& st, int filter, const EkfPercallIO
 
 // Fused-run equivalent for one filter: the host enqueues the kernel chain of every step; the
 // per-step flags (has_compass, n_z) come from the host mirror the C ABI keeps of the records.
+//
+// With look-ahead (wk.la, header comment) the chain is split over two streams. `stream` carries only
+// what has to sit between two sweeps: [gain of operation k] [sweep k]. wk.s_side carries everything
+// that works on the cache alone: [propagate] [gating k+1] [decision k+1], started as soon as gain k has
+// brought the cache up to date (event ev_a) and joined again before gain k+1 (event ev_b).
+static cudaError_t large_run_lookahead(const EkfState& st, int filter, const EkfRunIO& io, const uint8_t* has_compass,
+                                       const uint8_t* n_z, const EkfConst& k, const EkfLargeWork& wk,
+                                       EkfLargeTiming* tm, cudaStream_t A, long long* launches) {
+  LargeArgs a = make_args(st, filter, k, wk, 0);
+  a.la = 1;
+  cudaStream_t B = wk.s_side;
+  LargeSmall* const small0 = a.sm;
+  auto ctl = [&](long op) { return reinterpret_cast<LargeSmall*>(reinterpret_cast<unsigned char*>(small0) + (op & 1) * kSmallStride); };
+  const int rg = row_grid(st, wk), gg = gate_grid(st, wk);   // one landmark per thread: the gating grid fits both
+  large_la_load<<<rg, kThreads, 0, A>>>(a);
+  cudaEventRecord(wk.ev_a, A);
+  cudaStreamWaitEvent(B, wk.ev_a, 0);
+  *launches += 1;
+  long op = 0;
+  bool after_wait = true;          // the next side-stream kernel follows a cross-stream wait: plain launch
+  auto side = [&](auto kern, int grid, int threads, auto... args) {
+    if (after_wait) kern<<<grid, threads, 0, B>>>(args...);
+    else ekf_launch_pdl(kern, grid, threads, 0, B, args...);
+    after_wait = false;
+    *launches += 1;
+  };
+  for (int t = 0; t < io.T; ++t) {
+    const double* rec = io.records + ((size_t)filter * io.T + t) * io.L;
+    a.sm = ctl(op);
+    side(large_prop_setup<true>, 1, 32, a, rec + 0, rec + 1, rec + 2);
+    side(large_prop_strip<true>, rg, kThreads, a);
+    if (has_compass[t]) {
+      side(large_compass_setup<true>, 1, 32, a, rec + 3, rec + 4);
+      cudaEventRecord(wk.ev_b, B);
+      cudaStreamWaitEvent(A, wk.ev_b, 0);
+      large_compass_gain_la<<<gg, kThreads, 0, A>>>(a);
+      cudaEventRecord(wk.ev_a, A);
+      launch_sweep(a, wk, true, nullptr, A);
+      cudaStreamWaitEvent(B, wk.ev_a, 0);
+      after_wait = true;
+      *launches += 2;
+      a.sm = ctl(++op);
+    }
+    for (int m = 0; m < io.M; ++m) {
+      if (m >= n_z[t]) continue;
+      const size_t oi = ((size_t)filter * io.T + t) * io.M + m;
+      a.n_cand = gg;
+      side(large_gate<true>, gg, kThreads, a, rec + 8 + 6 * m, 0);
+      side(large_decide<true>, 1, kThreads, a, rec + 8 + 6 * m, io.decision ? io.decision + oi : nullptr,
+           io.index ? io.index + oi : nullptr, io.mahal ? io.mahal + oi : nullptr);
+      cudaEventRecord(wk.ev_b, B);
+      cudaStreamWaitEvent(A, wk.ev_b, 0);
+      large_gain_la<<<gg, kThreads, 0, A>>>(a);
+      cudaEventRecord(wk.ev_a, A);
+      launch_sweep(a, wk, false, tm, A);
+      cudaStreamWaitEvent(B, wk.ev_a, 0);
+      after_wait = true;
+      *launches += 2;
+      a.sm = ctl(++op);
+    }
+    if (io.pose_trace)             // the pose is written by side-stream kernels only
+      cudaMemcpyAsync(io.pose_trace + ((size_t)filter * io.T + t) * 3, st.x + (size_t)filter * st.xs,
+                      3 * sizeof(double), cudaMemcpyDeviceToDevice, B);
+  }
+  cudaEventRecord(wk.ev_b, B);
+  cudaStreamWaitEvent(A, wk.ev_b, 0);
+  large_la_store<<<rg, kThreads, 0, A>>>(a);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t ekf_large_run(const EkfState& st, int filter, const EkfRunIO& io, const uint8_t* has_compass,
                           const uint8_t* n_z, const EkfConst& k, const EkfLargeWork& wk, EkfLargeTiming* tm,
                           cudaStream_t stream, long long* launches) {
+  if (wk.la) return large_run_lookahead(st, filter, io, has_compass, n_z, k, wk, tm, stream, launches);
   const LargeArgs a = make_args(st, filter, k, wk, 0);
   for (int t = 0; t < io.T; ++t) {
     const double* rec = io.records + ((size_t)filter * io.T + t) * io.L;

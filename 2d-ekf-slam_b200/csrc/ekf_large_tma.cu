@@ -72,8 +72,9 @@ struct TmaParams {
   const double* m0;        // -sign(d0)
   const double* m1;        // -sign(d1) (unused for rank 1)
   const double2* W;
-  int* nlm_out;            // for the New bookkeeping the plain kernel also does
+  int* nlm_out;            // for the New bookkeeping the plain kernel also does (null: look-ahead run, done earlier)
   const int* n_lm;
+  int reverse;             // walk the tiles back to front (see ekf_large_tma_downdate)
 };
 
 template <int RANK, bool COMPASS>
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
   if (!COMPASS) {
     const int dec = *q.decision;
     if (dec != EKF_DEC_OLD) {
-      if (dec == EKF_DEC_NEW && blockIdx.x == 0 && threadIdx.x == 0) *q.nlm_out = *q.n_lm + 1;
+      if (dec == EKF_DEC_NEW && q.nlm_out && blockIdx.x == 0 && threadIdx.x == 0) *q.nlm_out = *q.n_lm + 1;
       return;
     }
   }
@@ -97,6 +98,8 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
   const long first = blockIdx.x;
   const long count = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
   const int tid = threadIdx.x;
+  const long t_sign = q.reverse ? -1 : 1, t_base = q.reverse ? n_tiles - 1 - first : first;
+  auto tile_of = [&](long k) { return t_base + t_sign * k * (long)gridDim.x; };
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], 1); }
     fence_barrier_init();
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
     // ---- producer: one thread drives the TMA engine ------------------------------------------------
     if (tid == kConsumers) {
       auto issue = [&](long k) {
-        const long tile = first + k * gridDim.x;
+        const long tile = tile_of(k);
         const int rt = (int)(tile % n_rt), ct = (int)(tile / n_rt);
         const int s = (int)(k % STAGES);
         mbar_expect_tx(&full[s], kTileBytes);
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
       for (long k = 0; k < count; ++k) {
         const int s = (int)(k % STAGES);
         mbar_wait(&done[s], (uint32_t)((k / STAGES) & 1));     // consumers finished tile k in stage s
-        const long tile = first + k * gridDim.x;
+        const long tile = tile_of(k);
         const int rt = (int)(tile % n_rt), ct = (int)(tile / n_rt);
         tma_store_2d(&tmap, rt * TR, ct * TC, tiles + (size_t)s * TR * TC);
         bulk_commit();
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
   const double2* __restrict__ W = q.W;
   for (long k = 0; k < count; ++k) {
     const int s = (int)(k % STAGES);
-    const long tile = first + k * gridDim.x;
+    const long tile = tile_of(k);
     const int rt = (int)(tile % n_rt), ct = (int)(tile / n_rt);
     const double2 wi = W[rt * TR + tid];
     const double u0 = m0 * wi.x, u1 = m1 * wi.y;
@@ -210,6 +213,7 @@ cudaError_t ekf_large_tma_prepare(int sm_count, int* grid) {
 cudaError_t ekf_large_tma_downdate(const EkfLargeTmaArgs& t, const void* map, int grid, bool compass, cudaStream_t s) {
   TmaParams q;
   q.decision = t.decision; q.n_dim = t.n_dim; q.m0 = t.m0; q.m1 = t.m1; q.W = t.W; q.nlm_out = t.nlm_out; q.n_lm = t.n_lm;
+  q.reverse = t.reverse;
   const size_t bytes = (size_t)STAGES * kTileBytes + 2 * STAGES * sizeof(uint64_t);
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(map);
   if (compass) return ekf_launch_pdl(large_downdate_tma<1, true>, grid, kThreadsTma, bytes, s, q, *m);

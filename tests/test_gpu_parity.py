@@ -152,6 +152,48 @@ def test_large_regime_fused_run(ekf, oracle):
     fb.close()
 
 
+@pytest.mark.parametrize("tma", [1, 0], ids=["tma", "plain"])
+def test_large_regime_lookahead_is_bit_identical_to_the_single_stream_chain(ekf, oracle, tma, monkeypatch):
+    """ekf_run() in regime B overlaps propagate / gating / decision of operation k+1 with the dense sweep of
+    operation k (second stream, O(n) cache of the robot columns and diagonal blocks, ekf_large.cu). The
+    cache is updated with the sweep's own fma pair, so the result must not differ by a single bit from
+    the one-stream chain (EKF_LARGE_LOOKAHEAD=0): map building (New), Old updates, two measurements per
+    step, compass updates, two filters, and runs cut into several calls (cache written back and reloaded).
+    The per-call surface (which never uses the cache) continues from the same state afterwards."""
+    monkeypatch.setenv("EKF_LARGE_TMA", str(tma))
+    N, F, T, cap, M = 40, 2, 260, 44, 2
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=M, compass_every=5)
+    lap = syn.generate(F, T)
+    rec = np.ascontiguousarray(np.concatenate([lap, lap], axis=1))
+    want = oracle.run_batch(rec, M, cap, pose_trace=True, final_state=True)
+    res = []
+    for la in ("1", "0"):
+        monkeypatch.setenv("EKF_LARGE_LOOKAHEAD", la)
+        fb = ekf.FilterBatch(F, cap, regime=2)
+        parts, lo = [], 0
+        for hi in (1, 9, 200, 333, 2 * T):
+            parts.append(fb.run(np.ascontiguousarray(rec[:, lo:hi]), M, trace=True, pose_trace=True))
+            lo = hi
+        got = {k: np.concatenate([q[k] for q in parts], axis=1) for k in ("decision", "index", "mahal", "pose_trace")}
+        got["final_nlm"] = parts[-1]["final_nlm"]
+        r = rec[0, 7]
+        fb.propagate(np.full(F, r[0]), np.full(F, r[1]), np.full(F, r[2]))
+        dec, idx, mah = fb.update(np.tile(r[8:10], (F, 1)), np.tile(r[10:14], (F, 1)))
+        res.append((got, _final_states(fb, F), (dec, idx, mah)))
+        fb.close()
+    (a, sa, ca), (b, sb, cb) = res
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    for (xa, Pa), (xb, Pb) in zip(sa, sb):
+        assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
+        assert np.array_equal(Pa, Pa.T)
+    for u, v in zip(ca, cb):
+        assert np.array_equal(u, v)
+    assert_trace_equal(a, want, "look-ahead run")
+    assert np.array_equal(a["final_nlm"], want["final_nlm"]) and (a["final_nlm"] == N).all()
+    assert rel_state(a["pose_trace"], want["pose_trace"]) <= TOL
+
+
 @pytest.mark.parametrize("N,steps", [(300, 40), (2000, 4)])
 def test_large_map_injected_state(ekf, oracle, N, steps):
     """BASELINE config 4 shape: state injected, then Old-updates streamed from HBM."""
@@ -367,6 +409,36 @@ def test_randomised_configuration_sweep(ekf, oracle, kernel):
             assert_state_close(x, P, xr, Pr, what + " filter %d" % f)
         fb.close()
     assert done >= 8
+
+
+@pytest.mark.parametrize("kernel,N,cap", [(1, 50, 50), (2, 50, 50), (3, 50, 50), (4, 50, 50), (0, 53, 56), (0, 20, 24)],
+                         ids=["smem", "tile", "stile", "dtile", "auto-grow", "auto-n20"])
+def test_fused_run_state_and_covariance_at_intermediate_steps(ekf, oracle, kernel, N, cap):
+    """The fused kernels keep x and P on chip for a whole ekf_run() call, so a final-state comparison
+    alone would not see a covariance error that a later step happens to hide. Cut the run into 14
+    calls (uneven lengths, cuts inside the map-building phase, at its end and deep in the second lap)
+    and compare the full state vector and covariance with the oracle after every one of them - the
+    oracle restarted from scratch on the same prefix of records, so the two sides share nothing."""
+    T, F, M = 1000, 3, 2
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=M, compass_every=7)
+    lap = syn.generate(F, T)
+    rec = np.ascontiguousarray(np.concatenate([lap, lap], axis=1))
+    cuts = [1, 2, 7, 40, 133, 290, 517, 760, 999, 1000, 1001, 1350, 1777, 2000]
+    fb = ekf.FilterBatch(F, cap, batch_kernel=kernel)
+    lo = 0
+    for hi in cuts:
+        got = fb.run(np.ascontiguousarray(rec[:, lo:hi]), M, trace=True)
+        want = oracle.run_batch(np.ascontiguousarray(rec[:, :hi]), M, cap, final_state=True)
+        assert not want["bad"]
+        for k in ("decision", "index"):
+            assert np.array_equal(got[k], want[k][:, lo:hi]), "%s in steps %d..%d" % (k, lo, hi)
+        assert np.array_equal(got["final_nlm"], want["final_nlm"])
+        for f, ((x, P), (xr, Pr)) in enumerate(zip(_final_states(fb, F), _oracle_states(want, F))):
+            assert_state_close(x, P, xr, Pr, "after step %d, filter %d" % (hi, f))
+            assert np.array_equal(P, P.T), "covariance must stay bit-symmetric (step %d)" % hi
+        lo = hi
+    assert (got["final_nlm"] == N).all()
+    fb.close()
 
 
 @pytest.mark.parametrize("N,cap", [(53, 56), (58, 62), (51, 51)])
