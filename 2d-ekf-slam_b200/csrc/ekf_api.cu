@@ -71,9 +71,12 @@ struct ekf_handle_s {
   // whether it can ride in one launch with the doUpdate that follows it (slam.cpp:136,170)
   bool prop_pending = false;
   std::vector<double> pend;   // [3][F]: vel, rotvel, dt of the held-back call
-  DevBuf<double> pc_rec;      // [F][14] step records of the fused propagate+update launch
-  double* stage[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned staging ring for those records
-  cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // [F][14] step records of the fused propagate+update launch: a ring of pinned staging buffers, each with
+  // its own device buffer, copied on the upload stream so the copy of call k+1 overlaps the kernel of call k
+  DevBuf<double> pc_rec[4];
+  double* stage[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};    // the copy out of stage[i] is done
+  cudaEvent_t stage_kev[4] = {nullptr, nullptr, nullptr, nullptr};   // the kernel that read pc_rec[i] is done
   int stage_i = 0;
   int rec_T = 0, rec_M = 0, rec_L = 0;
   bool have_trace = false, have_pose_trace = false;
@@ -420,7 +423,8 @@ int ekf_destroy(ekf_handle h) {
   if (h->wk.ev_a) cudaEventDestroy(h->wk.ev_a);
   if (h->wk.ev_b) cudaEventDestroy(h->wk.ev_b);
   h->in.release(); h->o_dec.release(); h->o_idx.release(); h->o_mah.release(); h->in_valid.release();
-  h->resume.release(); h->pc_rec.release();
+  h->resume.release();
+  for (int i = 0; i < 4; ++i) h->pc_rec[i].release();
   if (h->s_grow) {
     cudaStreamDestroy(h->s_grow);
     cudaEventDestroy(h->ev_grow0);
@@ -429,6 +433,7 @@ int ekf_destroy(ekf_handle h) {
   for (int i = 0; i < 4; ++i) {
     if (h->stage[i]) cudaFreeHost(h->stage[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+    if (h->stage_kev[i]) cudaEventDestroy(h->stage_kev[i]);
   }
   h->records.release(); h->t_dec.release(); h->t_idx.release(); h->t_mah.release(); h->t_pose.release();
   if (h->ev0) {
@@ -634,6 +639,8 @@ int ekf_update(ekf_handle h, int n_z, const double* z, const double* R, int32_t*
     if (!h->stage[si]) {
       EKF_CK(h, cudaMallocHost(&h->stage[si], F * L * sizeof(double)));
       EKF_CK(h, cudaEventCreateWithFlags(&h->stage_ev[si], cudaEventDisableTiming));
+      EKF_CK(h, cudaEventCreateWithFlags(&h->stage_kev[si], cudaEventDisableTiming));
+      EKF_CK(h, h->pc_rec[si].reserve(F * L));
     } else {
       EKF_CK(h, cudaEventSynchronize(h->stage_ev[si]));   // the copy that last read this staging buffer is done
     }
@@ -645,11 +652,12 @@ int ekf_update(ekf_handle h, int n_z, const double* z, const double* R, int32_t*
       r[8] = z[2 * f]; r[9] = z[2 * f + 1];
       for (int c = 0; c < 4; ++c) r[10 + c] = R[4 * f + c];
     }
-    EKF_CK(h, h->pc_rec.reserve(F * L));
-    EKF_CK(h, cudaMemcpyAsync(h->pc_rec.p, rec, F * L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    EKF_CK(h, cudaEventRecord(h->stage_ev[si], h->stream));
+    EKF_CK(h, cudaStreamWaitEvent(h->s_in, h->stage_kev[si], 0));   // (no-op until recorded) four calls ago
+    EKF_CK(h, cudaMemcpyAsync(h->pc_rec[si].p, rec, F * L * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    EKF_CK(h, cudaEventRecord(h->stage_ev[si], h->s_in));
+    EKF_CK(h, cudaStreamWaitEvent(h->stream, h->stage_ev[si], 0));
     EkfRunIO io{};
-    io.records = h->pc_rec.p; io.T = 1; io.M = 1; io.L = L;
+    io.records = h->pc_rec[si].p; io.T = 1; io.M = 1; io.L = L;
     const bool want = decision || lm_index || mahal;
     if (want) {
       EKF_CK(h, h->o_dec.reserve(F));
@@ -660,6 +668,7 @@ int ekf_update(ekf_handle h, int n_z, const double* z, const double* R, int32_t*
     kernel_event_begin(h);
     EKF_CK(h, launch_batch_kernel(h, pick_batch_kernel(h), h->st, io));
     kernel_event_end(h);
+    EKF_CK(h, cudaEventRecord(h->stage_kev[si], h->stream));
     h->launches += 1;
     if (!want) return EKF_OK;                        // fully asynchronous: no host round trip
     if (decision) EKF_CK(h, cudaMemcpyAsync(decision, h->o_dec.p, F * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

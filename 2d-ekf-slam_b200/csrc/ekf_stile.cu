@@ -211,30 +211,19 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
       // Column by column (a warp per column, a lane per row): the HBM reads are contiguous runs and
       // the scatter into the plane-major tiles is conflict-free. Column c of the stored triangle
       // starts at row 8*(c/8) (its diagonal tile is stored whole); dead entries are zeroed.
-      for (int c0 = warp; c0 < C::NI; c0 += 2 * C::NW) {        // two columns per pass: eight loads in flight per lane
-        double v[2][4];
+      // The copies are cp.async (global -> shared without passing through registers), so a lane has
+      // its whole share of the covariance in flight at once instead of eight loads per pass.
+      for (int c = warp; c < C::NI; c += C::NW) {
+        const bool col_live = c != 3 && c < n_int;
+        const double* gc = gP + (size_t)ext_index(c) * ld;
+        const int rlo = c & ~7, cb = 4 * (c & 7) * NT, cj = c >> 3;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = c0 + h * C::NW;
-          const bool col_live = c < C::NI && c != 3 && c < n_int;
-          const double* gc = gP + (size_t)ext_index(c < C::NI ? c : 0) * ld;
-          const int rlo = c & ~7;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int r = rlo + lane + 32 * k;
-            const bool live = col_live && r != 3 && r < n_int;
-            v[h][k] = live ? gc[ext_index(r)] : 0.0;
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = c0 + h * C::NW;
-          if (c >= C::NI) continue;
-          const int rlo = c & ~7, cb = 4 * (c & 7) * NT, cj = c >> 3;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int r = rlo + lane + 32 * k;
-            if (r < C::NI) T[(r & 3) * NT + cb + tile_number<NB>(r >> 2, cj)] = v[h][k];
+        for (int k = 0; k < 4; ++k) {
+          const int r = rlo + lane + 32 * k;
+          if (r < C::NI) {
+            double* dst = &T[(r & 3) * NT + cb + tile_number<NB>(r >> 2, cj)];
+            if (col_live && r != 3 && r < n_int) cp_async8(dst, gc + ext_index(r));
+            else *dst = 0.0;
           }
         }
       }
@@ -610,9 +599,10 @@ __global__ void __launch_bounds__(STileCfg<NB>::THREADS, STileCfg<NB>::MINB) ekf
       for (int c = warp; c < n_int; c += C::NW) {
         if (c == 3) continue;
         double* gc = gP + (size_t)ext_index(c) * ld;
-        for (int r = lane; r < n_int; r += 32) {
-          if (r == 3) continue;
-          gc[ext_index(r)] = T[pidx<NB>(r, c)];
+#pragma unroll
+        for (int k = 0; k < (C::NI + 31) / 32; ++k) {
+          const int r = lane + 32 * k;
+          if (r != 3 && r < n_int) gc[ext_index(r)] = T[pidx<NB>(r, c)];
         }
       }
       for (int r = tid; r < n_int; r += C::THREADS)
