@@ -38,7 +38,7 @@ struct DevBuf {
 };
 
 constexpr int kTimingPairs = 64;
-constexpr int kMaxChunks = 16;
+constexpr int kMaxChunks = 48;
 
 }  // namespace
 
@@ -805,13 +805,31 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
   const size_t wave = (size_t)(kern == 4 ? ekf_dtile_ctas_per_sm() * h->sm_count
                                : kern == 3 ? ekf_stile_ctas_per_sm(h->cfg.batch_kernel == EKF_BATCH_KERNEL_AUTO ? 1 : st.cap_lm) * h->sm_count
                                            : (kern == 2 ? 2 * h->sm_count : h->grid_cap));
-  size_t chunk = 2 * wave;
-  while ((F + chunk - 1) / chunk > (size_t)kMaxChunks) chunk += wave;
-  const int n_chunks = (int)((F + chunk - 1) / chunk);
+  // Chunk sizes in waves: 1, 1, 2, 2, 4, 4, 8, 8, 8, ... - the first copy (nothing to overlap it with) is
+  // short, later chunks are long enough to amortise their launch and the tail of their last wave.
+  size_t begin[kMaxChunks + 1];
+  int n_chunks = 0;
+  {
+    size_t cap_waves = 8;
+    for (;;) {
+      size_t f = 0, w = 1;
+      n_chunks = 0;
+      bool twice = false;
+      while (f < F && n_chunks < kMaxChunks) {
+        begin[n_chunks++] = f;
+        f += w * wave;
+        if (twice && w < cap_waves) w *= 2;
+        twice = !twice;
+      }
+      if (f >= F) break;
+      cap_waves *= 2;                                          // too many chunks for the event ring: longer ones
+    }
+    begin[n_chunks] = F;
+  }
   EKF_CK(h, cudaEventRecord(h->ev_done, h->stream));          // order after earlier work on the handle
   EKF_CK(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
   for (int c = 0; c < n_chunks; ++c) {
-    const size_t f0 = (size_t)c * chunk, nf = (f0 + chunk <= F) ? chunk : F - f0;
+    const size_t f0 = begin[c], nf = begin[c + 1] - begin[c];
     EKF_CK(h, cudaMemcpyAsync(h->records.p + f0 * T * L, records + f0 * T * L, nf * T * L * sizeof(double),
                               cudaMemcpyHostToDevice, h->s_in));
     EKF_CK(h, cudaEventRecord(h->ev_in[c], h->s_in));
