@@ -115,6 +115,9 @@ struct EkfLargeTmaArgs {
   // Consecutive sweeps walk the tiles in opposite directions: what one sweep touched last is what the next
   // touches first, so a covariance of about the size of the 126 MB L2 is largely served from it.
   int reverse;
+  // A column-sharded map (ekf_shard.cu): the tensor map covers columns [c0, c1) only; 0, 0 = the whole matrix.
+  int c0, c1;
+  int no_early_trigger;    // 1: dependents are released when the sweep ends (chains without events, ekf_pdl.cuh)
 };
 size_t ekf_large_tma_map_bytes();
 cudaError_t ekf_large_tma_encode(void* map_out, double* P, int cap_n, int ld);

@@ -31,11 +31,16 @@
 // decision of operation k+1 never overwrites what the sweep of operation k is reading.
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
+#include "ekf_la.cuh"
 #include "ekf_pdl.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
+// Side-stream kernels of a look-ahead run share the SMs with the persistent CTAs of the sweep, which leave
+// about a third of the register file free: small CTAs, so they are scheduled while the sweep is running
+// instead of after its first CTAs retire.
+constexpr int kSideThreads = 64;
 
 struct LargeSmall {
   PropSetup prop;
@@ -68,6 +73,7 @@ struct LargeArgs {
 
 __device__ __forceinline__ double* filt_P(const LargeArgs& a) { return a.st.P + (size_t)a.f * a.st.slab; }
 __device__ __forceinline__ double* filt_x(const LargeArgs& a) { return a.st.x + (size_t)a.f * a.st.xs; }
+__device__ __forceinline__ LaCache la_cache(const LargeArgs& a) { return LaCache{a.strip, a.diag, a.lds}; }
 
 // ---- propagate ---------------------------------------------------------------------------------
 // The 3x3 robot block lives in P (element (i,j) at P[i + j*ld]) or, in a look-ahead run, in the cache.
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) large_prop_strip(const LargeArgs a) 
   double* P = filt_P(a);
   const int ld = a.st.ld;
   const int n = 3 + 2 * a.st.nlm[a.f];
-  for (int j = 3 + blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
+  for (int j = 3 + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     if (LA) {                                   // the cache is the strip; P's copy is written back by la_store
       double* c = a.strip + j;
       double a0 = c[0], a1 = c[a.lds], a2 = c[2 * (size_t)a.lds];
@@ -128,14 +134,7 @@ __global__ void __launch_bounds__(kThreads) large_prop_strip(const LargeArgs a) 
 template <bool LA>
 __device__ __forceinline__ void load_gate_inputs(const LargeArgs& a, const double* P, int ld, int Li, double* p, double* pll) {
   if constexpr (LA) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      p[0 + 2 * j] = a.strip[(size_t)j * a.lds + Li];
-      p[1 + 2 * j] = a.strip[(size_t)j * a.lds + Li + 1];
-    }
-    const double2* d = reinterpret_cast<const double2*>(a.diag + 2 * (Li - 3));   // 4 doubles per landmark
-    const double2 d0 = d[0], d1 = d[1];
-    pll[0] = d0.x; pll[1] = d0.y; pll[2] = d1.x; pll[3] = d1.y;
+    la_gate_inputs(la_cache(a), Li, p, pll);
   } else {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) large_gate(const LargeArgs a, const 
   __syncthreads();
   double best = INFINITY;
   int best_idx = INT_MAX;
-  for (int lm = blockIdx.x * kThreads + threadIdx.x; lm < n_lm; lm += gridDim.x * kThreads) {
+  for (int lm = blockIdx.x * blockDim.x + threadIdx.x; lm < n_lm; lm += gridDim.x * blockDim.x) {
     const int Li = 3 + 2 * lm;
     double p[6], pll[4];
     load_gate_inputs<LA>(a, P, ld, Li, p, pll);
@@ -200,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
   ekf_pdl_entry();
   double val = INFINITY;
   int idx = INT_MAX;
-  for (int c = threadIdx.x; c < a.n_cand; c += kThreads) {
+  for (int c = threadIdx.x; c < a.n_cand; c += blockDim.x) {
     const double v = a.cand_val[c];
     const int i = a.cand_idx[c];
     if (v < val || (v == val && i < idx)) { val = v; idx = i; }
@@ -233,37 +232,7 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
     sm->sq1 = sqrt(fabs(d1));
     sm->m0 = d0 < 0 ? 1.0 : -1.0;
     sm->m1 = d1 < 0 ? 1.0 : -1.0;
-    if (LA) {
-      // pose rows i = 0..2 of large_gain's Old branch (same expressions), then the 3x3 block of the cache
-      // in the sweep's element form v <- fma(u_i1, w_j.y, v); v <- fma(u_i0, w_j.x, v)
-      const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = g.h3_0;
-      const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = g.h3_1;
-      const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
-      const double s00 = sm->Si[0], s10 = sm->Si[1], s01 = sm->Si[2], s11 = sm->Si[3];
-      double2 w[3];
-      for (int i = 0; i < 3; ++i) {
-        const double p0 = a.strip[i], p1 = a.strip[a.lds + i], p2 = a.strip[2 * (size_t)a.lds + i];
-        const double pa = a.strip[(size_t)i * a.lds + opt_i], pb = a.strip[(size_t)i * a.lds + opt_i + 1];
-        const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
-        const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
-        const double B0 = pa * c00 + pb * c10;
-        const double B1 = pa * c01 + pb * c11;
-        const double M0 = A0 + B0, M1 = A1 + B1;
-        const double K0 = M0 * s00 + M1 * s10;
-        const double K1 = M0 * s01 + M1 * s11;
-        x[i] = x[i] + (K0 * g.res0 + K1 * g.res1);
-        w[i] = make_double2(sm->sq0 * fma(l, K1, K0), sm->sq1 * K1);
-        sm->Wp[i] = w[i];
-      }
-      for (int j = 0; j < 3; ++j)
-        for (int i = 0; i < 3; ++i) {
-          double* e = prr_elem<true>(a, nullptr, i, j);
-          double v = *e;
-          v = fma(sm->m1 * w[i].y, w[j].y, v);
-          v = fma(sm->m0 * w[i].x, w[j].x, v);
-          *e = v;
-        }
-    }
+    if (LA) la_pose_rows_old(la_cache(a), sm, x, opt_i);   // the pose rows of large_gain's Old branch + the cache's 3x3 block
   } else if (decision == EKF_DEC_NEW) {
     if (n_lm >= a.st.cap_lm) {
       decision = EKF_DEC_DROPPED;
@@ -293,24 +262,7 @@ __global__ void __launch_bounds__(kThreads) large_decide(const LargeArgs a, cons
       sm->nl[0] = nl0; sm->nl[1] = nl1;
       sm->h3n[0] = h30; sm->h3n[1] = h31;
       index = n;
-      if (LA) {
-        // pose rows of large_gain's New branch, the new diagonal block, the new state entries and the
-        // landmark count - all cache / vector writes, nothing the running sweep touches
-        const double ct00 = u.Ct[0], ct10 = u.Ct[1], ct01 = u.Ct[2], ct11 = u.Ct[3];
-        for (int i = 0; i < 3; ++i) {
-          const double q0 = -a.strip[i], q1 = -a.strip[a.lds + i], q2 = -a.strip[2 * (size_t)a.lds + i];
-          const double t0 = (q0 * HR[0] + q1 * HR[2]) + q2 * h30;
-          const double t1 = (q0 * HR[1] + q1 * HR[3]) + q2 * h31;
-          a.strip[(size_t)i * a.lds + n] = t0 * ct00 + t1 * ct10;
-          a.strip[(size_t)i * a.lds + n + 1] = t0 * ct01 + t1 * ct11;
-        }
-        const double off = 0.5 * (sm->PLL[2] + sm->PLL[1]);
-        double* d = a.diag + 4 * (size_t)n_lm;
-        d[0] = sm->PLL[0]; d[1] = off; d[2] = off; d[3] = sm->PLL[3];
-        x[n] = nl0;
-        x[n + 1] = nl1;
-        a.st.nlm[a.f] = n_lm + 1;
-      }
+      if (LA) la_pose_rows_new(la_cache(a), sm, x, a.st.nlm + a.f, n, n_lm);
     }
   }
   sm->decision = decision;
@@ -394,67 +346,39 @@ __global__ void __launch_bounds__(kThreads) large_gain_la(const LargeArgs a) {
   if (decision != EKF_DEC_OLD && decision != EKF_DEC_NEW) return;
   double* P = filt_P(a);
   double* x = filt_x(a);
+  const LaCache c = la_cache(a);
   const int ld = a.st.ld, n = sm->n, n_lm = sm->n_lm, lds = a.lds;
-  const UpdateSetup& u = sm->upd;
   const int lm0 = blockIdx.x * kThreads + threadIdx.x, stride = gridDim.x * kThreads;
   if (decision == EKF_DEC_OLD) {
     const int opt_i = sm->opt_i;
-    const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = sm->h3[0];
-    const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = sm->h3[1];
-    const double c00 = u.Ct[0], c10 = u.Ct[2], c01 = u.Ct[1], c11 = u.Ct[3];
-    const double s00 = sm->Si[0], s10 = sm->Si[1], s01 = sm->Si[2], s11 = sm->Si[3];
-    const double r0 = sm->res[0], r1 = sm->res[1], l = sm->l, sq0 = sm->sq0, sq1 = sm->sq1;
+    const LaGain q = la_gain_coef(sm);
     const double m0 = sm->m0, m1 = sm->m1;
-    const double2 wp0 = sm->Wp[0], wp1 = sm->Wp[1], wp2 = sm->Wp[2];
+    const double2 wp[3] = {sm->Wp[0], sm->Wp[1], sm->Wp[2]};
     if (lm0 == 0) {
-      a.W[0] = wp0; a.W[1] = wp1; a.W[2] = wp2;
+      a.W[0] = wp[0]; a.W[1] = wp[1]; a.W[2] = wp[2];
       a.W[n] = make_double2(0.0, 0.0);            // pad row of the double2 sweep (n is odd)
     }
     for (int lm = lm0; lm < n_lm; lm += stride) {
-      const int Li = 3 + 2 * lm;
       double2 w[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int i = Li + e;
-        const double p0 = a.strip[i], p1 = a.strip[lds + i], p2 = a.strip[2 * (size_t)lds + i];
-        const double pa = P[i + (size_t)opt_i * ld], pb = P[i + (size_t)(opt_i + 1) * ld];
-        const double A0 = (p0 * h00 + p1 * h01) + p2 * h02;
-        const double A1 = (p0 * h10 + p1 * h11) + p2 * h12;
-        const double B0 = pa * c00 + pb * c10;
-        const double B1 = pa * c01 + pb * c11;
-        const double M0 = A0 + B0, M1 = A1 + B1;
-        const double K0 = M0 * s00 + M1 * s10;      // Update.cpp:186
-        const double K1 = M0 * s01 + M1 * s11;
-        x[i] = x[i] + (K0 * r0 + K1 * r1);          // :187
-        w[e] = make_double2(sq0 * fma(l, K1, K0), sq1 * K1);
+        const int i = 3 + 2 * lm + e;
+        double dx;
+        la_gain_row(q, a.strip[i], a.strip[lds + i], a.strip[2 * (size_t)lds + i], P[i + (size_t)opt_i * ld],
+                    P[i + (size_t)(opt_i + 1) * ld], dx, w[e]);
+        x[i] = x[i] + dx;                           // Update.cpp:187
         a.W[i] = w[e];
-        const double u0 = m0 * w[e].x, u1 = m1 * w[e].y;
-        a.strip[i] = fma(u0, wp0.x, fma(u1, wp0.y, p0));
-        a.strip[lds + i] = fma(u0, wp1.x, fma(u1, wp1.y, p1));
-        a.strip[2 * (size_t)lds + i] = fma(u0, wp2.x, fma(u1, wp2.y, p2));
       }
-      double2* d = reinterpret_cast<double2*>(a.diag + 4 * (size_t)lm);
-      double2 d0 = d[0], d1 = d[1];               // (Li,Li) (Li+1,Li) | (Li,Li+1) (Li+1,Li+1)
-      const double ua0 = m0 * w[0].x, ua1 = m1 * w[0].y, ub0 = m0 * w[1].x, ub1 = m1 * w[1].y;
-      d0.x = fma(ua0, w[0].x, fma(ua1, w[0].y, d0.x));
-      d0.y = fma(ub0, w[0].x, fma(ub1, w[0].y, d0.y));
-      d1.x = fma(ua0, w[1].x, fma(ua1, w[1].y, d1.x));
-      d1.y = fma(ub0, w[1].x, fma(ub1, w[1].y, d1.y));
-      d[0] = d0; d[1] = d1;
+      la_cache_landmark(c, lm, w, wp, m0, m1);
     }
   } else {
-    const double h00 = u.mCt[0], h01 = u.mCt[2], h02 = sm->h3n[0];
-    const double h10 = u.mCt[1], h11 = u.mCt[3], h12 = sm->h3n[1];
-    const double ct00 = u.Ct[0], ct10 = u.Ct[1], ct01 = u.Ct[2], ct11 = u.Ct[3];
+    const LaNew q = la_new_coef(sm);
     for (int lm = lm0; lm < n_lm; lm += stride) {   // Update.cpp:169,175-176 (rows 0..2: large_decide<true>)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int i = 3 + 2 * lm + e;
-        const double q0 = -a.strip[i], q1 = -a.strip[lds + i], q2 = -a.strip[2 * (size_t)lds + i];
-        const double t0 = (q0 * h00 + q1 * h01) + q2 * h02;
-        const double t1 = (q0 * h10 + q1 * h11) + q2 * h12;
-        const double o0 = t0 * ct00 + t1 * ct10;
-        const double o1 = t0 * ct01 + t1 * ct11;
+        double o0, o1;
+        la_new_row(q, a.strip[i], a.strip[lds + i], a.strip[2 * (size_t)lds + i], o0, o1);
         P[i + (size_t)n * ld] = o0;
         P[i + (size_t)(n + 1) * ld] = o1;
         P[n + (size_t)i * ld] = o0;
@@ -546,21 +470,7 @@ __global__ void large_compass_setup(const LargeArgs a, const double* z, const do
   sm->csq = sqrt(fabs(S));
   sm->cm0 = S < 0 ? 1.0 : -1.0;
   sm->n = 3 + 2 * a.st.nlm[a.f];
-  if (LA) {   // pose rows of large_compass_gain and the 3x3 block of the cache (rank-1 sweep form)
-    const double res = sm->cres, invS = 1 / sm->cS, sq = sm->csq;
-    double2 w[3];
-    for (int i = 0; i < 3; ++i) {
-      const double Ki = invS * a.strip[2 * (size_t)a.lds + i];
-      x[i] = x[i] + res * Ki;
-      w[i] = make_double2(sq * Ki, 0.0);
-      sm->Wp[i] = w[i];
-    }
-    for (int j = 0; j < 3; ++j)
-      for (int i = 0; i < 3; ++i) {
-        double* e = prr_elem<true>(a, nullptr, i, j);
-        *e = fma(sm->cm0 * w[i].x, w[j].x, *e);
-      }
-  }
+  if (LA) la_compass_pose_rows(la_cache(a), sm, x);   // pose rows of large_compass_gain + the cache's 3x3 block
 }
 
 __global__ void __launch_bounds__(kThreads) large_compass_gain(const LargeArgs a) {
@@ -584,9 +494,8 @@ __global__ void __launch_bounds__(kThreads) large_compass_gain_la(const LargeArg
   ekf_pdl_entry();
   const LargeSmall* sm = a.sm;
   double* x = filt_x(a);
-  const int n = sm->n, n_lm = (n - 3) / 2, lds = a.lds;
-  const double res = sm->cres, invS = 1 / sm->cS, sq = sm->csq, m0 = sm->cm0;
-  const double w0 = sm->Wp[0].x, w1 = sm->Wp[1].x, w2 = sm->Wp[2].x;
+  const LaCache c = la_cache(a);
+  const int n = sm->n, n_lm = (n - 3) / 2;
   const int lm0 = blockIdx.x * kThreads + threadIdx.x;
   if (lm0 == 0) {
     a.W[0] = sm->Wp[0]; a.W[1] = sm->Wp[1]; a.W[2] = sm->Wp[2];
@@ -594,27 +503,9 @@ __global__ void __launch_bounds__(kThreads) large_compass_gain_la(const LargeArg
   }
   for (int lm = lm0; lm < n_lm; lm += gridDim.x * kThreads) {
     double wv[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int i = 3 + 2 * lm + e;
-      const double p0 = a.strip[i], p1 = a.strip[lds + i], p2 = a.strip[2 * (size_t)lds + i];
-      const double Ki = invS * p2;
-      x[i] = x[i] + res * Ki;
-      wv[e] = sq * Ki;
-      a.W[i] = make_double2(wv[e], 0.0);
-      const double u0 = m0 * wv[e];
-      a.strip[i] = fma(u0, w0, p0);
-      a.strip[lds + i] = fma(u0, w1, p1);
-      a.strip[2 * (size_t)lds + i] = fma(u0, w2, p2);
-    }
-    double2* d = reinterpret_cast<double2*>(a.diag + 4 * (size_t)lm);
-    double2 d0 = d[0], d1 = d[1];
-    const double ua = m0 * wv[0], ub = m0 * wv[1];
-    d0.x = fma(ua, wv[0], d0.x);
-    d0.y = fma(ub, wv[0], d0.y);
-    d1.x = fma(ua, wv[1], d1.x);
-    d1.y = fma(ub, wv[1], d1.y);
-    d[0] = d0; d[1] = d1;
+    la_compass_landmark(c, sm, x, lm, wv);
+    a.W[3 + 2 * lm] = make_double2(wv[0], 0.0);
+    a.W[4 + 2 * lm] = make_double2(wv[1], 0.0);
   }
 }
 
@@ -767,6 +658,12 @@ static cudaError_t large_run_lookahead(const EkfState& st, int filter, const Ekf
   LargeSmall* const small0 = a.sm;
   auto ctl = [&](long op) { return reinterpret_cast<LargeSmall*>(reinterpret_cast<unsigned char*>(small0) + (op & 1) * kSmallStride); };
   const int rg = row_grid(st, wk), gg = gate_grid(st, wk);   // one landmark per thread: the gating grid fits both
+  auto side_grid = [&](int count) {
+    int g = (count + kSideThreads - 1) / kSideThreads;
+    if (g > wk.grid) g = wk.grid;
+    return g < 1 ? 1 : g;
+  };
+  const int sg_rows = side_grid(st.cap_n), sg_lm = side_grid(st.cap_lm);
   large_la_load<<<rg, kThreads, 0, A>>>(a);
   cudaEventRecord(wk.ev_a, A);
   cudaStreamWaitEvent(B, wk.ev_a, 0);
@@ -783,7 +680,7 @@ static cudaError_t large_run_lookahead(const EkfState& st, int filter, const Ekf
     const double* rec = io.records + ((size_t)filter * io.T + t) * io.L;
     a.sm = ctl(op);
     side(large_prop_setup<true>, 1, 32, a, rec + 0, rec + 1, rec + 2);
-    side(large_prop_strip<true>, rg, kThreads, a);
+    side(large_prop_strip<true>, sg_rows, kSideThreads, a);
     if (has_compass[t]) {
       side(large_compass_setup<true>, 1, 32, a, rec + 3, rec + 4);
       cudaEventRecord(wk.ev_b, B);
@@ -799,9 +696,9 @@ static cudaError_t large_run_lookahead(const EkfState& st, int filter, const Ekf
     for (int m = 0; m < io.M; ++m) {
       if (m >= n_z[t]) continue;
       const size_t oi = ((size_t)filter * io.T + t) * io.M + m;
-      a.n_cand = gg;
-      side(large_gate<true>, gg, kThreads, a, rec + 8 + 6 * m, 0);
-      side(large_decide<true>, 1, kThreads, a, rec + 8 + 6 * m, io.decision ? io.decision + oi : nullptr,
+      a.n_cand = sg_lm;
+      side(large_gate<true>, sg_lm, kSideThreads, a, rec + 8 + 6 * m, 0);
+      side(large_decide<true>, 1, kSideThreads, a, rec + 8 + 6 * m, io.decision ? io.decision + oi : nullptr,
            io.index ? io.index + oi : nullptr, io.mahal ? io.mahal + oi : nullptr);
       cudaEventRecord(wk.ev_b, B);
       cudaStreamWaitEvent(A, wk.ev_b, 0);

@@ -10,6 +10,7 @@
 // inside a boundary tile but beyond n see W = 0 (unchanged), out-of-bounds parts are zero-filled
 // on load and clipped on store.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "ekf_cta.cuh"
@@ -75,6 +76,8 @@ struct TmaParams {
   int* nlm_out;            // for the New bookkeeping the plain kernel also does (null: look-ahead run, done earlier)
   const int* n_lm;
   int reverse;             // walk the tiles back to front (see ekf_large_tma_downdate)
+  int c0, c1;              // the tensor map covers columns [c0, c1) of the matrix (a shard's slab; 0, INT_MAX: all)
+  int early_trigger;       // programmatic dependent launch: let the next kernel be scheduled at once
 };
 
 template <int RANK, bool COMPASS>
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
   double* tiles = reinterpret_cast<double*>(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * kTileBytes);
   uint64_t* done = full + STAGES;
-  ekf_pdl_entry();
+  if (q.early_trigger) ekf_pdl_trigger();
+  ekf_pdl_wait();
   if (!COMPASS) {
     const int dec = *q.decision;
     if (dec != EKF_DEC_OLD) {
@@ -93,7 +97,9 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
   }
   const int n = *q.n_dim;
   const double m0 = *q.m0, m1 = RANK == 2 ? *q.m1 : 0.0;
-  const int n_rt = (n + TR - 1) / TR, n_ct = (n + TC - 1) / TC;
+  const int ncols = (q.c1 < n ? q.c1 : n) - q.c0;     // live columns of this slab
+  if (ncols <= 0) return;
+  const int n_rt = (n + TR - 1) / TR, n_ct = (ncols + TC - 1) / TC;
   const long n_tiles = (long)n_rt * n_ct;
   const long first = blockIdx.x;
   const long count = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParam
     const double u0 = m0 * wi.x, u1 = m1 * wi.y;
     double2 wj[TC];
 #pragma unroll
-    for (int c = 0; c < TC; ++c) wj[c] = W[ct * TC + c];
+    for (int c = 0; c < TC; ++c) wj[c] = W[q.c0 + ct * TC + c];
     mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
     double* t = tiles + (size_t)s * TR * TC + tid;
 #pragma unroll
@@ -206,6 +212,10 @@ cudaError_t ekf_large_tma_prepare(int sm_count, int* grid) {
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   if (per_sm > 3) per_sm = 3;
+  if (const char* env = getenv("EKF_TMA_CTAS_PER_SM")) {     // experiment hook
+    const int v = atoi(env);
+    if (v >= 1 && v < per_sm) per_sm = v;
+  }
   *grid = per_sm * sm_count;
   return cudaSuccess;
 }
@@ -214,6 +224,8 @@ cudaError_t ekf_large_tma_downdate(const EkfLargeTmaArgs& t, const void* map, in
   TmaParams q;
   q.decision = t.decision; q.n_dim = t.n_dim; q.m0 = t.m0; q.m1 = t.m1; q.W = t.W; q.nlm_out = t.nlm_out; q.n_lm = t.n_lm;
   q.reverse = t.reverse;
+  q.c0 = t.c0; q.c1 = t.c1 > t.c0 ? t.c1 : 0x7fffffff;
+  q.early_trigger = !t.no_early_trigger;
   const size_t bytes = (size_t)STAGES * kTileBytes + 2 * STAGES * sizeof(uint64_t);
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(map);
   if (compass) return ekf_launch_pdl(large_downdate_tma<1, true>, grid, kThreadsTma, bytes, s, q, *m);

@@ -16,6 +16,13 @@ __device__ __forceinline__ void ekf_pdl_entry() {
   asm volatile("griddepcontrol.wait;" ::: "memory");                // everything in front has completed
 }
 
+// The two halves on their own. A kernel that may spin on a flag (ekf_shard.cu) must not let its dependents
+// be scheduled before the spin is over - CTAs parked in griddepcontrol.wait hold registers that the kernel
+// it is waiting for may need on the same device - and a long sweep in a chain without events does not
+// trigger early either, or the whole future chain queues up behind it and competes for its SM slots.
+__device__ __forceinline__ void ekf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ekf_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t ekf_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -26,6 +26,13 @@
 // An exchange step is stream-ordered: every shard records an event after its producer kernel and
 // every other shard's stream waits on it; no kernel ever spins on a peer.
 //
+// ekf_sharded_run additionally overlaps the O(n) chain with the sweep (look-ahead, ekf_la.cuh): every
+// shard keeps a full replica of the O(n) cache (robot columns + diagonal blocks), so gating and the
+// decision need NO exchange at all and run on a side stream while the sweep of the previous operation is
+// still streaming the shard's slab; what stays between two sweeps is the gain kernel (own rows, peer
+// stores of W and x) and its exchange. Compass updates need no exchange either (every input is in the
+// cache). See run_shard_thread_la.
+//
 // Arithmetic is ekf_small.cuh (the reference's operation order) and the bit-symmetric two-fma
 // downdate of ekf_cta.cuh, i.e. results are bit-identical to the single-GPU regime B and
 // independent of the shard count.
@@ -41,12 +48,14 @@
 
 #include "ekf_cta.cuh"
 #include "ekf_internal.h"
+#include "ekf_la.cuh"
 #include "ekf_pdl.cuh"
 #include "ekf_slam_b200.h"
 
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kSideThreads = 64;   // side-stream kernels of a look-ahead run: small CTAs that fit beside the sweep's
 constexpr int kMaxShards = EKF_SHARDED_MAX_SHARDS;
 constexpr int kCB = 8;
 
@@ -62,6 +71,7 @@ struct ShardSmall {
   double nl[2], PLL[4], h3n[2];
   double cres, cS, csq, cm0;
   double PRR[9];   // replica of P(0:3,0:3), column-major
+  double2 Wp[3];   // look-ahead runs: downdate vectors of the pose rows (computed with the decision)
 };
 
 // A shard's best gating candidate plus everything the decision needs about it, so that no shard
@@ -90,6 +100,21 @@ struct ShardArgs {
   double* x_all[kMaxShards];
   ShardCand* xcand_all[kMaxShards];
   EkfConst k;
+  // look-ahead runs: full replica of the O(n) cache (ekf_la.cuh) and every shard's copy of it (filled once
+  // per run by peer stores); la = 1 tells the sweep that the New bookkeeping is done elsewhere
+  double* strip;
+  double* diag;
+  int lds, la;
+  double* strip_all[kMaxShards];
+  double* diag_all[kMaxShards];
+  // flags of a look-ahead run, in this shard's memory and written by every shard (peer stores):
+  // flags_d[t] = number of operations whose decision shard t has finished, flags_g[t] = ... whose gain
+  // kernel (W / x stores into every shard) shard t has finished. gain_count: last-CTA counter of the gain kernels.
+  unsigned* flags_d;
+  unsigned* flags_g;
+  unsigned* gain_count;
+  unsigned* flags_d_all[kMaxShards];
+  unsigned* flags_g_all[kMaxShards];
 };
 
 __device__ __forceinline__ double* scol(const ShardArgs& a, int j) { return a.P + (size_t)(j - a.c0) * a.ld; }
@@ -361,11 +386,12 @@ __global__ void __launch_bounds__(kThreads) shard_gain(const ShardArgs a) {
 // ---- the HBM-bound kernel over the own columns ---------------------------------------------------
 template <int RANK, bool COMPASS>
 __global__ void __launch_bounds__(kThreads) shard_downdate(const ShardArgs a) {
-  ekf_pdl_entry();
+  if (!a.la) ekf_pdl_trigger();   // look-ahead runs: no early trigger, or the whole future chain queues up behind the sweep (ekf_pdl.cuh)
+  ekf_pdl_wait();
   ShardSmall* sm = a.sm;
   const int n = sm->n;
   if (!COMPASS && sm->decision != EKF_DEC_OLD) {
-    if (sm->decision == EKF_DEC_NEW) {
+    if (sm->decision == EKF_DEC_NEW && !a.la) {
       if (a.c0 <= n && n < a.c1) {                    // owner of the two new columns: rows from W
         double* ca = scol(a, n);
         double* cb = scol(a, n + 1);
@@ -388,7 +414,7 @@ __global__ void __launch_bounds__(kThreads) shard_downdate(const ShardArgs a) {
   }
   const double m0 = COMPASS ? sm->cm0 : sm->m0, m1 = COMPASS ? 0.0 : sm->m1;
   const double2* __restrict__ W = a.W;
-  if (blockIdx.x == 0 && threadIdx.x < 9) {           // the replica of P_RR, same two fma
+  if (!a.la && blockIdx.x == 0 && threadIdx.x < 9) {  // the replica of P_RR, same two fma
     const int i = threadIdx.x % 3, j = threadIdx.x / 3;
     const double2 wi = W[i], wj = W[j];
     double v = sm->PRR[i + 3 * j];
@@ -471,6 +497,359 @@ __global__ void __launch_bounds__(kThreads) shard_compass_gain(const ShardArgs a
   if (g0 == 0) a.W[n] = make_double2(0.0, 0.0);
 }
 
+// ---- look-ahead runs (ekf_la.cuh): kernels that work on the replicated O(n) cache ------------------
+__device__ __forceinline__ LaCache shard_cache(const ShardArgs& a) { return LaCache{a.strip, a.diag, a.lds}; }
+
+// Exchange steps of a look-ahead run are flags, not events: a producer kernel stores its data, fences, and
+// its last CTA stores the operation count into the flag word it owns on every shard; a consumer polls the
+// flag words in its OWN memory. Compared with cudaStreamWaitEvent on G-1 peer events this costs one poll
+// instead of G-1 serially processed stream waits, and the host threads need no barrier. Polls are bounded
+// (about two seconds): on expiry status bit 2 is set and the run continues, so a lost peer cannot hang a GPU.
+__device__ __forceinline__ unsigned long long shard_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void shard_poll(const unsigned* flags, int lo, int hi, unsigned want, int* status) {
+  const unsigned long long t0 = shard_now_ns();
+  for (int t = lo; t < hi; ++t) {
+    const volatile unsigned* f = flags + t;
+    while (*f < want) {
+      if (shard_now_ns() - t0 > 2000000000ull) { atomicOr(status, 2); break; }
+    }
+  }
+  __threadfence_system();
+}
+// Called by every thread of the kernel after its stores; the last CTA to arrive publishes `done` in the
+// flag word of this shard on shards [lo, hi).
+__device__ __forceinline__ void shard_signal_last(const ShardArgs& a, unsigned* const* flag_all, int lo, int hi, unsigned done) {
+  __shared__ bool last_cta;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = atomicAdd(a.gain_count, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last_cta || threadIdx.x != 0) return;
+  *a.gain_count = 0;
+  __threadfence_system();
+  for (int t = lo; t < hi; ++t) *const_cast<volatile unsigned*>(flag_all[t] + a.shard) = done;
+}
+// One warp that waits for flag words [lo, hi) (side stream, and the main stream between gain and sweep).
+__global__ void shard_poll_kernel(const ShardArgs a, int which, int lo, int hi, unsigned want) {
+  ekf_pdl_wait();          // dependents are released by the exit, i.e. after the poll (ekf_pdl.cuh)
+  if (threadIdx.x == 0) shard_poll(which ? a.flags_g : a.flags_d, lo, hi, want, a.status);
+}
+
+// Start of a run: every shard stores the cache entries of its own columns into every shard's cache.
+__global__ void __launch_bounds__(kThreads) shard_la_load(const ShardArgs a) {
+  const int n = 3 + 2 * a.nlm[0];
+  const int ihi = a.c1 < n ? a.c1 : n;
+  for (int i = a.c0 + blockIdx.x * kThreads + threadIdx.x; i < ihi; i += gridDim.x * kThreads) {
+    const double* c = scol(a, i);
+    const double v0 = c[0], v1 = c[1], v2 = c[2];          // P(r, i) == P(i, r)
+    double d0 = 0.0, d1 = 0.0;
+    int slot = 0;
+    if (i >= 3) {                                           // column e of the landmark's 2x2 block
+      const int Li = 3 + 2 * ((i - 3) >> 1), e = (i - 3) & 1;
+      d0 = c[Li];
+      d1 = c[Li + 1];
+      slot = 2 * (Li - 3) + 2 * e;
+    }
+    for (int t = 0; t < a.n_shards; ++t) {
+      double* st = a.strip_all[t];
+      st[i] = v0;
+      st[a.lds + i] = v1;
+      st[2 * (size_t)a.lds + i] = v2;
+      if (i >= 3) { a.diag_all[t][slot] = d0; a.diag_all[t][slot + 1] = d1; }
+    }
+  }
+}
+// End of a run: the robot rows of the own columns, shard 0's robot columns and the P_RR replica of the
+// per-call surface from the cache (the rest of the slab is current).
+__global__ void __launch_bounds__(kThreads) shard_la_store(const ShardArgs a) {
+  const int n = 3 + 2 * a.nlm[0];
+  const int g0 = blockIdx.x * kThreads + threadIdx.x, stride = gridDim.x * kThreads;
+  const int ihi = a.c1 < n ? a.c1 : n;
+  for (int i = a.c0 + g0; i < ihi; i += stride) {
+    double* c = scol(a, i);
+    c[0] = a.strip[i];
+    c[1] = a.strip[a.lds + i];
+    c[2] = a.strip[2 * (size_t)a.lds + i];
+  }
+  if (a.c0 == 0)
+    for (int j = 3 + g0; j < n; j += stride) {
+      a.P[j] = a.strip[j];
+      a.P[j + (size_t)a.ld] = a.strip[a.lds + j];
+      a.P[j + (size_t)2 * a.ld] = a.strip[2 * (size_t)a.lds + j];
+    }
+  if (g0 < 9) a.sm->PRR[g0] = *la_prr(shard_cache(a), g0 % 3, g0 / 3);
+}
+
+__global__ void shard_prop_setup_la(const ShardArgs a, const double* in3) {
+  ekf_pdl_entry();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* x = a.x;
+  const LaCache c = shard_cache(a);
+  PropSetup p;
+  ekf_build_prop(p, in3[0], in3[1], in3[2], x[2], a.k);
+  a.sm->prop = p;
+  const double xm0 = p.v * p.c, xm1 = p.v * p.s, xm2 = p.w;   // Propagate.cpp:33-37
+  x[0] = x[0] + p.dt * xm0;
+  x[1] = x[1] + p.dt * xm1;
+  x[2] = x[2] + p.dt * xm2;
+  double PRR[9];
+  for (int q = 0; q < 9; ++q) PRR[q] = *la_prr(c, q % 3, q / 3);
+  ekf_prop_prr(p, PRR);
+  for (int q = 0; q < 9; ++q) *la_prr(c, q % 3, q / 3) = PRR[q];
+}
+
+__global__ void __launch_bounds__(kThreads) shard_prop_strip_la(const ShardArgs a) {
+  ekf_pdl_entry();
+  __shared__ PropSetup ps;
+  if (threadIdx.x == 0) ps = a.sm->prop;
+  __syncthreads();
+  const int n = 3 + 2 * a.nlm[0];
+  for (int j = 3 + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double* c = a.strip + j;
+    double a0 = c[0], a1 = c[a.lds], a2 = c[2 * (size_t)a.lds];
+    ekf_prop_col(ps, a0, a1, a2);
+    c[0] = a0; c[a.lds] = a1; c[2 * (size_t)a.lds] = a2;
+  }
+}
+
+// Gating over ALL landmarks on every shard (the cache is replicated): no exchange, per-CTA candidates.
+__global__ void __launch_bounds__(kThreads) shard_gate_la(const ShardArgs a, const double* zr) {
+  ekf_pdl_entry();
+  __shared__ CtaScratch sc;
+  const double* x = a.x;
+  const LaCache c = shard_cache(a);
+  const int n_lm = a.nlm[0];
+  if (threadIdx.x == 0) {
+    double PRR[9];
+    for (int q = 0; q < 9; ++q) PRR[q] = *la_prr(c, q % 3, q / 3);
+    UpdateSetup u;
+    ekf_build_setup(u, x[2], x[0], x[1], PRR, zr[0], zr[1], zr + 2);
+    sc.upd = u;
+    if (blockIdx.x == 0) a.sm->upd = u;
+  }
+  __syncthreads();
+  double best = INFINITY;
+  int best_idx = INT_MAX;
+  for (int lm = blockIdx.x * blockDim.x + threadIdx.x; lm < n_lm; lm += gridDim.x * blockDim.x) {
+    const int Li = 3 + 2 * lm;
+    double p[6], pll[4];
+    la_gate_inputs(c, Li, p, pll);
+    GateResult g;
+    ekf_gate_landmark(sc.upd, x[Li], x[Li + 1], p, pll, a.k.cond_max, g);
+    const bool valid = !g.skip && (a.k.mahal_init > g.d2);
+    if (valid && g.d2 < best) { best = g.d2; best_idx = Li; }
+  }
+  cta_argmin(best, best_idx, &sc);
+  if (threadIdx.x == 0) {
+    a.cand_val[blockIdx.x] = best;
+    a.cand_idx[blockIdx.x] = best_idx;
+  }
+}
+
+// Decision on every shard, identically; the decision thread also finishes the pose rows (ekf_la.cuh).
+__global__ void __launch_bounds__(kThreads) shard_decide_la(const ShardArgs a, const double* zr, int n_cand, unsigned done,
+                                                           int* out_decision, int* out_index, double* out_mahal) {
+  ekf_pdl_entry();
+  __shared__ CtaScratch sc;
+  double val = INFINITY;
+  int idx = INT_MAX;
+  for (int q = threadIdx.x; q < n_cand; q += blockDim.x) {
+    const double v = a.cand_val[q];
+    const int i = a.cand_idx[q];
+    if (v < val || (v == val && i < idx)) { val = v; idx = i; }
+  }
+  cta_argmin(val, idx, &sc);
+  if (threadIdx.x != 0) return;
+  ShardSmall* sm = a.sm;
+  double* x = a.x;
+  const LaCache c = shard_cache(a);
+  const int n_lm = a.nlm[0];
+  const int n = 3 + 2 * n_lm;
+  const int opt_i = (idx == INT_MAX) ? 0 : idx;
+  const double mahal = (idx == INT_MAX) ? a.k.mahal_init : val;
+  int decision = ekf_decide(opt_i, mahal, a.k);
+  int index = opt_i;
+  const UpdateSetup& u = sm->upd;
+  if (decision == EKF_DEC_OLD) {
+    double p[6], pll[4];
+    la_gate_inputs(c, opt_i, p, pll);
+    GateResult g;
+    ekf_gate_landmark(u, x[opt_i], x[opt_i + 1], p, pll, a.k.cond_max, g);   // same bits as the gating pass
+    sm->res[0] = g.res0; sm->res[1] = g.res1;
+    for (int q = 0; q < 4; ++q) sm->S[q] = g.S[q];
+    sm->h3[0] = g.h3_0; sm->h3[1] = g.h3_1;
+    ekf_inv2(g.S, sm->Si);
+    const double d0 = g.S[0], l = g.S[1] / g.S[0], d1 = g.S[3] - l * g.S[1];
+    sm->l = l;
+    sm->sq0 = sqrt(fabs(d0));
+    sm->sq1 = sqrt(fabs(d1));
+    sm->m0 = d0 < 0 ? 1.0 : -1.0;
+    sm->m1 = d1 < 0 ? 1.0 : -1.0;
+    la_pose_rows_old(c, sm, x, opt_i);
+  } else if (decision == EKF_DEC_NEW) {
+    if (n_lm >= a.cap_lm) {
+      decision = EKF_DEC_DROPPED;
+      index = -1;
+      a.status[0] |= 1;
+    } else {
+      const double cs = u.c, sn = u.s, z0 = zr[0], z1 = zr[1];
+      const double Cz0 = cs * z0 + (-sn) * z1, Cz1 = sn * z0 + cs * z1;   // Update.cpp:155
+      const double nl0 = u.x0 + Cz0, nl1 = u.x1 + Cz1;
+      const double dn0 = nl0 - u.x0, dn1 = nl1 - u.x1;
+      const double h30 = u.mCtJ[0] * dn0 + u.mCtJ[2] * dn1;
+      const double h31 = u.mCtJ[1] * dn0 + u.mCtJ[3] * dn1;
+      const double HR[6] = {u.mCt[0], u.mCt[1], u.mCt[2], u.mCt[3], h30, h31};
+      double a1[6], t1[4], in[4], b1[4];
+      for (int j = 0; j < 3; ++j) {
+        a1[0 + 2 * j] = u.q[0 + 2 * j] + h30 * u.PRR[2 + 3 * j];
+        a1[1 + 2 * j] = u.q[1 + 2 * j] + h31 * u.PRR[2 + 3 * j];
+      }
+      for (int j = 0; j < 2; ++j)
+        for (int i = 0; i < 2; ++i) t1[i + 2 * j] = (a1[i] * HR[j] + a1[i + 2] * HR[j + 2]) + a1[i + 4] * HR[j + 4];
+      for (int q = 0; q < 4; ++q) in[q] = t1[q] + u.R[q];
+      const double Cm[4] = {u.Ct[0], u.Ct[2], u.Ct[1], u.Ct[3]};
+      for (int j = 0; j < 2; ++j)
+        for (int i = 0; i < 2; ++i) b1[i + 2 * j] = Cm[i] * in[0 + 2 * j] + Cm[i + 2] * in[1 + 2 * j];
+      for (int j = 0; j < 2; ++j)       // Update.cpp:168
+        for (int i = 0; i < 2; ++i) sm->PLL[i + 2 * j] = b1[i] * u.Ct[0 + 2 * j] + b1[i + 2] * u.Ct[1 + 2 * j];
+      sm->nl[0] = nl0; sm->nl[1] = nl1;
+      sm->h3n[0] = h30; sm->h3n[1] = h31;
+      index = n;
+      la_pose_rows_new(c, sm, x, a.nlm, n, n_lm);
+    }
+  }
+  sm->decision = decision;
+  sm->opt_i = opt_i;
+  sm->n = n;
+  sm->n_lm = n_lm;
+  sm->mahal = mahal;
+  if (out_decision) *out_decision = decision;
+  if (out_index) *out_index = index;
+  if (out_mahal) *out_mahal = mahal;
+  // this shard's gating has read x: every shard's gain kernel may now overwrite its entries of it
+  __threadfence_system();
+  for (int t = 0; t < a.n_shards; ++t) *const_cast<volatile unsigned*>(a.flags_d_all[t] + a.shard) = done;
+}
+
+// The one kernel left between two sweeps: gain rows / state / downdate vectors of the OWN rows, stored
+// into every shard (exchange 2). Row i of P at the gain columns: the robot part from the cache, the
+// Opt_i part from the shard's own column i (rows Opt_i, Opt_i+1 - swept, never stale).
+__global__ void __launch_bounds__(kThreads) shard_gain_la(const ShardArgs a, unsigned done) {
+  ekf_pdl_wait();
+  if (threadIdx.x == 0) shard_poll(a.flags_d, 0, a.n_shards, done, a.status);   // every shard's decision is made
+  __syncthreads();
+  const ShardSmall* sm = a.sm;
+  const int decision = sm->decision;
+  ekf_pdl_trigger();       // the spin is over: the one-warp poll kernel behind may be scheduled
+  const int n = sm->n, lds = a.lds;
+  const int g0 = blockIdx.x * kThreads + threadIdx.x, stride = gridDim.x * kThreads;
+  const int ilo = a.c0 < 3 ? 3 : a.c0, ihi = a.c1 < n ? a.c1 : n;
+  if (decision == EKF_DEC_OLD) {
+    const int opt_i = sm->opt_i;
+    const LaGain q = la_gain_coef(sm);
+    if (g0 == 0) {                                  // pose rows (every shard has them) and the pad row, locally
+      a.W[0] = sm->Wp[0]; a.W[1] = sm->Wp[1]; a.W[2] = sm->Wp[2];
+      a.W[n] = make_double2(0.0, 0.0);
+    }
+    for (int i = ilo + g0; i < ihi; i += stride) {
+      const double* col = scol(a, i);
+      double dx;
+      double2 w;
+      la_gain_row(q, a.strip[i], a.strip[lds + i], a.strip[2 * (size_t)lds + i], col[opt_i], col[opt_i + 1], dx, w);
+      const double xi = a.x[i] + dx;                // Update.cpp:187
+      for (int t = 0; t < a.n_shards; ++t) {        // the all-gather: peer stores over NVLink
+        a.x_all[t][i] = xi;
+        a.W_all[t][i] = w;
+      }
+    }
+  } else if (decision == EKF_DEC_NEW) {
+    // Update.cpp:169,175-176. Every input is in the replicated cache, so nothing is exchanged: each shard
+    // writes rows n, n+1 of its own columns, the owner of the new columns writes them whole.
+    const LaNew q = la_new_coef(sm);
+    for (int i = ilo + g0; i < ihi; i += stride) {
+      double o0, o1;
+      la_new_row(q, a.strip[i], a.strip[lds + i], a.strip[2 * (size_t)lds + i], o0, o1);
+      double* col = scol(a, i);
+      col[n] = o0;
+      col[n + 1] = o1;
+    }
+    if (a.c0 <= n && n < a.c1) {
+      double* ca = scol(a, n);
+      double* cb = scol(a, n + 1);
+      for (int i = 3 + g0; i < n; i += stride) {
+        double o0, o1;
+        la_new_row(q, a.strip[i], a.strip[lds + i], a.strip[2 * (size_t)lds + i], o0, o1);
+        ca[i] = o0;
+        cb[i] = o1;
+      }
+      if (g0 == 0) {
+        const double off = 0.5 * (sm->PLL[2] + sm->PLL[1]);
+        ca[n] = sm->PLL[0];
+        ca[n + 1] = off;
+        cb[n] = off;
+        cb[n + 1] = sm->PLL[3];
+      }
+    }
+  }
+  shard_signal_last(a, a.flags_g_all, 0, a.n_shards, done);   // exchange 2
+}
+
+// After exchange 2 every shard holds the full W: bring the whole cache replica up to date (O(n)).
+__global__ void __launch_bounds__(kThreads) shard_cache_update(const ShardArgs a) {
+  ekf_pdl_entry();
+  const ShardSmall* sm = a.sm;
+  if (sm->decision != EKF_DEC_OLD) return;
+  const LaCache c = shard_cache(a);
+  const int n_lm = sm->n_lm;
+  const double m0 = sm->m0, m1 = sm->m1;
+  const double2 wp[3] = {sm->Wp[0], sm->Wp[1], sm->Wp[2]};
+  for (int lm = blockIdx.x * blockDim.x + threadIdx.x; lm < n_lm; lm += gridDim.x * blockDim.x) {
+    const double2 w[2] = {a.W[3 + 2 * lm], a.W[4 + 2 * lm]};
+    la_cache_landmark(c, lm, w, wp, m0, m1);
+  }
+}
+
+__global__ void shard_compass_setup_la(const ShardArgs a, const double* zR, unsigned done) {
+  ekf_pdl_entry();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ShardSmall* sm = a.sm;
+  const LaCache c = shard_cache(a);
+  sm->cres = ekf_compass_residual(a.x[2], zR[0], a.k);
+  const double S = *la_prr(c, 2, 2) + zR[1];
+  sm->cS = S;
+  sm->csq = sqrt(fabs(S));
+  sm->cm0 = S < 0 ? 1.0 : -1.0;
+  sm->n = 3 + 2 * a.nlm[0];
+  la_compass_pose_rows(c, sm, a.x);
+  __threadfence();
+  *const_cast<volatile unsigned*>(a.flags_d + a.shard) = done;    // local: the compass path has no cross-shard step
+}
+// Compass gain: every input is in the replicated cache, every shard computes all rows - no exchange.
+__global__ void __launch_bounds__(kThreads) shard_compass_gain_la(const ShardArgs a, unsigned done) {
+  ekf_pdl_wait();          // no early trigger: the sweep behind must not occupy the device while this spins
+  if (threadIdx.x == 0) shard_poll(a.flags_d, a.shard, a.shard + 1, done, a.status);
+  __syncthreads();
+  const ShardSmall* sm = a.sm;
+  const LaCache c = shard_cache(a);
+  const int n = sm->n, n_lm = (n - 3) / 2;
+  const int lm0 = blockIdx.x * kThreads + threadIdx.x;
+  if (lm0 == 0) {
+    a.W[0] = sm->Wp[0]; a.W[1] = sm->Wp[1]; a.W[2] = sm->Wp[2];
+    a.W[n] = make_double2(0.0, 0.0);
+  }
+  for (int lm = lm0; lm < n_lm; lm += gridDim.x * kThreads) {
+    double wv[2];
+    la_compass_landmark(c, sm, a.x, lm, wv);
+    a.W[3 + 2 * lm] = make_double2(wv[0], 0.0);
+    a.W[4 + 2 * lm] = make_double2(wv[1], 0.0);
+  }
+  shard_signal_last(a, a.flags_g_all, a.shard, a.shard + 1, done);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 struct Shard {
   int device = 0, sms = 0, grid = 0;
@@ -491,6 +870,19 @@ struct Shard {
   size_t rec_cap = 0;
   double* stage = nullptr;   // per-call inputs [64 + 6*EKF_MAX_MEAS]
   ShardArgs args;
+  // look-ahead runs: side stream, the O(n) cache replica, the second W buffer, and the argument blocks of
+  // even / odd operations (control block and W buffer alternate)
+  cudaStream_t side = nullptr;
+  cudaEvent_t evc = nullptr, evl = nullptr;     // main -> side at the start of a run, side -> main at its end
+  double* strip = nullptr;
+  double* diag = nullptr;
+  double2* W2 = nullptr;
+  unsigned* flags = nullptr;   // [kMaxShards] decisions, [kMaxShards] gains, [1] last-CTA counter
+  // look-ahead runs sweep the slab with the TMA-staged kernel of ekf_large_tma.cu (its five-warp CTAs leave
+  // room on every SM sub-partition for the side stream's warps; the 8-warp double2 sweep does not)
+  std::vector<unsigned char> tmap;
+  int tma_grid = 0;
+  ShardArgs args_la[2];
 };
 
 std::string g_shard_create_error;
@@ -502,7 +894,9 @@ struct ekf_sharded_s {
   Shard sh[kMaxShards];
   EkfConst k{};
   ekf_config cfg{};
-  int cap_lm = 0, cap_n = 0, ld = 0;
+  int cap_lm = 0, cap_n = 0, ld = 0, lds = 0;
+  int lookahead = 1;         // ekf_sharded_run overlaps the O(n) chain with the sweep (EKF_SHARD_LOOKAHEAD=0: off)
+  int use_tma = 1;           // look-ahead runs: TMA-staged sweep (EKF_LARGE_TMA=0: the plain double2 sweep)
   size_t w_count = 0;
   // outputs of the fused run (device of shard 0)
   int* t_dec = nullptr;
@@ -733,6 +1127,143 @@ void run_shard_thread(RunCtx& c, int s) {
   TH_CK(cudaGetLastError());
   TH_CK(cudaStreamSynchronize(sh.stream));
 }
+
+// Look-ahead run (header comment, ekf_la.cuh). Per shard two streams: A = sh.stream carries what has to sit
+// between two sweeps, B = sh.side the chain that works on the cache replica alone. Operation k (1-based count
+// `done`), landmark update:
+//   B: gating k, decision k (-> flags_d = done on every shard)
+//   A: gain k (waits for flags_d of EVERY shard: a peer's gain overwrites x entries its gating reads;
+//              stores W / x into every shard, -> flags_g = done on every shard)
+//   A: poll (flags_g of every shard: W and x complete), sweep k
+//   B: poll (the same), cache update k, then propagate / gating of operation k+1 ...
+// A compass operation has no cross-shard step (own flags only). Operations alternate between two control
+// blocks and two W buffers, so the chain of operation k+1 never touches what the sweep of operation k reads.
+// The two streams and the G host threads are coupled by the flags alone: no event, no host barrier per step.
+// (Tools that serialise kernel execution cannot run this: EKF_SHARD_LOOKAHEAD=0 selects the event chain.)
+void run_shard_thread_la(RunCtx& c, int s) {
+  ekf_sharded m = c.m;
+  Shard& sh = m->sh[s];
+  const int G = m->G;
+  cudaStream_t A = sh.stream, B = sh.side;
+  int xk = 0;
+  auto xchg = [&]() {                       // full exchange on the main streams (start / end of the run)
+    if (G == 1) return;
+    TH_CK(cudaEventRecord(sh.evx[xk & 1], A));
+    c.bar.wait();
+    for (int t = 0; t < G; ++t)
+      if (t != s) TH_CK(cudaStreamWaitEvent(A, m->sh[t].evx[xk & 1], 0));
+    ++xk;
+  };
+  TH_CK(cudaSetDevice(sh.device));
+  TH_CK(cudaMemsetAsync(sh.flags, 0, (2 * kMaxShards + 1) * sizeof(unsigned), A));
+  xchg();                                   // uploads and resets of every shard precede the first peer store
+  if (s == 0) TH_CK(cudaEventRecord(m->t0, A));
+  const int n_all = m->cap_n, lm_all = m->cap_lm;
+  const int g_own = rows_grid(sh, sh.c1 - sh.c0), g_n = rows_grid(sh, n_all), g_lm = rows_grid(sh, lm_all);
+  auto side_grid = [&](int count) {
+    int g = (count + kSideThreads - 1) / kSideThreads;
+    if (g > sh.grid) g = sh.grid;
+    return g < 1 ? 1 : g;
+  };
+  const int sg_n = side_grid(n_all), sg_lm = side_grid(lm_all);
+  shard_la_load<<<g_own, kThreads, 0, A>>>(sh.args_la[0]);
+  xchg();                                   // every shard's cache replica is complete
+  TH_CK(cudaEventRecord(sh.evc, A));
+  TH_CK(cudaStreamWaitEvent(B, sh.evc, 0));
+  unsigned op = 0;
+  bool timed = false;
+  auto sweep = [&](const ShardArgs& a, bool compass) {
+    if (m->use_tma) {
+      EkfLargeTmaArgs q{&a.sm->decision, &a.sm->n, &a.sm->m0, &a.sm->m1, a.W, nullptr, &a.sm->n_lm, 0, sh.c0, sh.c1, 1};
+      if (compass) q = EkfLargeTmaArgs{nullptr, &a.sm->n, &a.sm->cm0, &a.sm->cm0, a.W, nullptr, nullptr, 0, sh.c0, sh.c1, 1};
+      TH_CK(ekf_large_tma_downdate(q, sh.tmap.data(), sh.tma_grid, compass, A));
+    } else if (compass) {
+      ekf_launch_pdl(shard_downdate<1, true>, sh.grid, kThreads, 0, A, a);
+    } else {
+      ekf_launch_pdl(shard_downdate<2, false>, sh.grid, kThreads, 0, A, a);
+    }
+  };
+  // EKF_SHARD_TIMELINE=1: CUDA events around every kernel of two mid-run steps of shard 0, printed to stderr
+  const bool dbg = s == 0 && getenv("EKF_SHARD_TIMELINE") && atoi(getenv("EKF_SHARD_TIMELINE")) != 0;
+  std::vector<cudaEvent_t> dev;
+  std::vector<std::string> dname;
+  auto mark = [&](cudaStream_t st, const char* name, int t) {
+    if (!dbg || t < c.T / 2 || t >= c.T / 2 + 2) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    dev.push_back(e);
+    dname.push_back(std::string(st == A ? "A " : "B ") + name + " t=" + std::to_string(t));
+  };
+  for (int t = 0; t < c.T; ++t) {
+    const double* hrec = c.hrec + (size_t)t * c.L;
+    const double* rec = sh.records + (size_t)t * c.L;
+    mark(B, "before prop_setup", t);
+    ekf_launch_pdl(shard_prop_setup_la, 1, 32, 0, B, sh.args_la[op & 1], rec);
+    mark(B, "after prop_setup", t);
+    ekf_launch_pdl(shard_prop_strip_la, sg_n, kSideThreads, 0, B, sh.args_la[op & 1]);
+    if (hrec[6] != 0.0) {
+      const ShardArgs& a = sh.args_la[op & 1];
+      const unsigned done = op + 1;
+      ekf_launch_pdl(shard_compass_setup_la, 1, 32, 0, B, a, rec + 3, done);
+      ekf_launch_pdl(shard_compass_gain_la, g_lm, kThreads, 0, A, a, done);
+      sweep(a, true);
+      ekf_launch_pdl(shard_poll_kernel, 1, 32, 0, B, a, 1, s, s + 1, done);   // own compass gain has updated cache and x
+      ++op;
+    }
+    int nz = (int)hrec[5];
+    nz = nz < 0 ? 0 : nz > c.max_meas ? c.max_meas : nz;
+    for (int q = 0; q < nz; ++q) {
+      const ShardArgs& a = sh.args_la[op & 1];
+      const unsigned done = op + 1;
+      const double* zr = rec + 8 + 6 * q;
+      const size_t oi = (size_t)t * c.M + q;
+      const bool out = s == 0 && c.want_trace;
+      mark(B, "after prop_strip", t);
+      ekf_launch_pdl(shard_gate_la, sg_lm, kSideThreads, 0, B, a, zr);
+      mark(B, "after gate", t);
+      ekf_launch_pdl(shard_decide_la, 1, kSideThreads, 0, B, a, zr, sg_lm, done, out ? m->t_dec + oi : nullptr,
+                     out ? m->t_idx + oi : nullptr, out ? m->t_mah + oi : nullptr);
+      mark(B, "after decide", t);
+      mark(A, "before gain", t);
+      ekf_launch_pdl(shard_gain_la, g_own, kThreads, 0, A, a, done);
+      mark(A, "after gain", t);
+      ekf_launch_pdl(shard_poll_kernel, 1, 32, 0, A, a, 1, 0, G, done);
+      mark(A, "after poll", t);
+      const bool time_this = s == 0 && !timed && t >= c.T / 2;   // one downdate sampled mid-run on shard 0
+      if (time_this) TH_CK(cudaEventRecord(m->d0, A));
+      sweep(a, false);
+      if (time_this) TH_CK(cudaEventRecord(m->d1, A));
+      timed = timed || time_this;
+      mark(A, "after sweep", t);
+      ekf_launch_pdl(shard_poll_kernel, 1, 32, 0, B, a, 1, 0, G, done);
+      mark(B, "after poll", t);
+      ekf_launch_pdl(shard_cache_update, sg_lm, kSideThreads, 0, B, a);
+      mark(B, "after cache_update", t);
+      ++op;
+    }
+    if (s == 0 && c.want_pose)               // the pose is written by side-stream kernels only
+      TH_CK(cudaMemcpyAsync(m->t_pose + (size_t)t * 3, sh.x, 3 * sizeof(double), cudaMemcpyDeviceToDevice, B));
+  }
+  TH_CK(cudaEventRecord(sh.evl, B));
+  TH_CK(cudaStreamWaitEvent(A, sh.evl, 0));
+  shard_la_store<<<g_n, kThreads, 0, A>>>(sh.args);
+  xchg();
+  if (s == 0) {
+    TH_CK(cudaEventRecord(m->t1, A));
+    c.timed = timed;
+  }
+  TH_CK(cudaGetLastError());
+  TH_CK(cudaStreamSynchronize(B));
+  TH_CK(cudaStreamSynchronize(A));
+  for (size_t i = 0; i < dev.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, dev[0], dev[i]);
+    fprintf(stderr, "[shard timeline] %9.1f us  %s\n", ms * 1e3, dname[i].c_str());
+    if (i) cudaEventDestroy(dev[i]);
+  }
+  if (!dev.empty()) cudaEventDestroy(dev[0]);
+}
 #undef TH_CK
 
 // Copy the same small host block into every shard's staging buffer at offset off.
@@ -782,7 +1313,14 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
   m->cap_lm = max_landmarks;
   m->cap_n = 3 + 2 * max_landmarks;
   m->ld = (m->cap_n + 15) & ~15;
-  m->w_count = (size_t)m->cap_n + 16;
+  m->w_count = (size_t)m->cap_n + 512;     // zero tail: boundary tiles of the TMA sweep read past n
+  m->lds = (m->cap_n + 2 + 7) & ~7;
+  {
+    const char* env = getenv("EKF_SHARD_LOOKAHEAD");
+    m->lookahead = env ? (atoi(env) != 0) : 1;
+    env = getenv("EKF_LARGE_TMA");
+    m->use_tma = env ? (atoi(env) != 0) : 1;
+  }
   auto bail = [&](int code, const std::string& msg) {
     g_shard_create_error = msg;
     ekf_sharded_destroy(m);
@@ -817,8 +1355,29 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
     SH_ALLOC(sh.x, (size_t)(m->cap_n + 1) * sizeof(double));
     SH_ALLOC(sh.nlm, sizeof(int));
     SH_ALLOC(sh.status, sizeof(int));
-    SH_ALLOC(sh.sm, sizeof(ShardSmall));
+    SH_ALLOC(sh.sm, 2 * sizeof(ShardSmall));
     SH_ALLOC(sh.W, m->w_count * sizeof(double2));
+    SH_ALLOC(sh.W2, m->w_count * sizeof(double2));
+    SH_ALLOC(sh.strip, 3 * (size_t)m->lds * sizeof(double));
+    SH_ALLOC(sh.diag, 4 * ((size_t)max_landmarks + 1) * sizeof(double));
+    SH_ALLOC(sh.flags, (2 * kMaxShards + 1) * sizeof(unsigned));
+    if (m->use_tma) {
+      sh.tmap.resize(ekf_large_tma_map_bytes());
+      if (ekf_large_tma_prepare(sh.sms, &sh.tma_grid) != cudaSuccess ||
+          ekf_large_tma_encode(sh.tmap.data(), sh.P, sh.c1 - sh.c0, m->ld) != cudaSuccess)
+        return bail(EKF_ERR_CUDA, "the tensor map of the TMA-staged covariance sweep could not be encoded "
+                                  "(set EKF_LARGE_TMA=0 to run the plain double2 sweep instead)");
+      // Two CTAs per SM, not three: measured, the sweep is no slower (HBM-bound either way), and with three the
+      // side stream's kernels are not scheduled until two thirds of the sweep are over (profiles/r02_shard_timeline.txt)
+      if (sh.tma_grid > 2 * sh.sms) sh.tma_grid = 2 * sh.sms;
+    }
+    {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if ((e = cudaStreamCreateWithPriority(&sh.side, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+      for (cudaEvent_t* ev : {&sh.evc, &sh.evl})
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    }
     SH_ALLOC(sh.cand_val, (size_t)sh.grid * sizeof(double));
     SH_ALLOC(sh.cand_idx, (size_t)sh.grid * sizeof(int));
     SH_ALLOC(sh.xcand, (size_t)kMaxShards * sizeof(ShardCand));
@@ -846,6 +1405,24 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
       a.W_all[t] = o.W; a.x_all[t] = o.x; a.xcand_all[t] = o.xcand;
     }
     a.k = m->k;
+    a.strip = sh.strip; a.diag = sh.diag; a.lds = m->lds; a.la = 0;
+    a.flags_d = sh.flags; a.flags_g = sh.flags + kMaxShards; a.gain_count = sh.flags + 2 * kMaxShards;
+    for (int t = 0; t < kMaxShards; ++t) {
+      const Shard& o = m->sh[t < n_shards ? t : 0];
+      a.strip_all[t] = o.strip; a.diag_all[t] = o.diag;
+      a.flags_d_all[t] = o.flags; a.flags_g_all[t] = o.flags + kMaxShards;
+    }
+    for (int b = 0; b < 2; ++b) {
+      ShardArgs& l = sh.args_la[b];
+      l = a;
+      l.la = 1;
+      l.sm = sh.sm + b;
+      l.W = b ? sh.W2 : sh.W;
+      for (int t = 0; t < kMaxShards; ++t) {
+        const Shard& o = m->sh[t < n_shards ? t : 0];
+        l.W_all[t] = b ? o.W2 : o.W;
+      }
+    }
   }
   int rc = ekf_sharded_reset(m);
   if (rc != EKF_OK) {
@@ -868,6 +1445,10 @@ int ekf_sharded_destroy(ekf_sharded m) {
     cudaSetDevice(sh.device);
     cudaFree(sh.P); cudaFree(sh.x); cudaFree(sh.nlm); cudaFree(sh.status); cudaFree(sh.sm); cudaFree(sh.W);
     cudaFree(sh.cand_val); cudaFree(sh.cand_idx); cudaFree(sh.xcand); cudaFree(sh.records); cudaFree(sh.stage);
+    cudaFree(sh.W2); cudaFree(sh.strip); cudaFree(sh.diag); cudaFree(sh.flags);
+    for (cudaEvent_t ev : {sh.evc, sh.evl})
+      if (ev) cudaEventDestroy(ev);
+    if (sh.side) { cudaStreamSynchronize(sh.side); cudaStreamDestroy(sh.side); }
     if (s == 0) {
       cudaFree(m->t_dec); cudaFree(m->t_idx); cudaFree(m->t_mah); cudaFree(m->t_pose);
       cudaFree(m->o_dec); cudaFree(m->o_idx); cudaFree(m->o_mah);
@@ -891,8 +1472,9 @@ int ekf_sharded_reset(ekf_sharded m) {
     SH_CK(m, cudaMemsetAsync(sh.x, 0, (size_t)(m->cap_n + 1) * sizeof(double), sh.stream));
     SH_CK(m, cudaMemsetAsync(sh.nlm, 0, sizeof(int), sh.stream));
     SH_CK(m, cudaMemsetAsync(sh.status, 0, sizeof(int), sh.stream));
-    SH_CK(m, cudaMemsetAsync(sh.sm, 0, sizeof(ShardSmall), sh.stream));
+    SH_CK(m, cudaMemsetAsync(sh.sm, 0, 2 * sizeof(ShardSmall), sh.stream));
     SH_CK(m, cudaMemsetAsync(sh.W, 0, m->w_count * sizeof(double2), sh.stream));
+    SH_CK(m, cudaMemsetAsync(sh.W2, 0, m->w_count * sizeof(double2), sh.stream));
     SH_CK(m, cudaMemsetAsync(sh.xcand, 0, (size_t)kMaxShards * sizeof(ShardCand), sh.stream));
   }
   return sync_all(m);
@@ -1089,25 +1671,32 @@ int ekf_sharded_run(ekf_sharded m, int n_steps, int max_meas, const double* reco
   c.want_pose = want_pose;
   c.bar.n = m->G;
   for (int s = 0; s < kMaxShards; ++s) c.err[s] = cudaSuccess;
+  void (*body)(RunCtx&, int) = m->lookahead ? run_shard_thread_la : run_shard_thread;
   if (m->G == 1) {
-    run_shard_thread(c, 0);
+    body(c, 0);
   } else {
     std::vector<std::thread> th;
-    for (int s = 1; s < m->G; ++s) th.emplace_back(run_shard_thread, std::ref(c), s);
-    run_shard_thread(c, 0);
+    for (int s = 1; s < m->G; ++s) th.emplace_back(body, std::ref(c), s);
+    body(c, 0);
     for (auto& t : th) t.join();
   }
-  long long per_step = 0;
+  long long per_step = m->lookahead ? 2 : 0;      // look-ahead: cache load / store
   for (int t = 0; t < T; ++t) {
     const double* hrec = records + (size_t)t * L;
     int nz = (int)hrec[5];
     nz = nz < 0 ? 0 : nz > max_meas ? max_meas : nz;
-    per_step += 2 + (hrec[6] != 0.0 ? 3 : 0) + 4 * nz;
+    per_step += 2 + (hrec[6] != 0.0 ? (m->lookahead ? 4 : 3) : 0) + (m->lookahead ? 7 : 4) * nz;
   }
   m->launches += per_step * m->G;
   for (int s = 0; s < m->G; ++s)
     if (c.err[s] != cudaSuccess)
       return sfail(m, EKF_ERR_CUDA, "ekf_sharded_run, shard " + std::to_string(s) + ": " + cudaGetErrorString(c.err[s]));
+  for (int s = 0; s < m->G; ++s) {
+    int st = 0;
+    SH_CK(m, cudaSetDevice(m->sh[s].device));
+    SH_CK(m, cudaMemcpy(&st, m->sh[s].status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st & 2) return sfail(m, EKF_ERR_CUDA, "ekf_sharded_run: shard " + std::to_string(s) + " gave up waiting for a peer (exchange flag not set within 2 s); the map state is undefined");
+  }
   SH_CK(m, cudaSetDevice(s0.device));
   SH_CK(m, cudaEventElapsedTime(&m->last_ms, m->t0, m->t1));
   m->last_downdate_ms = 0.f;
@@ -1131,6 +1720,8 @@ int ekf_sharded_last_run_ms(ekf_sharded m, float* run_ms, float* downdate_ms) {
 }
 
 long long ekf_sharded_kernel_launches(ekf_sharded m) { return m ? m->launches : 0; }
+
+int ekf_sharded_run_mode(ekf_sharded m) { return !m ? -1 : !m->lookahead ? 0 : m->use_tma ? 2 : 1; }
 
 const char* ekf_sharded_last_error(ekf_sharded m) { return m ? m->err.c_str() : g_shard_create_error.c_str(); }
 

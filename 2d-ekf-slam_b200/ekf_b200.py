@@ -164,6 +164,7 @@ def core_lib():
         L.ekf_sharded_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.ekf_sharded_kernel_launches.argtypes = [H]
         L.ekf_sharded_kernel_launches.restype = C.c_longlong
+        L.ekf_sharded_run_mode.argtypes = [H]
         L.ekf_sharded_last_error.argtypes = [H]
         L.ekf_sharded_last_error.restype = C.c_char_p
         _core = L
@@ -565,6 +566,12 @@ class ShardedMap:
 
     def kernel_launches(self):
         return int(self.L.ekf_sharded_kernel_launches(self.h))
+
+    def run_mode(self):
+        """What ekf_sharded_run does: the sweep kernel it launches and whether the O(n) chain is overlapped."""
+        return {2: "large_downdate_tma<2,0> on the shard's slab, look-ahead run",
+                1: "shard_downdate<2>, look-ahead run",
+                0: "shard_downdate<2>, event chain"}[int(self.L.ekf_sharded_run_mode(self.h))]
 
 
 HOUGH_THETA, HOUGH_RADIUS, HOUGH_PEAKS = 180, 1601, 200

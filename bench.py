@@ -318,6 +318,7 @@ def sharded_map_leg(ekf, n_lm, steps, hbm_peak, devices):
     rec = syn.generate(1, steps)
     x0, P0 = injected_state(syn.world(), seed=n_lm)
     sm = ekf.ShardedMap(devices, n_lm + 2)
+    mode = sm.run_mode()
     sm.set_state(x0, P0, symmetric=True)
     sm.run(rec, 1, trace=True)                 # warm-up pass
     sm.set_state(x0, P0, symmetric=True)
@@ -338,7 +339,7 @@ def sharded_map_leg(ekf, n_lm, steps, hbm_peak, devices):
             "shards": G, "old_updates": n_old, "steps": steps, "ms_per_step": ms / steps,
             "update_steps_per_s": steps / (ms * 1e-3), "gpu_launches": int(l1 - l0),
             "step_gbs_aggregate": alg * n_old / (ms * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "shard_downdate<2> (shard 0, one launch sampled mid-run)",
+            "roofline": {"bound": "hbm", "kernel": mode + " (shard 0, one launch sampled mid-run)",
                          "achieved": alg0 / (dms * 1e-3) / 1e9 if dms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (alg0 / (dms * 1e-3) / 1e9) / hbm_peak if dms > 0 else None, "traffic": None,
                          "algorithmic_bytes_per_launch": alg0, "avg_kernel_ms": dms, "launches_timed": 1 if dms > 0 else 0}}

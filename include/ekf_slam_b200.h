@@ -233,8 +233,16 @@ int ekf_sharded_update(ekf_sharded m, int n_z, const double* z, const double* R,
                        double* mahal);
 int ekf_sharded_update_compass(ekf_sharded m, double z, double R);
 /* slam.cpp:127-182 for n_steps step records of the one map (layout above, F = 1): all kernels and
- * exchange steps of all steps are enqueued without a host round trip. */
+ * exchange steps of all steps are enqueued without a host round trip. By default the run overlaps
+ * propagate / gating / decision of the next operation with the covariance sweep of the current one
+ * (a replicated O(n) cache on a side stream per shard, exchange steps as flags in peer memory, the
+ * TMA-staged sweep); EKF_SHARD_LOOKAHEAD=0 in the environment at ekf_sharded_create() selects the chain
+ * with an event exchange per gating pass and per gain (also what the per-call functions above run). Same
+ * results either way. */
 int ekf_sharded_run(ekf_sharded m, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out);
+/* How ekf_sharded_run sweeps the covariance: 2 = look-ahead run with the TMA-staged sweep, 1 = look-ahead
+ * run with the plain double2 sweep (EKF_LARGE_TMA=0), 0 = event chain with the plain sweep. */
+int ekf_sharded_run_mode(ekf_sharded m);
 /* Device time of the last ekf_sharded_run (events on shard 0 bracketing cross-shard barriers) and
  * of one covariance downdate sampled mid-run on shard 0 (0 if none ran). */
 int ekf_sharded_last_run_ms(ekf_sharded m, float* run_ms, float* downdate_ms);

@@ -77,6 +77,47 @@ def test_sharded_equals_single_gpu_large_regime_bitwise(ekf):
     sm.close()
 
 
+def test_sharded_lookahead_run_is_bit_identical_to_the_exchange_per_gating_chain(ekf, monkeypatch):
+    """ekf_sharded_run() overlaps gating / decision with the previous sweep through a replicated O(n) cache
+    (no gating exchange, compass without any exchange, second stream per shard). Same bits as the chain with
+    an exchange per gating pass (EKF_SHARD_LOOKAHEAD=0), on every shard layout, for runs cut into several
+    calls (cache loaded and written back each time) and for per-call operations that follow a run."""
+    N, T, cap, M = 26, 300, 30, 2
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=M, compass_every=7)
+    lap = syn.generate(1, T)
+    rec = np.ascontiguousarray(np.concatenate([lap, lap], axis=1))
+    ref = None
+    for devs in _device_lists(ekf):
+        for la in ("0", "1"):
+            monkeypatch.setenv("EKF_SHARD_LOOKAHEAD", la)
+            sm = ekf.ShardedMap(devs, cap)
+            parts, lo = [], 0
+            for hi in (1, 10, 250, 2 * T):
+                parts.append(sm.run(np.ascontiguousarray(rec[:, lo:hi]), M, trace=True, pose_trace=True))
+                lo = hi
+            got = {k: np.concatenate([q[k] for q in parts], axis=1) for k in ("decision", "index", "mahal", "pose_trace")}
+            r = rec[0, 5]
+            sm.propagate(r[0], r[1], r[2])
+            sm.update_compass(r[3] + 0.01, 0.02)
+            dec, idx, mah = sm.update(r[8:10].reshape(1, 2), r[10:14].reshape(1, 4))
+            x, P = sm.get_state()
+            reps = [sm.get_replica(s) for s in range(len(devs))]
+            sm.close()
+            assert parts[-1]["final_nlm"][0] == N
+            for nl, xs, prr in reps:
+                assert 3 + 2 * nl == len(x) and np.array_equal(xs, x) and np.array_equal(prr, P[:3, :3])
+            assert np.array_equal(P, P.T)
+            cur = (got, x, P, dec, idx, mah)
+            if ref is None:
+                ref = cur
+                continue
+            what = "devices %s, look-ahead %s" % (devs, la)
+            for k in got:
+                assert np.array_equal(got[k], ref[0][k]), what + ": " + k
+            for u, v in zip(cur[1:], ref[1:]):
+                assert np.array_equal(u, v), what
+
+
 def test_sharded_percall_surface(ekf, oracle):
     """doPropagation / doUpdateCompass / doUpdate(n_z = 3, gating bound frozen at call entry) one
     call at a time on 3 shards."""
