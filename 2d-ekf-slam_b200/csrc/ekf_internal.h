@@ -118,10 +118,11 @@ struct EkfLargeTmaArgs {
   // A column-sharded map (ekf_shard.cu): the tensor map covers columns [c0, c1) only; 0, 0 = the whole matrix.
   int c0, c1;
   int no_early_trigger;    // 1: dependents are released when the sweep ends (chains without events, ekf_pdl.cuh)
+  int slim;                // 1: the four-stage instance (leaves shared memory for kernels running beside the sweep)
 };
 size_t ekf_large_tma_map_bytes();
 cudaError_t ekf_large_tma_encode(void* map_out, double* P, int cap_n, int ld);
-cudaError_t ekf_large_tma_prepare(int sm_count, int* grid);
+cudaError_t ekf_large_tma_prepare(int sm_count, int* grid, bool slim = false);
 cudaError_t ekf_large_tma_downdate(const EkfLargeTmaArgs& t, const void* map, int grid, bool compass, cudaStream_t s);
 
 // Optional CUDA-event sampling of the dominant (downdate) kernel: every `every`-th launch is

@@ -19,7 +19,12 @@
 
 namespace {
 
-constexpr int TR = 128, TC = 16, STAGES = 4;
+constexpr int TR = 128, TC = 16;
+// Ring depth. Two CTAs per SM in both uses. One GPU: six stages (192 KB of tiles in flight per SM - measured
+// best from N = 1,000 to 10,000). A shard of a look-ahead run: four stages (128 KB per SM) - with more than
+// that in shared memory the side stream's small kernels are not scheduled beside the sweep until most of it
+// is over (profiles/r02_shard_timeline.txt).
+constexpr int kStagesWide = 6, kStagesSlim = 4;
 constexpr int kConsumers = 128, kThreadsTma = kConsumers + 32;
 constexpr uint32_t kTileBytes = TR * TC * sizeof(double);
 
@@ -80,7 +85,7 @@ struct TmaParams {
   int early_trigger;       // programmatic dependent launch: let the next kernel be scheduled at once
 };
 
-template <int RANK, bool COMPASS>
+template <int RANK, bool COMPASS, int STAGES>
 __global__ void __launch_bounds__(kThreadsTma) large_downdate_tma(const TmaParams q, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* tiles = reinterpret_cast<double*>(smem);
@@ -201,23 +206,30 @@ cudaError_t ekf_large_tma_encode(void* map_out, double* P, int cap_n, int ld) {
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t ekf_large_tma_prepare(int sm_count, int* grid) {
+template <int STAGES>
+static cudaError_t tma_prepare(int sm_count, int* grid) {
   const size_t bytes = (size_t)STAGES * kTileBytes + 2 * STAGES * sizeof(uint64_t);
-  cudaError_t e = cudaFuncSetAttribute(large_downdate_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaError_t e = cudaFuncSetAttribute(large_downdate_tma<2, false, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(large_downdate_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  e = cudaFuncSetAttribute(large_downdate_tma<1, true, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, large_downdate_tma<2, false>, kThreadsTma, bytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, large_downdate_tma<2, false, STAGES>, kThreadsTma, bytes);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  if (per_sm > 3) per_sm = 3;
-  if (const char* env = getenv("EKF_TMA_CTAS_PER_SM")) {     // experiment hook
-    const int v = atoi(env);
-    if (v >= 1 && v < per_sm) per_sm = v;
-  }
+  if (per_sm > 2) per_sm = 2;
   *grid = per_sm * sm_count;
   return cudaSuccess;
+}
+cudaError_t ekf_large_tma_prepare(int sm_count, int* grid, bool slim) {
+  return slim ? tma_prepare<kStagesSlim>(sm_count, grid) : tma_prepare<kStagesWide>(sm_count, grid);
+}
+
+template <int STAGES>
+static cudaError_t tma_launch(const TmaParams& q, const CUtensorMap* m, int grid, bool compass, cudaStream_t s) {
+  const size_t bytes = (size_t)STAGES * kTileBytes + 2 * STAGES * sizeof(uint64_t);
+  if (compass) return ekf_launch_pdl(large_downdate_tma<1, true, STAGES>, grid, kThreadsTma, bytes, s, q, *m);
+  return ekf_launch_pdl(large_downdate_tma<2, false, STAGES>, grid, kThreadsTma, bytes, s, q, *m);
 }
 
 cudaError_t ekf_large_tma_downdate(const EkfLargeTmaArgs& t, const void* map, int grid, bool compass, cudaStream_t s) {
@@ -226,8 +238,6 @@ cudaError_t ekf_large_tma_downdate(const EkfLargeTmaArgs& t, const void* map, in
   q.reverse = t.reverse;
   q.c0 = t.c0; q.c1 = t.c1 > t.c0 ? t.c1 : 0x7fffffff;
   q.early_trigger = !t.no_early_trigger;
-  const size_t bytes = (size_t)STAGES * kTileBytes + 2 * STAGES * sizeof(uint64_t);
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(map);
-  if (compass) return ekf_launch_pdl(large_downdate_tma<1, true>, grid, kThreadsTma, bytes, s, q, *m);
-  return ekf_launch_pdl(large_downdate_tma<2, false>, grid, kThreadsTma, bytes, s, q, *m);
+  return t.slim ? tma_launch<kStagesSlim>(q, m, grid, compass, s) : tma_launch<kStagesWide>(q, m, grid, compass, s);
 }

@@ -1174,8 +1174,8 @@ void run_shard_thread_la(RunCtx& c, int s) {
   bool timed = false;
   auto sweep = [&](const ShardArgs& a, bool compass) {
     if (m->use_tma) {
-      EkfLargeTmaArgs q{&a.sm->decision, &a.sm->n, &a.sm->m0, &a.sm->m1, a.W, nullptr, &a.sm->n_lm, 0, sh.c0, sh.c1, 1};
-      if (compass) q = EkfLargeTmaArgs{nullptr, &a.sm->n, &a.sm->cm0, &a.sm->cm0, a.W, nullptr, nullptr, 0, sh.c0, sh.c1, 1};
+      EkfLargeTmaArgs q{&a.sm->decision, &a.sm->n, &a.sm->m0, &a.sm->m1, a.W, nullptr, &a.sm->n_lm, 0, sh.c0, sh.c1, 1, 1};
+      if (compass) q = EkfLargeTmaArgs{nullptr, &a.sm->n, &a.sm->cm0, &a.sm->cm0, a.W, nullptr, nullptr, 0, sh.c0, sh.c1, 1, 1};
       TH_CK(ekf_large_tma_downdate(q, sh.tmap.data(), sh.tma_grid, compass, A));
     } else if (compass) {
       ekf_launch_pdl(shard_downdate<1, true>, sh.grid, kThreads, 0, A, a);
@@ -1363,13 +1363,10 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
     SH_ALLOC(sh.flags, (2 * kMaxShards + 1) * sizeof(unsigned));
     if (m->use_tma) {
       sh.tmap.resize(ekf_large_tma_map_bytes());
-      if (ekf_large_tma_prepare(sh.sms, &sh.tma_grid) != cudaSuccess ||
+      if (ekf_large_tma_prepare(sh.sms, &sh.tma_grid, true) != cudaSuccess ||
           ekf_large_tma_encode(sh.tmap.data(), sh.P, sh.c1 - sh.c0, m->ld) != cudaSuccess)
         return bail(EKF_ERR_CUDA, "the tensor map of the TMA-staged covariance sweep could not be encoded "
                                   "(set EKF_LARGE_TMA=0 to run the plain double2 sweep instead)");
-      // Two CTAs per SM, not three: measured, the sweep is no slower (HBM-bound either way), and with three the
-      // side stream's kernels are not scheduled until two thirds of the sweep are over (profiles/r02_shard_timeline.txt)
-      if (sh.tma_grid > 2 * sh.sms) sh.tma_grid = 2 * sh.sms;
     }
     {
       int lo = 0, hi = 0;
