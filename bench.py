@@ -534,6 +534,30 @@ def main():
     e2e_s = max_over_ranks(dist, local, e2e_s)
     clocks = sampler.stop()
     e2e_val = world * F * T_LAP * args.steps / e2e_s
+    # what the host side of this box can deliver: the same pinned records copied host -> device and nothing
+    # else, on every rank at the same time (the end-to-end lap cannot be shorter than this copy)
+    barrier(dist, local)
+    h2d_only_ms = -1.0
+    try:                                                # local work only inside the try: the collectives below always run
+        import torch
+        with torch.cuda.device(local):
+            src = torch.from_numpy(rec.reshape(-1))
+            dst = torch.empty(src.numel(), dtype=src.dtype, device="cuda:%d" % local)
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(local)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize(local)
+            h2d_only_ms = e0.elapsed_time(e1) / 3
+            del dst
+    except Exception:                                   # noqa: BLE001  an extra, never fatal
+        h2d_only_ms = -1.0
+    h2d_only_ms = max_over_ranks(dist, local, h2d_only_ms)
+    if h2d_only_ms <= 0:
+        h2d_only_ms = None
     h2d = int(rec.nbytes)
     d2h = fb.output_bytes(outs)
     # dropped New associations over ALL timed laps (device-resident and end-to-end) and ALL ranks
@@ -595,6 +619,10 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "h2d_gbs_per_rank": h2d / (e2e_s / args.steps) / 1e9, "d2h_gbs_per_rank": d2h / (e2e_s / args.steps) / 1e9,
+                    "h2d_only_ms": h2d_only_ms,
+                    "h2d_only_gbs_per_rank": (h2d / (h2d_only_ms * 1e-3) / 1e9) if h2d_only_ms else None,
+                    "h2d_only_note": "this rank's records copied host -> device with nothing else running, all ranks at "
+                                     "once (max over ranks): the floor the host side of the box sets for an end-to-end lap",
                     "note": "per rank: pinned H2D of the step records and D2H of the decisions, pipelined over chunks of filters "
                             "with the kernel (three streams); the byte counts are this rank's"},
             "gpu_launches": int(l1 - l0), "clocks": clocks, "roofline": roofline}
