@@ -805,23 +805,34 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
   const size_t wave = (size_t)(kern == 4 ? ekf_dtile_ctas_per_sm() * h->sm_count
                                : kern == 3 ? ekf_stile_ctas_per_sm(h->cfg.batch_kernel == EKF_BATCH_KERNEL_AUTO ? 1 : st.cap_lm) * h->sm_count
                                            : (kern == 2 ? 2 * h->sm_count : h->grid_cap));
-  // Chunk sizes in waves: 1, 1, 2, 2, 4, 4, 8, 8, 8, ... - the first copy (nothing to overlap it with) is
-  // short, later chunks are long enough to amortise their launch and the tail of their last wave.
+  // Chunk sizes in waves: 1, 1, 2, 2, 4, 4, 8, 8, ... 8, 8, 4, 4, 2, 2, 1, 1 - the first copy in (nothing to
+  // overlap it with) and the last copy out (nothing left to hide it behind) are short, the chunks between are
+  // long enough to amortise their launch and the tail of their last wave.
   size_t begin[kMaxChunks + 1];
   int n_chunks = 0;
   {
+    const size_t waves = (F + wave - 1) / wave;
     size_t cap_waves = 8;
     for (;;) {
-      size_t f = 0, w = 1;
-      n_chunks = 0;
-      bool twice = false;
-      while (f < F && n_chunks < kMaxChunks) {
-        begin[n_chunks++] = f;
-        f += w * wave;
-        if (twice && w < cap_waves) w *= 2;
-        twice = !twice;
+      // ramp sizes up from both ends towards the middle
+      size_t front[kMaxChunks], back[kMaxChunks];
+      int nf = 0, nb = 0;
+      size_t left = waves, w = 1;
+      bool twice = false, at_front = true;
+      while (left > 0 && nf + nb < kMaxChunks) {
+        const size_t take = w < left ? w : left;
+        if (at_front) front[nf++] = take; else back[nb++] = take;
+        left -= take;
+        if (!at_front) { if (twice && w < cap_waves) w *= 2; twice = !twice; }
+        at_front = !at_front;
       }
-      if (f >= F) break;
+      if (left == 0) {
+        size_t f = 0;
+        n_chunks = 0;
+        for (int c = 0; c < nf; ++c) { begin[n_chunks++] = f; f += front[c] * wave; }
+        for (int c = nb - 1; c >= 0; --c) { begin[n_chunks++] = f; f += back[c] * wave; }
+        break;
+      }
       cap_waves *= 2;                                          // too many chunks for the event ring: longer ones
     }
     begin[n_chunks] = F;
