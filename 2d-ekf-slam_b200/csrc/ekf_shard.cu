@@ -115,6 +115,7 @@ struct ShardArgs {
   unsigned* gain_count;
   unsigned* flags_d_all[kMaxShards];
   unsigned* flags_g_all[kMaxShards];
+  unsigned long long poll_ns;   // how long a poll waits before it gives up (2 s; EKF_SHARD_POLL_MS overrides)
 };
 
 __device__ __forceinline__ double* scol(const ShardArgs& a, int j) { return a.P + (size_t)(j - a.c0) * a.ld; }
@@ -510,12 +511,18 @@ __device__ __forceinline__ unsigned long long shard_now_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void shard_poll(const unsigned* flags, int lo, int hi, unsigned want, int* status) {
+// dbg: four words behind the last-CTA counter; the first poll that gives up leaves {site, wanted count, whose
+// flag, value seen} there for the error message.
+__device__ __forceinline__ void shard_poll(const unsigned* flags, int lo, int hi, unsigned want, int* status, unsigned* dbg,
+                                           unsigned site, unsigned long long limit_ns) {
   const unsigned long long t0 = shard_now_ns();
   for (int t = lo; t < hi; ++t) {
     const volatile unsigned* f = flags + t;
     while (*f < want) {
-      if (shard_now_ns() - t0 > 2000000000ull) { atomicOr(status, 2); break; }
+      if (shard_now_ns() - t0 > limit_ns) {
+        if ((atomicOr(status, 2) & 2) == 0) { dbg[0] = site; dbg[1] = want; dbg[2] = (unsigned)t; dbg[3] = *f; }
+        break;
+      }
     }
   }
   __threadfence_system();
@@ -536,7 +543,7 @@ __device__ __forceinline__ void shard_signal_last(const ShardArgs& a, unsigned* 
 // One warp that waits for flag words [lo, hi) (side stream, and the main stream between gain and sweep).
 __global__ void shard_poll_kernel(const ShardArgs a, int which, int lo, int hi, unsigned want) {
   ekf_pdl_wait();          // dependents are released by the exit, i.e. after the poll (ekf_pdl.cuh)
-  if (threadIdx.x == 0) shard_poll(which ? a.flags_g : a.flags_d, lo, hi, want, a.status);
+  if (threadIdx.x == 0) shard_poll(which ? a.flags_g : a.flags_d, lo, hi, want, a.status, a.gain_count + 1, 10 + which, a.poll_ns);
 }
 
 // Start of a run: every shard stores the cache entries of its own columns into every shard's cache.
@@ -740,7 +747,7 @@ __global__ void __launch_bounds__(kThreads) shard_decide_la(const ShardArgs a, c
 // Opt_i part from the shard's own column i (rows Opt_i, Opt_i+1 - swept, never stale).
 __global__ void __launch_bounds__(kThreads) shard_gain_la(const ShardArgs a, unsigned done) {
   ekf_pdl_wait();
-  if (threadIdx.x == 0) shard_poll(a.flags_d, 0, a.n_shards, done, a.status);   // every shard's decision is made
+  if (threadIdx.x == 0) shard_poll(a.flags_d, 0, a.n_shards, done, a.status, a.gain_count + 1, 1, a.poll_ns);   // every shard's decision is made
   __syncthreads();
   const ShardSmall* sm = a.sm;
   const int decision = sm->decision;
@@ -831,7 +838,7 @@ __global__ void shard_compass_setup_la(const ShardArgs a, const double* zR, unsi
 // Compass gain: every input is in the replicated cache, every shard computes all rows - no exchange.
 __global__ void __launch_bounds__(kThreads) shard_compass_gain_la(const ShardArgs a, unsigned done) {
   ekf_pdl_wait();          // no early trigger: the sweep behind must not occupy the device while this spins
-  if (threadIdx.x == 0) shard_poll(a.flags_d, a.shard, a.shard + 1, done, a.status);
+  if (threadIdx.x == 0) shard_poll(a.flags_d, a.shard, a.shard + 1, done, a.status, a.gain_count + 1, 2, a.poll_ns);
   __syncthreads();
   const ShardSmall* sm = a.sm;
   const LaCache c = shard_cache(a);
@@ -1155,7 +1162,7 @@ void run_shard_thread_la(RunCtx& c, int s) {
     ++xk;
   };
   TH_CK(cudaSetDevice(sh.device));
-  TH_CK(cudaMemsetAsync(sh.flags, 0, (2 * kMaxShards + 1) * sizeof(unsigned), A));
+  TH_CK(cudaMemsetAsync(sh.flags, 0, (2 * kMaxShards + 8) * sizeof(unsigned), A));
   xchg();                                   // uploads and resets of every shard precede the first peer store
   if (s == 0) TH_CK(cudaEventRecord(m->t0, A));
   const int n_all = m->cap_n, lm_all = m->cap_lm;
@@ -1320,6 +1327,14 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
     m->lookahead = env ? (atoi(env) != 0) : 1;
     env = getenv("EKF_LARGE_TMA");
     m->use_tma = env ? (atoi(env) != 0) : 1;
+    // The look-ahead run couples the shards through flags that kernels poll, which needs the kernels of
+    // different shards to make progress independently of each other. Shards on their own GPUs do. Shards
+    // that share a device (a convenience for testing the exchange logic on one GPU) do not reliably: late in
+    // long runs a shard's side stream stopped being scheduled while another shard's kernel polled
+    // (profiles/dbg_cap.py 6 0,0,0 - never with one shard per device), so they run the event chain.
+    for (int s = 0; s < n_shards; ++s)
+      for (int t = 0; t < s; ++t)
+        if (devices[s] == devices[t]) m->lookahead = 0;
   }
   auto bail = [&](int code, const std::string& msg) {
     g_shard_create_error = msg;
@@ -1360,7 +1375,7 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
     SH_ALLOC(sh.W2, m->w_count * sizeof(double2));
     SH_ALLOC(sh.strip, 3 * (size_t)m->lds * sizeof(double));
     SH_ALLOC(sh.diag, 4 * ((size_t)max_landmarks + 1) * sizeof(double));
-    SH_ALLOC(sh.flags, (2 * kMaxShards + 1) * sizeof(unsigned));
+    SH_ALLOC(sh.flags, (2 * kMaxShards + 8) * sizeof(unsigned));
     if (m->use_tma) {
       sh.tmap.resize(ekf_large_tma_map_bytes());
       if (ekf_large_tma_prepare(sh.sms, &sh.tma_grid, true) != cudaSuccess ||
@@ -1404,6 +1419,10 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
     a.k = m->k;
     a.strip = sh.strip; a.diag = sh.diag; a.lds = m->lds; a.la = 0;
     a.flags_d = sh.flags; a.flags_g = sh.flags + kMaxShards; a.gain_count = sh.flags + 2 * kMaxShards;
+    {
+      const char* env = getenv("EKF_SHARD_POLL_MS");
+      a.poll_ns = (env && atoll(env) > 0 ? (unsigned long long)atoll(env) : 2000ull) * 1000000ull;
+    }
     for (int t = 0; t < kMaxShards; ++t) {
       const Shard& o = m->sh[t < n_shards ? t : 0];
       a.strip_all[t] = o.strip; a.diag_all[t] = o.diag;
@@ -1692,7 +1711,13 @@ int ekf_sharded_run(ekf_sharded m, int n_steps, int max_meas, const double* reco
     int st = 0;
     SH_CK(m, cudaSetDevice(m->sh[s].device));
     SH_CK(m, cudaMemcpy(&st, m->sh[s].status, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st & 2) return sfail(m, EKF_ERR_CUDA, "ekf_sharded_run: shard " + std::to_string(s) + " gave up waiting for a peer (exchange flag not set within 2 s); the map state is undefined");
+    if (st & 2) {
+      unsigned dbg[4] = {0, 0, 0, 0};
+      cudaMemcpy(dbg, m->sh[s].flags + 2 * kMaxShards + 1, sizeof(dbg), cudaMemcpyDeviceToHost);
+      return sfail(m, EKF_ERR_CUDA, "ekf_sharded_run: shard " + std::to_string(s) + " gave up waiting for a peer (exchange flag not set within 2 s: wait site " +
+                   std::to_string(dbg[0]) + ", operation " + std::to_string(dbg[1]) + ", flag of shard " + std::to_string(dbg[2]) + " was " + std::to_string(dbg[3]) +
+                   "); the map state is undefined");
+    }
   }
   SH_CK(m, cudaSetDevice(s0.device));
   SH_CK(m, cudaEventElapsedTime(&m->last_ms, m->t0, m->t1));

@@ -237,8 +237,8 @@ int ekf_sharded_update_compass(ekf_sharded m, double z, double R);
  * propagate / gating / decision of the next operation with the covariance sweep of the current one
  * (a replicated O(n) cache on a side stream per shard, exchange steps as flags in peer memory, the
  * TMA-staged sweep); EKF_SHARD_LOOKAHEAD=0 in the environment at ekf_sharded_create() selects the chain
- * with an event exchange per gating pass and per gain (also what the per-call functions above run). Same
- * results either way. */
+ * with an event exchange per gating pass and per gain (also what the per-call functions above run, and
+ * what a map runs whose shards share a device - flags need one GPU per shard). Same results either way. */
 int ekf_sharded_run(ekf_sharded m, int n_steps, int max_meas, const double* records, const ekf_run_outputs* out);
 /* How ekf_sharded_run sweeps the covariance: 2 = look-ahead run with the TMA-staged sweep, 1 = look-ahead
  * run with the plain double2 sweep (EKF_LARGE_TMA=0), 0 = event chain with the plain sweep. */

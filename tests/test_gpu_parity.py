@@ -194,6 +194,34 @@ def test_large_regime_lookahead_is_bit_identical_to_the_single_stream_chain(ekf,
     assert rel_state(a["pose_trace"], want["pose_trace"]) <= TOL
 
 
+@pytest.mark.parametrize("knob", ["EKF_LARGE_LOOKAHEAD", "EKF_LARGE_SNAKE"])
+def test_large_regime_capacity_and_switches(ekf, oracle, knob, monkeypatch):
+    """Regime B with a map that wants more landmarks than the handle holds (dropped New associations are
+    reported and nothing else changes), with each of the two run-time switches of the fused large-map run
+    on and off: same trace as the oracle, identical bits between the two settings."""
+    N, F, T, cap, M = 14, 2, 160, 11, 2
+    rec = ekf.Synth(N, steps_per_lap=T, max_meas=M, compass_every=6).generate(F, T)
+    want = oracle.run_batch(rec, M, cap, pose_trace=True, final_state=True)
+    assert (want["decision"] == 3).any()
+    res = []
+    for v in ("1", "0"):
+        monkeypatch.setenv(knob, v)
+        fb = ekf.FilterBatch(F, cap, regime=2)
+        got = fb.run(rec, M, trace=True, pose_trace=True, allow_capacity=True)
+        assert fb.capacity_flags(clear=False) == F
+        sts = _final_states(fb, F)
+        fb.close()
+        assert_trace_equal(got, want, "%s=%s" % (knob, v))
+        assert np.array_equal(got["final_nlm"], want["final_nlm"])
+        for f, ((x, P), (xr, Pr)) in enumerate(zip(sts, _oracle_states(want, F))):
+            assert_state_close(x, P, xr, Pr, "%s=%s filter %d" % (knob, v, f))
+        res.append((got, sts))
+    for k in ("decision", "index", "mahal", "pose_trace"):
+        assert np.array_equal(res[0][0][k], res[1][0][k]), k
+    for (xa, Pa), (xb, Pb) in zip(res[0][1], res[1][1]):
+        assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
+
+
 @pytest.mark.parametrize("N,steps", [(300, 40), (2000, 4)])
 def test_large_map_injected_state(ekf, oracle, N, steps):
     """BASELINE config 4 shape: state injected, then Old-updates streamed from HBM."""

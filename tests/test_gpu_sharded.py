@@ -91,6 +91,8 @@ def test_sharded_lookahead_run_is_bit_identical_to_the_exchange_per_gating_chain
         for la in ("0", "1"):
             monkeypatch.setenv("EKF_SHARD_LOOKAHEAD", la)
             sm = ekf.ShardedMap(devs, cap)
+            # flags need one GPU per shard: device lists with repeats run the event chain whatever the switch says
+            assert ("look-ahead" in sm.run_mode()) == (la == "1" and len(set(devs)) == len(devs))
             parts, lo = [], 0
             for hi in (1, 10, 250, 2 * T):
                 parts.append(sm.run(np.ascontiguousarray(rec[:, lo:hi]), M, trace=True, pose_trace=True))
@@ -116,6 +118,35 @@ def test_sharded_lookahead_run_is_bit_identical_to_the_exchange_per_gating_chain
                 assert np.array_equal(got[k], ref[0][k]), what + ": " + k
             for u, v in zip(cur[1:], ref[1:]):
                 assert np.array_equal(u, v), what
+
+
+def test_sharded_run_reports_capacity_in_both_run_modes(ekf, oracle, monkeypatch):
+    """A run whose map wants more landmarks than the handle holds: the New associations that do not fit are
+    dropped (decision 3, index -1), the call returns EKF_ERR_CAPACITY, everything else goes on - the same
+    trace and the same state from the look-ahead run, the event chain and the oracle."""
+    N, T, cap, M = 14, 160, 11, 2
+    syn = ekf.Synth(N, steps_per_lap=T, max_meas=M, compass_every=6)
+    rec = syn.generate(1, T)
+    want = oracle.run_batch(rec, M, cap, pose_trace=True, final_state=True)
+    assert (want["decision"] == 3).any() and int(want["final_nlm"][0]) == cap
+    n = 3 + 2 * cap
+    res = []
+    for devs in _device_lists(ekf):
+        for la in ("1", "0"):
+            monkeypatch.setenv("EKF_SHARD_LOOKAHEAD", la)
+            sm = ekf.ShardedMap(devs, cap)
+            got = sm.run(rec, M, trace=True, pose_trace=True, allow_capacity=True)
+            x, P = sm.get_state()
+            sm.close()
+            what = "devices %s, look-ahead %s" % (devs, la)
+            assert_trace_equal(got, want, what)
+            assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL
+            assert_state_close(x, P, want["final_x"][0, :n], want["final_P"][0, :n, :n].T, what)
+            res.append((got, x, P))
+    for got, x, P in res[1:]:
+        for k in ("decision", "index", "mahal", "pose_trace"):
+            assert np.array_equal(got[k], res[0][0][k]), k
+        assert np.array_equal(x, res[0][1]) and np.array_equal(P, res[0][2])
 
 
 def test_sharded_percall_surface(ekf, oracle):
