@@ -211,7 +211,9 @@ def test_large_regime_capacity_and_switches(ekf, oracle, knob, monkeypatch):
         assert fb.capacity_flags(clear=False) == F
         sts = _final_states(fb, F)
         fb.close()
-        assert_trace_equal(got, want, "%s=%s" % (knob, v))
+        keep = want["decision"] != 3      # the oracle harness reports 0 as the distance of a dropped association
+        assert np.array_equal(got["decision"], want["decision"]) and np.array_equal(got["index"], want["index"])
+        assert (np.abs(got["mahal"][keep] - want["mahal"][keep]) <= TOL * np.maximum(1.0, np.abs(want["mahal"][keep]))).all()
         assert np.array_equal(got["final_nlm"], want["final_nlm"])
         for f, ((x, P), (xr, Pr)) in enumerate(zip(sts, _oracle_states(want, F))):
             assert_state_close(x, P, xr, Pr, "%s=%s filter %d" % (knob, v, f))

@@ -120,6 +120,15 @@ def test_sharded_lookahead_run_is_bit_identical_to_the_exchange_per_gating_chain
                 assert np.array_equal(u, v), what
 
 
+def _assert_trace_equal_but_dropped(got, want, what):
+    """assert_trace_equal, except that the Mahalanobis distance of a dropped association is not compared: the
+    reference has no such case (its map grows without bound) and the oracle harness reports 0 there."""
+    keep = want["decision"] != 3
+    assert np.array_equal(got["decision"], want["decision"]) and np.array_equal(got["index"], want["index"]), what
+    m, mr = got["mahal"][keep], want["mahal"][keep]
+    assert (np.abs(m - mr) <= TOL * np.maximum(1.0, np.abs(mr))).all(), what + ": Mahalanobis distances differ"
+
+
 def test_sharded_run_reports_capacity_in_both_run_modes(ekf, oracle, monkeypatch):
     """A run whose map wants more landmarks than the handle holds: the New associations that do not fit are
     dropped (decision 3, index -1), the call returns EKF_ERR_CAPACITY, everything else goes on - the same
@@ -139,7 +148,7 @@ def test_sharded_run_reports_capacity_in_both_run_modes(ekf, oracle, monkeypatch
             x, P = sm.get_state()
             sm.close()
             what = "devices %s, look-ahead %s" % (devs, la)
-            assert_trace_equal(got, want, what)
+            _assert_trace_equal_but_dropped(got, want, what)
             assert rel_state(got["pose_trace"], want["pose_trace"]) <= TOL
             assert_state_close(x, P, want["final_x"][0, :n], want["final_P"][0, :n, :n].T, what)
             res.append((got, x, P))
