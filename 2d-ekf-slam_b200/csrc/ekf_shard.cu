@@ -23,15 +23,17 @@
 //       downdate  the HBM-bound sweep over the own columns only: 16 n^2 / G bytes per shard
 //   doUpdateCompass (kalmanfilter.cpp:96-130): setup, exchange, gain (stores into peers),
 //       exchange, rank-1 downdate.
-// An exchange step is stream-ordered: every shard records an event after its producer kernel and
-// every other shard's stream waits on it; no kernel ever spins on a peer.
+// An exchange step of this chain (the per-call functions, runs with EKF_SHARD_LOOKAHEAD=0 or with shards
+// that share a device) is stream-ordered: every shard records an event after its producer kernel and
+// every other shard's stream waits on it; no kernel spins on a peer.
 //
 // ekf_sharded_run additionally overlaps the O(n) chain with the sweep (look-ahead, ekf_la.cuh): every
 // shard keeps a full replica of the O(n) cache (robot columns + diagonal blocks), so gating and the
 // decision need NO exchange at all and run on a side stream while the sweep of the previous operation is
 // still streaming the shard's slab; what stays between two sweeps is the gain kernel (own rows, peer
-// stores of W and x) and its exchange. Compass updates need no exchange either (every input is in the
-// cache). See run_shard_thread_la.
+// stores of W and x) and its exchange - flags in peer memory that one-warp kernels poll (bounded), one GPU
+// per shard required. Compass updates need no exchange either (every input is in the cache). See
+// run_shard_thread_la.
 //
 // Arithmetic is ekf_small.cuh (the reference's operation order) and the bit-symmetric two-fma
 // downdate of ekf_cta.cuh, i.e. results are bit-identical to the single-GPU regime B and
