@@ -633,7 +633,7 @@ def main():
         legs = []
         for tok in args.large_map.split(","):
             n_lm = int(tok)
-            steps = 10000 if n_lm <= 2000 else 30      # BASELINE configs[3]: 10,000 update steps
+            steps = 10000 if n_lm <= 2000 else 100     # BASELINE configs[3]: 10,000 update steps
             legs.append(large_map_leg(ekf, n_lm, steps, hbm_peak, local, verify_steps=4 if n_lm <= 2000 else 2))
         line["large_map"] = legs
         line["roofline_hbm"] = dict(legs[-1]["roofline"], peak_source=hbm_src)
