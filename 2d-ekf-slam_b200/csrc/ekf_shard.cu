@@ -1378,6 +1378,18 @@ int ekf_sharded_create(ekf_sharded* out, int n_shards, const int* devices, int m
     SH_ALLOC(sh.strip, 3 * (size_t)m->lds * sizeof(double));
     SH_ALLOC(sh.diag, 4 * ((size_t)max_landmarks + 1) * sizeof(double));
     SH_ALLOC(sh.flags, (2 * kMaxShards + 8) * sizeof(unsigned));
+    {
+      // Load every kernel of the look-ahead run now (CUDA loads a kernel lazily at its first launch, and that
+      // load may have to wait for kernels that are running): no first launch happens while a kernel polls.
+      cudaFuncAttributes fa;
+      const void* kernels[] = {(const void*)shard_poll_kernel, (const void*)shard_la_load, (const void*)shard_la_store,
+                               (const void*)shard_prop_setup_la, (const void*)shard_prop_strip_la, (const void*)shard_gate_la,
+                               (const void*)shard_decide_la, (const void*)shard_gain_la, (const void*)shard_cache_update,
+                               (const void*)shard_compass_setup_la, (const void*)shard_compass_gain_la,
+                               (const void*)shard_downdate<2, false>, (const void*)shard_downdate<1, true>};
+      for (const void* kf : kernels)
+        if ((e = cudaFuncGetAttributes(&fa, kf)) != cudaSuccess) return bail(EKF_ERR_CUDA, cudaGetErrorString(e));
+    }
     if (m->use_tma) {
       sh.tmap.resize(ekf_large_tma_map_bytes());
       if (ekf_large_tma_prepare(sh.sms, &sh.tma_grid, true) != cudaSuccess ||
