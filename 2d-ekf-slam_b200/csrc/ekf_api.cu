@@ -779,6 +779,44 @@ int ekf_download_outputs(ekf_handle h, const ekf_run_outputs* out) {
   return download(h, out);
 }
 
+// Chunk boundaries of the pipelined run. Sizes in waves of co-resident CTAs: 1, 1, 2, 2, 4, 4, 8, 8, ... 8, 8, 4,
+// 4, 2, 2, 1, 1 - the first copy in (nothing to overlap it with) and the last copy out (nothing left to hide it
+// behind) are short, the chunks between are long enough to amortise their launch and the tail of their last
+// wave. begin[0..n] (n <= kMaxChunks) are filter indices, begin[n] = F; returns n.
+static int pipeline_chunks(size_t F, size_t wave, size_t* begin) {
+  if (wave < 1) wave = 1;
+  const size_t waves = (F + wave - 1) / wave;
+  size_t cap_waves = 8;
+  int n_chunks = 0;
+  for (;;) {
+    size_t front[kMaxChunks], back[kMaxChunks];      // ramp sizes up from both ends towards the middle
+    int nf = 0, nb = 0;
+    size_t left = waves, w = 1;
+    bool twice = false, at_front = true;
+    while (left > 0 && nf + nb < kMaxChunks) {
+      const size_t take = w < left ? w : left;
+      if (at_front) front[nf++] = take; else back[nb++] = take;
+      left -= take;
+      if (!at_front) { if (twice && w < cap_waves) w *= 2; twice = !twice; }
+      at_front = !at_front;
+    }
+    if (left == 0) {
+      size_t f = 0;
+      for (int c = 0; c < nf; ++c) { begin[n_chunks++] = f; f += front[c] * wave; }
+      for (int c = nb - 1; c >= 0; --c) { begin[n_chunks++] = f; f += back[c] * wave; }
+      break;
+    }
+    if (cap_waves >= waves) {                        // more waves than any ramp of kMaxChunks chunks covers: equal chunks
+      const size_t per = (waves + kMaxChunks - 1) / kMaxChunks;
+      for (size_t w0 = 0; w0 < waves; w0 += per) begin[n_chunks++] = w0 * wave;
+      break;
+    }
+    cap_waves *= 2;                                  // too many chunks for the event ring: longer ones
+  }
+  begin[n_chunks] = F;
+  return n_chunks;
+}
+
 // End-to-end run of the batch regime, pipelined over chunks of filters: the H2D copy of chunk c+1
 // and the D2H copy of chunk c-1 overlap the kernel of chunk c (three streams, two copy engines).
 // Filters are independent, so a chunk is just a sub-range of the batch.
@@ -805,38 +843,8 @@ static int run_pipelined(ekf_handle h, int n_steps, int max_meas, const double* 
   const size_t wave = (size_t)(kern == 4 ? ekf_dtile_ctas_per_sm() * h->sm_count
                                : kern == 3 ? ekf_stile_ctas_per_sm(h->cfg.batch_kernel == EKF_BATCH_KERNEL_AUTO ? 1 : st.cap_lm) * h->sm_count
                                            : (kern == 2 ? 2 * h->sm_count : h->grid_cap));
-  // Chunk sizes in waves: 1, 1, 2, 2, 4, 4, 8, 8, ... 8, 8, 4, 4, 2, 2, 1, 1 - the first copy in (nothing to
-  // overlap it with) and the last copy out (nothing left to hide it behind) are short, the chunks between are
-  // long enough to amortise their launch and the tail of their last wave.
   size_t begin[kMaxChunks + 1];
-  int n_chunks = 0;
-  {
-    const size_t waves = (F + wave - 1) / wave;
-    size_t cap_waves = 8;
-    for (;;) {
-      // ramp sizes up from both ends towards the middle
-      size_t front[kMaxChunks], back[kMaxChunks];
-      int nf = 0, nb = 0;
-      size_t left = waves, w = 1;
-      bool twice = false, at_front = true;
-      while (left > 0 && nf + nb < kMaxChunks) {
-        const size_t take = w < left ? w : left;
-        if (at_front) front[nf++] = take; else back[nb++] = take;
-        left -= take;
-        if (!at_front) { if (twice && w < cap_waves) w *= 2; twice = !twice; }
-        at_front = !at_front;
-      }
-      if (left == 0) {
-        size_t f = 0;
-        n_chunks = 0;
-        for (int c = 0; c < nf; ++c) { begin[n_chunks++] = f; f += front[c] * wave; }
-        for (int c = nb - 1; c >= 0; --c) { begin[n_chunks++] = f; f += back[c] * wave; }
-        break;
-      }
-      cap_waves *= 2;                                          // too many chunks for the event ring: longer ones
-    }
-    begin[n_chunks] = F;
-  }
+  const int n_chunks = pipeline_chunks(F, wave, begin);
   EKF_CK(h, cudaEventRecord(h->ev_done, h->stream));          // order after earlier work on the handle
   EKF_CK(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
   for (int c = 0; c < n_chunks; ++c) {
@@ -968,6 +976,14 @@ int ekf_kernel_time(ekf_handle h, float* avg_ms, int* n_launches) {
 
 int ekf_debug_phase_cycles(long long* out8) {
   return ekf_tile_phase_cycles(out8) == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
+}
+
+int ekf_debug_pipeline_chunks(long long n_filters, long long wave, long long* begin, int capacity) {
+  if (n_filters < 1 || wave < 1 || !begin || capacity < kMaxChunks + 1) return -EKF_ERR_BAD_ARG;
+  size_t b[kMaxChunks + 1];
+  const int n = pipeline_chunks((size_t)n_filters, (size_t)wave, b);
+  for (int c = 0; c <= n; ++c) begin[c] = (long long)b[c];
+  return n;
 }
 
 int ekf_debug_dtile_timestamps(long long* out64) {

@@ -201,6 +201,10 @@ int ekf_debug_phase_cycles(long long* out16);
 int ekf_debug_stile_timestamps(long long* out128);
 /* Same for the deferred-downdate kernel (-DEKF_DTILE_TIMING builds): out64 = [4 warps][16 stamps]. */
 int ekf_debug_dtile_timestamps(long long* out64);
+/* Test hook (no GPU needed): the chunk boundaries ekf_run() would use to pipeline n_filters filters when
+ * `wave` filters are co-resident on the device. begin[0..n] with begin[n] = n_filters; capacity >= 49;
+ * returns n (>= 1) or -EKF_ERR_BAD_ARG. */
+int ekf_debug_pipeline_chunks(long long n_filters, long long wave, long long* begin, int capacity);
 
 /* ---- one large map sharded over several GPUs ---------------------------- */
 /* The covariance of ONE map is split by columns over n_shards devices (one process drives them;

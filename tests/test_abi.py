@@ -93,3 +93,31 @@ def test_dropin_header_compiles_against_the_reference_loop_shape():
                         "-Wl,-rpath," + os.path.join(ROOT, "2d-ekf-slam_b200", "lib"), "-o", out],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
+
+
+def test_pipeline_chunk_schedule(ekf):
+    """Host logic of ekf_run(): the filters of a batch are cut into chunks whose sizes, in waves of co-resident
+    CTAs, ramp up from one wave at both ends (short first copy in, short last copy out). No GPU needed."""
+    fn = ekf.core_lib().ekf_debug_pipeline_chunks
+    fn.argtypes = [C.c_longlong, C.c_longlong, C.POINTER(C.c_longlong), C.c_int]
+    buf = (C.c_longlong * 64)()
+    assert fn(0, 592, buf, 64) < 0 and fn(10, 592, buf, 8) < 0
+    for F, wave in [(1, 592), (591, 592), (592, 592), (593, 592), (8192, 592), (65536, 592), (65536, 296),
+                    (10 ** 6, 592), (10 ** 7, 148), (4096, 1184)]:
+        n = fn(F, wave, buf, 64)
+        assert 1 <= n <= 48
+        b = [buf[i] for i in range(n + 1)]
+        assert b[0] == 0 and b[-1] == F and all(x < y for x, y in zip(b, b[1:]))        # a partition of [0, F)
+        sizes = [y - x for x, y in zip(b, b[1:])]
+        assert all(sz % wave == 0 for sz in sizes[:-1])                                 # whole waves, except the last chunk
+        if F // wave > 10000:                                                           # beyond any ramp of 48 chunks: equal chunks
+            assert max(sizes) - min(sizes[:-1]) == 0
+            continue
+        assert sizes[0] <= wave and sizes[-1] <= wave                                   # one wave at both ends
+        w = [-(-sz // wave) for sz in sizes]
+        peak = w.index(max(w))
+        assert all(x <= y for x, y in zip(w[:peak], w[1:peak + 1]))                     # ramps up ...
+        last = len(w) - 1 - w[::-1].index(max(w))
+        assert all(x >= y for x, y in zip(w[last:], w[last + 1:]))                      # ... and down again
+    n = fn(8192, 592, buf, 64)
+    assert [buf[i + 1] - buf[i] for i in range(n)] == [592, 592, 1184, 1184, 1184, 1184, 1184, 592, 496]
